@@ -1,0 +1,183 @@
+"""ctypes access to oracle/ (test infrastructure; never imported by the product package).
+
+liboracle.so        : the C restatement (oracle/pikg_oracle.c), built on demand with gcc.
+_ref/libgplum_ref_* : the reference's own functors compiled from /root/reference (prebuilt;
+                      rebuilt here only when the reference tree is present).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gplum_b200 import structs as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(HERE), "oracle")
+
+ORDER_DSL, RANK_SQ, TRACE_FALLBACK = 1, 2, 4
+CANONICAL = 0            # ORDER_FALLBACK | RANK_ABS | TRACE_DSL
+AS_SHIPPED = TRACE_FALLBACK   # what the unmodified compiled reference computes
+
+_vp, _i, _f, _ip, _lp = C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_longlong)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    src = os.path.join(ORACLE_DIR, "pikg_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        lib = C.CDLL(build_oracle())
+        lib.oracle_epep.argtypes = [_vp, _i, _vp, _i, _vp, _f, _i]
+        lib.oracle_epsp_quad.argtypes = [_vp, _i, _vp, _i, _vp, _f, _i]
+        lib.oracle_epsp_mono.argtypes = [_vp, _i, _vp, _i, _vp, _f, _i]
+        lib.oracle_force_clear.argtypes = [_vp, _i]
+        lib.oracle_calc_walks.restype = C.c_longlong
+        lib.oracle_calc_walks.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _f, _i, _i, _i, _i]
+        _oracle = lib
+    return _oracle
+
+
+def have_ref(kind="scalar"):
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libgplum_ref_%s.so" % kind))
+
+
+_ref = {}
+
+
+def ref(kind="scalar"):
+    if kind not in _ref:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libgplum_ref_%s.so" % kind))
+        lib.ref_epep.argtypes = [_vp, _i, _vp, _i, _vp, _f]
+        lib.ref_epsp.argtypes = [_vp, _i, _vp, _i, _vp, _f]
+        lib.ref_force_clear.argtypes = [_vp, _i]
+        lib.ref_layout.argtypes = [_vp]
+        lib.ref_calc_walks.restype = C.c_longlong
+        lib.ref_calc_walks.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _f, _i, _i]
+        lib.ref_tree_build.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _f]
+        lib.ref_tree_sizes.argtypes = [_vp]
+        lib.ref_tree_copy.argtypes = [_vp] * 12
+        _ref[kind] = lib
+    return _ref[kind]
+
+
+# ------------------------------------------------------------------ single functor calls
+def epep(epi, epj, eps2, flags=CANONICAL, force=None, lib="oracle"):
+    f = S.cleared_force(len(epi)) if force is None else force.copy()
+    epi = np.ascontiguousarray(epi); epj = np.ascontiguousarray(epj)
+    if lib == "oracle":
+        oracle().oracle_epep(_ptr(epi), len(epi), _ptr(epj), len(epj), _ptr(f), eps2, flags)
+    else:
+        ref(lib).ref_epep(_ptr(epi), len(epi), _ptr(epj), len(epj), _ptr(f), eps2)
+    return f
+
+
+def epsp(epi, spj, eps2, flags=CANONICAL, force=None, lib="oracle"):
+    f = S.cleared_force(len(epi)) if force is None else force.copy()
+    epi = np.ascontiguousarray(epi); spj = np.ascontiguousarray(spj)
+    quad = spj.dtype.itemsize == 80
+    if lib == "oracle":
+        fn = oracle().oracle_epsp_quad if quad else oracle().oracle_epsp_mono
+        fn(_ptr(epi), len(epi), _ptr(spj), len(spj), _ptr(f), eps2, flags)
+    else:
+        assert quad
+        ref(lib).ref_epsp(_ptr(epi), len(epi), _ptr(spj), len(spj), _ptr(f), eps2)
+    return f
+
+
+# ------------------------------------------------------------------ batched walks
+class Walks:
+    """One FDPS force pass in index form: i-groups + index lists into epj_all / spj_all."""
+
+    def __init__(self, epi, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, epj_all, spj_all):
+        self.epi = np.ascontiguousarray(epi, dtype=S.EPI)
+        self.epi_off = np.ascontiguousarray(epi_off, dtype=np.int32)
+        self.ni = np.ascontiguousarray(ni, dtype=np.int32)
+        self.adr_epj = np.ascontiguousarray(adr_epj, dtype=np.int32)
+        self.epj_disp = np.ascontiguousarray(epj_disp, dtype=np.int64)
+        self.n_epj = np.ascontiguousarray(n_epj, dtype=np.int32)
+        self.adr_spj = np.ascontiguousarray(adr_spj, dtype=np.int32)
+        self.spj_disp = np.ascontiguousarray(spj_disp, dtype=np.int64)
+        self.n_spj = np.ascontiguousarray(n_spj, dtype=np.int32)
+        self.epj_all = np.ascontiguousarray(epj_all, dtype=S.EPJ)
+        self.spj_all = np.ascontiguousarray(spj_all)
+
+    @property
+    def n_walk(self):
+        return len(self.ni)
+
+    @property
+    def quad(self):
+        return self.spj_all.dtype.itemsize == 80
+
+    def n_interactions(self):
+        ni = self.ni.astype(np.int64)
+        return int((ni * self.n_epj).sum()), int((ni * self.n_spj).sum())
+
+    def save(self, path):
+        np.savez_compressed(path, **{k: getattr(self, k) for k in
+                                     ("epi", "epi_off", "ni", "adr_epj", "epj_disp", "n_epj", "adr_spj",
+                                      "spj_disp", "n_spj", "epj_all", "spj_all")})
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        return cls(*[z[k] for k in ("epi", "epi_off", "ni", "adr_epj", "epj_disp", "n_epj", "adr_spj",
+                                    "spj_disp", "n_spj", "epj_all", "spj_all")])
+
+
+def calc_walks(w, eps2, flags=CANONICAL, lib="oracle", n_threads=0, clear=True, force=None):
+    f = S.cleared_force(len(w.epi)) if force is None else force.copy()
+    args = [w.n_walk, _ptr(w.epi), _ptr(w.epi_off), _ptr(w.ni), _ptr(w.adr_epj), _ptr(w.epj_disp),
+            _ptr(w.n_epj), _ptr(w.adr_spj), _ptr(w.spj_disp), _ptr(w.n_spj), _ptr(w.epj_all),
+            _ptr(w.spj_all), _ptr(f), eps2]
+    if lib == "oracle":
+        n = oracle().oracle_calc_walks(*args, int(w.quad), flags, int(clear), n_threads)
+    else:
+        assert w.quad
+        n = ref(lib).ref_calc_walks(*args, int(clear), n_threads)
+    return f, n
+
+
+def ref_tree_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=64,
+                   n_walk_limit=200, eps2=0.0, vel=None, kind="scalar", with_force=False):
+    """Interaction lists produced by the reference's own FDPS tree (multi-walk-index interface)."""
+    lib = ref(kind)
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n = len(pos)
+    mass = np.ascontiguousarray(mass, dtype=np.float64)
+    r_out = np.ascontiguousarray(r_out, dtype=np.float64)
+    r_search = np.ascontiguousarray(r_search, dtype=np.float64)
+    velp = None if vel is None else _ptr(np.ascontiguousarray(vel, dtype=np.float64))
+    nw = lib.ref_tree_build(n, _ptr(pos), velp, _ptr(mass), _ptr(r_out), _ptr(r_search), theta,
+                            n_leaf_limit, n_group_limit, n_walk_limit, eps2)
+    sz = np.zeros(8, dtype=np.int64)
+    lib.ref_tree_sizes(_ptr(sz))
+    assert sz[0] == nw
+    epi = np.zeros(sz[1], dtype=S.EPI)
+    epi_off = np.zeros(nw, dtype=np.int32); ni = np.zeros(nw, dtype=np.int32)
+    adr_epj = np.zeros(sz[2], dtype=np.int32); epj_disp = np.zeros(nw, dtype=np.int64)
+    n_epj = np.zeros(nw, dtype=np.int32)
+    adr_spj = np.zeros(sz[3], dtype=np.int32); spj_disp = np.zeros(nw, dtype=np.int64)
+    n_spj = np.zeros(nw, dtype=np.int32)
+    epj_all = np.zeros(sz[4], dtype=S.EPJ); spj_all = np.zeros(sz[5], dtype=S.SPJ_QUAD)
+    force = np.zeros(sz[1], dtype=S.FORCE)
+    lib.ref_tree_copy(_ptr(epi), _ptr(epi_off), _ptr(ni), _ptr(adr_epj), _ptr(epj_disp), _ptr(n_epj),
+                      _ptr(adr_spj), _ptr(spj_disp), _ptr(n_spj), _ptr(epj_all), _ptr(spj_all), _ptr(force))
+    w = Walks(epi, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, epj_all, spj_all)
+    return (w, force) if with_force else w
