@@ -1,0 +1,64 @@
+"""ctypes binding of libgplum_b200.so (the C ABI in include/gplum_b200.h).
+
+The shared library is the product; this module only loads it.  There is no fallback: if the
+library is missing or no sm_100 device is usable, calls raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgplum_b200.so")
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> (restype, argtypes); every symbol include/gplum_b200.h declares
+SYMBOLS = {
+    "gplum_b200_abi_version": (_i, []),
+    "gplum_b200_last_error": (C.c_char_p, []),
+    "gplum_b200_init": (_i, [_i, C.c_size_t, C.c_size_t]),
+    "gplum_b200_finalize": (_i, []),
+    "gplum_b200_set_params": (_i, [_f, _i, _i]),
+    "gplum_b200_epep": (_i, [_vp, _i, _vp, _i, _vp, _f]),
+    "gplum_b200_epsp": (_i, [_vp, _i, _vp, _i, _vp, _f, _i]),
+    "gplum_b200_dispatch": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i]),
+    "gplum_b200_retrieve": (_i, [_i, _i, _vp, _vp]),
+    "gplum_b200_calc_walks": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i, _vp, _i]),
+    "gplum_b200_walks_upload": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i]),
+    "gplum_b200_walks_run": (_i, [_i]),
+    "gplum_b200_walks_download": (_i, [_vp]),
+    "gplum_b200_walks_time": (_i, [_i, _i, C.POINTER(_f)]),
+    "gplum_b200_walks_set_packed_dev": (_i, [_vp, _i, _vp, _i]),
+    "gplum_b200_pack_epj_dev": (_i, [_vp, _i, _vp]),
+    "gplum_b200_pack_spj_dev": (_i, [_vp, _i, _vp]),
+    "gplum_b200_packed_sizes": (None, [C.POINTER(_i), C.POINTER(_i)]),
+    "gplum_b200_set_stream": (_i, [_vp]),
+    "gplum_b200_synchronize": (_i, []),
+    "gplum_b200_counters": (None, [C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), _i]),
+    "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
+}
+
+_lib = None
+
+
+class GplumB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GplumB200Error("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 "(there is no CPU fallback)" % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise GplumB200Error("libgplum_b200 error %d: %s" % (rc, lib().gplum_b200_last_error().decode()))

@@ -1,0 +1,682 @@
+// gplum_b200.cu -- host side of libgplum_b200.so: the C ABI declared in include/gplum_b200.h.
+//
+// Mirrors what FDPS does around the interaction functors (FDPS/src/tree_for_force_impl_force.hpp
+// :63-266 multi-walk-index, :1404-1589 calcForce/calcForceOnly) with device-resident buffers:
+// j-particles are shipped and packed once per force pass ("send all"), walks arrive as index
+// lists, one kernel launch evaluates every walk of a dispatch, forces come back in one copy.
+// There is no CPU implementation in this library: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gplum_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+using namespace gb;
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(GPLUM_B200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) CU(cudaFree(p));
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) CU(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMallocHost(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// One set of walks resident on the device (a dispatch, a flat pass, or a per-call functor call)
+struct WalkSet {
+    DevBuf epi, epi_off, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, items, force;
+    PinBuf h_force, h_stage;     // pinned: results, flattened inputs of dispatch()
+    int n_walk = 0, n_items = 0;
+    long long n_epi = 0, n_adr_epj = 0, n_adr_spj = 0;
+    long long n_int_epep = 0, n_int_epsp = 0;
+    std::vector<int> ni_host;                    // for retrieve()
+    std::vector<long long> epi_off_host;
+    bool pending = false;
+    void release()
+    {
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force})
+            b->release();
+        h_force.release(); h_stage.release();
+    }
+};
+
+// j-particles of the current force pass
+struct JSet {
+    DevBuf epj_aos, spj_aos, epj_packed, spj_packed;
+    const void *ext_epj = nullptr, *ext_spj = nullptr;   // caller-owned packed arrays (all-gather output)
+    int n_epj = 0, n_spj = 0;
+    const EpjPacked *epj() const { return ext_epj ? (const EpjPacked *)ext_epj : (const EpjPacked *)epj_packed.p; }
+    const SpjPacked *spj() const { return ext_spj ? (const SpjPacked *)ext_spj : (const SpjPacked *)spj_packed.p; }
+    void release() { epj_aos.release(); spj_aos.release(); epj_packed.release(); spj_packed.release(); }
+};
+
+constexpr int N_TAG = 4;
+
+struct Ctx {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    float eps2 = 0.0f;
+    int quad = 1, flags = 0;
+    JSet jset;
+    WalkSet slots[N_TAG];
+    std::atomic<long long> launches{0}, n_epep{0}, n_epsp{0};
+    std::mutex mu;
+    int smem_bytes = 0;
+};
+Ctx g;
+
+int ensure_init()
+{
+    if (g.ready) return 0;
+    const char *env = getenv("GPLUM_B200_DEVICE");
+    return gplum_b200_init(env ? atoi(env) : 0, 0, 0);
+}
+
+// ---- work list: split every walk into i-tiles, choose a tile shape, longest first ----
+void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items)
+{
+    items.clear();
+    std::vector<std::pair<double, WorkItem>> tmp;
+    tmp.reserve((size_t)n_walk * 2);
+    for (int w = 0; w < n_walk; w++) {
+        int rem = ni[w], i0 = 0;
+        const double cost_j = 20.0 * n_epj[w] + 38.0 * n_spj[w] + 64.0;
+        while (rem > 0) {
+            int cfg;
+            if (rem >= 512) cfg = 4;
+            else if (rem > 256 && rem > 448) cfg = 4;
+            else if (rem >= 256) cfg = 3;
+            else if (rem > 224) cfg = 3;
+            else if (rem >= 128) cfg = 2;
+            else if (rem > 96) cfg = 2;
+            else if (rem >= 64) cfg = 1;
+            else if (rem > 32) cfg = 1;
+            else cfg = 0;
+            const int tile = cfg_tile(cfg);
+            const int n = std::min(rem, tile);
+            tmp.push_back({cost_j * tile, WorkItem{w, i0, n, cfg}});
+            rem -= n; i0 += n;
+        }
+    }
+    std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    items.reserve(tmp.size());
+    for (auto &t : tmp) items.push_back(t.second);
+}
+
+int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
+{
+    if (ws.n_items == 0) return 0;
+    PassParams p;
+    p.epi = (const EpiAos *)ws.epi.p;
+    p.epi_off = (const int *)ws.epi_off.p;
+    p.adr_epj = (const int *)ws.adr_epj.p; p.epj_disp = (const long long *)ws.epj_disp.p; p.n_epj = (const int *)ws.n_epj.p;
+    p.adr_spj = (const int *)ws.adr_spj.p; p.spj_disp = (const long long *)ws.spj_disp.p; p.n_spj = (const int *)ws.n_spj.p;
+    p.epj = g.jset.epj(); p.spj = g.jset.spj();
+    p.force = (ForceAos *)ws.force.p;
+    p.items = (const WorkItem *)ws.items.p;
+    p.eps2 = eps2;
+    p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
+    force_pass_kernel<<<ws.n_items, NT, g.smem_bytes, st>>>(p);
+    CU(cudaGetLastError());
+    g.launches++;
+    g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp;
+    return 0;
+}
+
+int pack_j(cudaStream_t st, float eps2)
+{
+    JSet &j = g.jset;
+    if (j.n_epj > 0 && !j.ext_epj) {
+        pack_epj_kernel<<<(j.n_epj + 255) / 256, 256, 0, st>>>((const EpjAos *)j.epj_aos.p, j.n_epj, (EpjPacked *)j.epj_packed.p);
+        CU(cudaGetLastError());
+        g.launches++;
+    }
+    if (j.n_spj > 0 && !j.ext_spj) {
+        pack_spj_kernel<<<(j.n_spj + 255) / 256, 256, 0, st>>>(j.spj_aos.p, j.n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
+                                                               (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, eps2);
+        CU(cudaGetLastError());
+        g.launches++;
+    }
+    return 0;
+}
+
+int upload_j(const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all, cudaStream_t st)
+{
+    JSet &j = g.jset;
+    const size_t ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
+    j.ext_epj = j.ext_spj = nullptr;
+    j.n_epj = n_epj_all; j.n_spj = n_spj_all;
+    if (int r = j.epj_aos.reserve((size_t)n_epj_all * sizeof(EpjAos))) return r;
+    if (int r = j.epj_packed.reserve((size_t)n_epj_all * sizeof(EpjPacked))) return r;
+    if (int r = j.spj_aos.reserve((size_t)n_spj_all * ssz)) return r;
+    if (int r = j.spj_packed.reserve((size_t)n_spj_all * sizeof(SpjPacked))) return r;
+    if (n_epj_all) CU(cudaMemcpyAsync(j.epj_aos.p, epj_all, (size_t)n_epj_all * sizeof(EpjAos), cudaMemcpyHostToDevice, st));
+    if (n_spj_all) CU(cudaMemcpyAsync(j.spj_aos.p, spj_all, (size_t)n_spj_all * ssz, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+// Copy flat walk arrays to the device and build the work list.
+int upload_walks(WalkSet &ws, int n_walk, const void *epi_all, const int *epi_off, const int *ni,
+                 const int *adr_epj, const long long *epj_disp, const int *n_epj,
+                 const int *adr_spj, const long long *spj_disp, const int *n_spj, cudaStream_t st)
+{
+    long long n_epi = 0, n_ae = 0, n_as = 0, i_ee = 0, i_es = 0;
+    for (int w = 0; w < n_walk; w++) {
+        if (ni[w] < 0 || n_epj[w] < 0 || n_spj[w] < 0) return fail(GPLUM_B200_ERR_ARG, "negative count in walk %d", w);
+        n_epi = std::max(n_epi, (long long)epi_off[w] + ni[w]);
+        n_ae = std::max(n_ae, epj_disp[w] + n_epj[w]);
+        n_as = std::max(n_as, spj_disp[w] + n_spj[w]);
+        i_ee += (long long)ni[w] * n_epj[w];
+        i_es += (long long)ni[w] * n_spj[w];
+    }
+    ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
+    ws.n_int_epep = i_ee; ws.n_int_epsp = i_es;
+    std::vector<WorkItem> items;
+    build_items(n_walk, ni, n_epj, n_spj, items);
+    ws.n_items = (int)items.size();
+    if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
+    if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
+    if (int r = ws.epi_off.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.n_epj.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.n_spj.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.epj_disp.reserve((size_t)n_walk * 8)) return r;
+    if (int r = ws.spj_disp.reserve((size_t)n_walk * 8)) return r;
+    if (int r = ws.adr_epj.reserve((size_t)n_ae * 4)) return r;
+    if (int r = ws.adr_spj.reserve((size_t)n_as * 4)) return r;
+    if (int r = ws.items.reserve(items.size() * sizeof(WorkItem))) return r;
+    if (n_walk == 0) return 0;
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+    if (n_epi) CU(cudaMemcpyAsync(ws.epi.p, epi_all, (size_t)n_epi * sizeof(EpiAos), H2D, st));
+    CU(cudaMemcpyAsync(ws.epi_off.p, epi_off, (size_t)n_walk * 4, H2D, st));
+    CU(cudaMemcpyAsync(ws.n_epj.p, n_epj, (size_t)n_walk * 4, H2D, st));
+    CU(cudaMemcpyAsync(ws.n_spj.p, n_spj, (size_t)n_walk * 4, H2D, st));
+    CU(cudaMemcpyAsync(ws.epj_disp.p, epj_disp, (size_t)n_walk * 8, H2D, st));
+    CU(cudaMemcpyAsync(ws.spj_disp.p, spj_disp, (size_t)n_walk * 8, H2D, st));
+    if (n_ae) CU(cudaMemcpyAsync(ws.adr_epj.p, adr_epj, (size_t)n_ae * 4, H2D, st));
+    if (n_as) CU(cudaMemcpyAsync(ws.adr_spj.p, adr_spj, (size_t)n_as * 4, H2D, st));
+    if (!items.empty()) {
+        // items lives on the host stack frame: the copy below is from pageable memory and therefore
+        // complete (staged) when cudaMemcpyAsync returns.
+        CU(cudaMemcpyAsync(ws.items.p, items.data(), items.size() * sizeof(WorkItem), H2D, st));
+    }
+    return 0;
+}
+
+inline void accumulate_force(ForceAos *dst, const ForceAos *src, long long n, bool overwrite)
+{
+    if (overwrite) { memcpy(dst, src, (size_t)n * sizeof(ForceAos)); return; }
+    for (long long i = 0; i < n; i++) {   // "+=" / max / min: src/gravity_kernel.hpp:115-120
+        dst[i].acc[0] += src[i].acc[0]; dst[i].acc[1] += src[i].acc[1]; dst[i].acc[2] += src[i].acc[2];
+        dst[i].phi += src[i].phi;
+        dst[i].number += src[i].number; dst[i].rank += src[i].rank;
+        dst[i].id_max = std::max(dst[i].id_max, src[i].id_max);
+        dst[i].id_min = std::min(dst[i].id_min, src[i].id_min);
+    }
+}
+
+// per-thread state of the per-call functor form
+struct CallSlot {
+    cudaStream_t st = nullptr;
+    DevBuf epi, jaos, jpacked, iota, force, meta;
+    PinBuf h_force;
+    int iota_n = 0;
+    ~CallSlot() {}
+};
+thread_local CallSlot t_slot;
+
+__global__ void iota_kernel(int *p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// One functor call: which = 0 EP-EP, 1 EP-SP.
+int single_call(int which, const void *epi, int ni, const void *jp, int nj, void *force, float eps2, int quad)
+{
+    if (int r = ensure_init()) return r;
+    if (ni < 0 || nj < 0) return fail(GPLUM_B200_ERR_ARG, "negative ni/nj");
+    if (ni == 0) return 0;
+    if (!epi || !force || (nj > 0 && !jp)) return fail(GPLUM_B200_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(g.device));
+    CallSlot &s = t_slot;
+    if (!s.st) CU(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    const size_t jsz = which == 0 ? sizeof(EpjAos) : (quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos));
+    const size_t psz = which == 0 ? sizeof(EpjPacked) : sizeof(SpjPacked);
+    if (int r = s.epi.reserve((size_t)ni * sizeof(EpiAos))) return r;
+    if (int r = s.force.reserve((size_t)ni * sizeof(ForceAos))) return r;
+    if (int r = s.h_force.reserve((size_t)ni * sizeof(ForceAos))) return r;
+    if (int r = s.jaos.reserve((size_t)std::max(nj, 1) * jsz)) return r;
+    if (int r = s.jpacked.reserve((size_t)std::max(nj, 1) * psz)) return r;
+    if (nj > s.iota_n) {
+        if (int r = s.iota.reserve((size_t)nj * 4)) return r;
+        s.iota_n = (int)(s.iota.cap / 4);
+        iota_kernel<<<(s.iota_n + 255) / 256, 256, 0, s.st>>>((int *)s.iota.p, s.iota_n);
+        CU(cudaGetLastError());
+    }
+    // meta: [epi_off(int) | n_epj | n_spj | pad | epj_disp(ll) | spj_disp(ll) | items...]
+    std::vector<WorkItem> items;
+    const int zero = 0;
+    const int ne = which == 0 ? nj : 0, ns = which == 1 ? nj : 0;
+    build_items(1, &ni, &ne, &ns, items);
+    struct Meta { int epi_off, n_epj, n_spj, pad; long long epj_disp, spj_disp; } meta = {zero, ne, ns, 0, 0, 0};
+    const size_t meta_bytes = sizeof(Meta) + items.size() * sizeof(WorkItem);
+    if (int r = s.meta.reserve(meta_bytes)) return r;
+    std::vector<unsigned char> hm(meta_bytes);
+    memcpy(hm.data(), &meta, sizeof(Meta));
+    memcpy(hm.data() + sizeof(Meta), items.data(), items.size() * sizeof(WorkItem));
+    CU(cudaMemcpyAsync(s.meta.p, hm.data(), meta_bytes, cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.epi.p, epi, (size_t)ni * sizeof(EpiAos), cudaMemcpyHostToDevice, s.st));
+    if (nj) CU(cudaMemcpyAsync(s.jaos.p, jp, (size_t)nj * jsz, cudaMemcpyHostToDevice, s.st));
+    if (nj && which == 0) {
+        pack_epj_kernel<<<(nj + 255) / 256, 256, 0, s.st>>>((const EpjAos *)s.jaos.p, nj, (EpjPacked *)s.jpacked.p);
+        g.launches++;
+    } else if (nj) {
+        pack_spj_kernel<<<(nj + 255) / 256, 256, 0, s.st>>>(s.jaos.p, nj, (SpjPacked *)s.jpacked.p, quad,
+                                                           (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, eps2);
+        g.launches++;
+    }
+    CU(cudaGetLastError());
+    PassParams p;
+    const unsigned char *dm = (const unsigned char *)s.meta.p;
+    p.epi = (const EpiAos *)s.epi.p;
+    p.epi_off = (const int *)(dm + offsetof(Meta, epi_off));
+    p.n_epj = (const int *)(dm + offsetof(Meta, n_epj));
+    p.n_spj = (const int *)(dm + offsetof(Meta, n_spj));
+    p.epj_disp = (const long long *)(dm + offsetof(Meta, epj_disp));
+    p.spj_disp = (const long long *)(dm + offsetof(Meta, spj_disp));
+    p.adr_epj = (const int *)s.iota.p; p.adr_spj = (const int *)s.iota.p;
+    p.epj = (const EpjPacked *)s.jpacked.p; p.spj = (const SpjPacked *)s.jpacked.p;
+    p.force = (ForceAos *)s.force.p;
+    p.items = (const WorkItem *)(dm + sizeof(Meta));
+    p.eps2 = eps2;
+    p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
+    force_pass_kernel<<<(int)items.size(), NT, g.smem_bytes, s.st>>>(p);
+    CU(cudaGetLastError());
+    g.launches++;
+    if (which == 0) g.n_epep += (long long)ni * nj; else g.n_epsp += (long long)ni * nj;
+    CU(cudaMemcpyAsync(s.h_force.p, s.force.p, (size_t)ni * sizeof(ForceAos), cudaMemcpyDeviceToHost, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    accumulate_force((ForceAos *)force, (const ForceAos *)s.h_force.p, ni, (g.flags & GPLUM_B200_NO_ACCUMULATE) != 0);
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int gplum_b200_abi_version(void) { return GPLUM_B200_ABI_VERSION; }
+const char *gplum_b200_last_error(void) { return g_err; }
+
+int gplum_b200_init(int device, size_t max_i, size_t max_j)
+{
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.ready && g.device == device) return 0;
+    if (g.ready) return fail(GPLUM_B200_ERR_STATE, "already initialised on device %d", g.device);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(GPLUM_B200_ERR_NO_DEVICE, "no CUDA device (%s); libgplum_b200 has no CPU path",
+                    e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return fail(GPLUM_B200_ERR_ARG, "device %d out of range (%d devices)", device, n_dev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GPLUM_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    g.smem_bytes = (int)sizeof(SmemLayout);
+    CU(cudaFuncSetAttribute(force_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    g.device = device;
+    if (max_i) {
+        if (int r = g.slots[0].epi.reserve(max_i * sizeof(EpiAos))) return r;
+        if (int r = g.slots[0].force.reserve(max_i * sizeof(ForceAos))) return r;
+    }
+    if (max_j) {
+        if (int r = g.slots[0].adr_epj.reserve(max_j * 4)) return r;
+    }
+    g.ready = true;
+    return 0;
+}
+
+int gplum_b200_finalize(void)
+{
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.ready) return 0;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    g.jset.release();
+    for (auto &s : g.slots) s.release();
+    if (g.own_stream) cudaStreamDestroy(g.own_stream);
+    g.own_stream = g.stream = nullptr;
+    g.ready = false;
+    g.device = -1;
+    return 0;
+}
+
+int gplum_b200_set_params(float eps2, int quad, int flags)
+{
+    g.eps2 = eps2; g.quad = quad ? 1 : 0; g.flags = flags;
+    return 0;
+}
+
+int gplum_b200_set_stream(void *cuda_stream)
+{
+    if (int r = ensure_init()) return r;
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return 0;
+}
+
+int gplum_b200_synchronize(void)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+void gplum_b200_counters(long long *kernel_launches, long long *n_epep, long long *n_epsp, int reset)
+{
+    if (kernel_launches) *kernel_launches = g.launches.load();
+    if (n_epep) *n_epep = g.n_epep.load();
+    if (n_epsp) *n_epsp = g.n_epsp.load();
+    if (reset) { g.launches = 0; g.n_epep = 0; g.n_epsp = 0; }
+}
+
+void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes)
+{
+    if (epj_packed_bytes) *epj_packed_bytes = (int)sizeof(EpjPacked);
+    if (spj_packed_bytes) *spj_packed_bytes = (int)sizeof(SpjPacked);
+}
+
+// ---- per-call functor form ----
+int gplum_b200_epep(const void *epi, int ni, const void *epj, int nj, void *force, float eps2)
+{
+    return single_call(0, epi, ni, epj, nj, force, eps2, 1);
+}
+
+int gplum_b200_epsp(const void *epi, int ni, const void *spj, int ns, void *force, float eps2, int quad)
+{
+    return single_call(1, epi, ni, spj, ns, force, eps2, quad);
+}
+
+// ---- flat form ----
+int gplum_b200_calc_walks(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
+                          const int *adr_epj, const long long *epj_disp, const int *n_epj,
+                          const int *adr_spj, const long long *spj_disp, const int *n_spj,
+                          const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all,
+                          void *force_all, int clear)
+{
+    if (int r = ensure_init()) return r;
+    if (n_walk < 0) return fail(GPLUM_B200_ERR_ARG, "n_walk < 0");
+    if (n_walk == 0) return 0;
+    CU(cudaSetDevice(g.device));
+    WalkSet &ws = g.slots[0];
+    cudaStream_t st = g.stream;
+    if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
+    if (int r = pack_j(st, g.eps2)) return r;
+    if (int r = upload_walks(ws, n_walk, epi_all, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, st)) return r;
+    if (int r = launch_pass(ws, st, g.eps2)) return r;
+    if (ws.n_epi == 0) { CU(cudaStreamSynchronize(st)); return 0; }
+    if (clear) {
+        // walks tile [0, n_epi) in FDPS; entries not covered by any walk keep the caller's values
+        if (int r = ws.h_force.reserve((size_t)ws.n_epi * sizeof(ForceAos))) return r;
+        CU(cudaMemcpyAsync(ws.h_force.p, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int w = 0; w < n_walk; w++)
+            memcpy((ForceAos *)force_all + epi_off[w], (const ForceAos *)ws.h_force.p + epi_off[w], (size_t)ni[w] * sizeof(ForceAos));
+    } else {
+        if (int r = ws.h_force.reserve((size_t)ws.n_epi * sizeof(ForceAos))) return r;
+        CU(cudaMemcpyAsync(ws.h_force.p, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (int w = 0; w < n_walk; w++)
+            accumulate_force((ForceAos *)force_all + epi_off[w], (const ForceAos *)ws.h_force.p + epi_off[w], ni[w], false);
+    }
+    return 0;
+}
+
+// ---- FDPS multi-walk-index form ----
+int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *ni,
+                        const int *const *adr_epj, const int *n_epj,
+                        const int *const *adr_spj, const int *n_spj,
+                        const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all,
+                        int send_all)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    if (send_all) {
+        if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
+        return pack_j(st, g.eps2);
+    }
+    if (tag < 0 || tag >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "tag %d out of range [0,%d)", tag, N_TAG);
+    if (n_walk < 0) return fail(GPLUM_B200_ERR_ARG, "n_walk < 0");
+    WalkSet &ws = g.slots[tag];
+    if (ws.pending) return fail(GPLUM_B200_ERR_STATE, "dispatch(tag=%d) while a previous dispatch is not retrieved", tag);
+    // flatten the per-walk pointers into one pinned staging block
+    long long n_epi = 0, n_ae = 0, n_as = 0;
+    for (int w = 0; w < n_walk; w++) { n_epi += ni[w]; n_ae += n_epj[w]; n_as += n_spj[w]; }
+    const size_t b_epi = (size_t)n_epi * sizeof(EpiAos), b_ae = (size_t)n_ae * 4, b_as = (size_t)n_as * 4;
+    const size_t b_meta = (size_t)n_walk * (4 * 3 + 8 * 2);
+    if (int r = ws.h_stage.reserve(b_epi + b_ae + b_as + b_meta + 64)) return r;
+    unsigned char *h = (unsigned char *)ws.h_stage.p;
+    EpiAos *h_epi = (EpiAos *)h;
+    long long *h_edisp = (long long *)(h + ((b_epi + 15) & ~(size_t)15));
+    long long *h_sdisp = h_edisp + n_walk;
+    int *h_off = (int *)(h_sdisp + n_walk);
+    int *h_ne = h_off + n_walk, *h_ns = h_ne + n_walk;
+    int *h_ae = h_ns + n_walk, *h_as = h_ae + n_ae;
+    ws.ni_host.assign(ni, ni + n_walk);
+    ws.epi_off_host.resize(n_walk);
+    long long oi = 0, oe = 0, os = 0;
+    for (int w = 0; w < n_walk; w++) {
+        h_off[w] = (int)oi; h_edisp[w] = oe; h_sdisp[w] = os; h_ne[w] = n_epj[w]; h_ns[w] = n_spj[w];
+        ws.epi_off_host[w] = oi;
+        oi += ni[w]; oe += n_epj[w]; os += n_spj[w];
+    }
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < n_walk; w++) {
+        memcpy(h_epi + h_off[w], epi[w], (size_t)ni[w] * sizeof(EpiAos));
+        memcpy(h_ae + h_edisp[w], adr_epj[w], (size_t)n_epj[w] * 4);
+        memcpy(h_as + h_sdisp[w], adr_spj[w], (size_t)n_spj[w] * 4);
+    }
+    if (int r = upload_walks(ws, n_walk, h_epi, h_off, ws.ni_host.data(), h_ae, h_edisp, h_ne, h_as, h_sdisp, h_ns, st)) return r;
+    if (int r = launch_pass(ws, st, g.eps2)) return r;
+    if (int r = ws.h_force.reserve((size_t)std::max<long long>(ws.n_epi, 1) * sizeof(ForceAos))) return r;
+    if (ws.n_epi) CU(cudaMemcpyAsync(ws.h_force.p, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost, st));
+    ws.pending = true;
+    return 0;
+}
+
+int gplum_b200_retrieve(int tag, int n_walk, const int *ni, void *const *force)
+{
+    if (int r = ensure_init()) return r;
+    if (tag < 0 || tag >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "tag %d out of range", tag);
+    WalkSet &ws = g.slots[tag];
+    if (!ws.pending) return fail(GPLUM_B200_ERR_STATE, "retrieve(tag=%d) without dispatch", tag);
+    if (n_walk != ws.n_walk) return fail(GPLUM_B200_ERR_ARG, "retrieve n_walk %d != dispatched %d", n_walk, ws.n_walk);
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamSynchronize(g.stream));
+    ws.pending = false;
+    const bool overwrite = (g.flags & GPLUM_B200_NO_ACCUMULATE) != 0;
+    const ForceAos *src = (const ForceAos *)ws.h_force.p;
+#pragma omp parallel for schedule(static)
+    for (int w = 0; w < n_walk; w++) {
+        if (ni[w] != ws.ni_host[w]) continue;
+        accumulate_force((ForceAos *)force[w], src + ws.epi_off_host[w], ni[w], overwrite);
+    }
+    for (int w = 0; w < n_walk; w++)
+        if (ni[w] != ws.ni_host[w]) return fail(GPLUM_B200_ERR_ARG, "retrieve ni[%d]=%d != dispatched %d", w, ni[w], ws.ni_host[w]);
+    return 0;
+}
+
+// ---- device-resident form ----
+int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
+                            const int *adr_epj, const long long *epj_disp, const int *n_epj,
+                            const int *adr_spj, const long long *spj_disp, const int *n_spj,
+                            const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
+    if (int r = pack_j(st, g.eps2)) return r;
+    if (int r = upload_walks(g.slots[0], n_walk, epi_all, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, st)) return r;
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gplum_b200_walks_run(int repack)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    if (repack) if (int r = pack_j(g.stream, g.eps2)) return r;
+    return launch_pass(g.slots[0], g.stream, g.eps2);
+}
+
+int gplum_b200_walks_download(void *force_all)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    WalkSet &ws = g.slots[0];
+    CU(cudaStreamSynchronize(g.stream));
+    if (ws.n_epi) CU(cudaMemcpy(force_all, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int gplum_b200_walks_time(int iters, int repack, float *ms_per_pass)
+{
+    if (int r = ensure_init()) return r;
+    if (iters <= 0) return fail(GPLUM_B200_ERR_ARG, "iters <= 0");
+    CU(cudaSetDevice(g.device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(g.stream));
+    CU(cudaEventRecord(e0, g.stream));
+    for (int i = 0; i < iters; i++) {
+        if (repack) if (int r = pack_j(g.stream, g.eps2)) return r;
+        if (int r = launch_pass(g.slots[0], g.stream, g.eps2)) return r;
+    }
+    CU(cudaEventRecord(e1, g.stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_per_pass) *ms_per_pass = ms / iters;
+    return 0;
+}
+
+int gplum_b200_walks_set_packed_dev(const void *epj_packed_dev, int n_epj_all, const void *spj_packed_dev, int n_spj_all)
+{
+    if (int r = ensure_init()) return r;
+    g.jset.ext_epj = epj_packed_dev; g.jset.ext_spj = spj_packed_dev;
+    if (epj_packed_dev) g.jset.n_epj = n_epj_all;
+    if (spj_packed_dev) g.jset.n_spj = n_spj_all;
+    return 0;
+}
+
+int gplum_b200_pack_epj_dev(const void *epj_aos_dev, int n, void *epj_packed_dev)
+{
+    if (int r = ensure_init()) return r;
+    if (n <= 0) return 0;
+    CU(cudaSetDevice(g.device));
+    pack_epj_kernel<<<(n + 255) / 256, 256, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)epj_packed_dev);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev)
+{
+    if (int r = ensure_init()) return r;
+    if (n <= 0) return 0;
+    CU(cudaSetDevice(g.device));
+    pack_spj_kernel<<<(n + 255) / 256, 256, 0, g.stream>>>(spj_aos_dev, n, (SpjPacked *)spj_packed_dev, g.quad,
+                                                          (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_fp32_peak(int iters, float *tflops, float *ms_out)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, g.device));
+    float *d = nullptr;
+    CU(cudaMalloc(&d, 4));
+    const int blocks = prop.multiProcessorCount * 8, inner = 4096;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    fp32_peak_kernel<<<blocks, 256, 0, g.stream>>>(d, inner, 1.0000001f, 1e-9f);
+    CU(cudaStreamSynchronize(g.stream));
+    CU(cudaEventRecord(e0, g.stream));
+    for (int i = 0; i < iters; i++) fp32_peak_kernel<<<blocks, 256, 0, g.stream>>>(d, inner, 1.0000001f, 1e-9f);
+    CU(cudaEventRecord(e1, g.stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flop = 2.0 * 16.0 * inner * 256.0 * blocks * iters;
+    if (tflops) *tflops = (float)(flop / (ms * 1e-3) / 1e12);
+    if (ms_out) *ms_out = ms / iters;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+// kernels.cuh -- sm_100a device code of the P3T soft-force pass.
+//
+// One launch evaluates a whole FDPS force pass (TreeForForce::calcForce,
+// FDPS/src/tree_for_force_impl_force.hpp:1404-1564): every work item is one i-tile of one
+// i-group ("walk") against that group's EP and SP interaction lists, given as indices into
+// packed j-arrays resident in HBM.  Arithmetic follows src/gravity_kernel_epep.pikg:53-97 and
+// src/gravity_kernel_epsp.pikg:47-100: FP64 shift by the group's first i-particle, then FP32.
+//
+// Per pair, EP-EP (hot loop, 20 issue slots for the DSL's 30 flop + rsqrt):
+//   d = xj-xi (3 FADD); r2 = d.d+eps2 (3 FFMA); hit |= r2 < T_i (FSETP);
+//   r2c = max3(r2, rout2_i, rout2_j) (FMNMX3; max(a,b)^2 == max(a^2,b^2) exactly in FP);
+//   y = MUFU.RSQ(r2c) + the DSL's Newton step (4); mr = m*y; mr3 = y*y*mr (3);
+//   acc += mr3*d (3 FFMA); phi -= mr (FADD).
+// Neighbour candidates: the hot loop only evaluates a conservative filter (r2 < T_i with
+// T_i >= rsearch2 of the pair, widened by 2^-16); pairs that pass (rare: self + true
+// candidates) are re-tested in the reference's exact, non-fused evaluation order
+// (src/gravity_kernel.hpp:94,104-111) so number/rank/id_max/id_min are bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gb {
+
+constexpr int NT = 256;        // threads per CTA
+constexpr int JT = 256;        // j-particles staged per tile
+constexpr int JPAD = 64;       // slack for per-slice round-up
+constexpr int UNROLL = 4;
+
+// ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
+struct __align__(16) EpjPacked {   // 48 B
+    double x, y;
+    double z; float m, rout2;
+    float rs2; int id; int rank; int pad;
+};
+struct __align__(16) SpjPacked {   // 64 B; Q = 3q - tr*I, mtr = -(eps2*tr) hoisted (j-only terms)
+    double x, y;
+    double z; float m, qxx;
+    float qyy, qzz, qxy, qyz;
+    float qzx, mtr, pad0, pad1;
+};
+static_assert(sizeof(EpjPacked) == 48 && sizeof(SpjPacked) == 64, "packed layout");
+
+// ---- the reference's AoS structs as seen by the device (default macro set) ----
+struct EpiAos { int id_local, myrank; double pos[3]; double r_out, r_search; };                    // 48
+struct EpjAos { int id_local, myrank; double pos[3]; double r_out, r_search; long long id;
+                double mass; double vel[3]; double acc_d[3]; };                                    // 112
+struct SpjQuadAos { double mass; double pos[3]; double quad[6]; };                                 // 80
+struct SpjMonoAos { double mass; double pos[3]; };                                                 // 32
+struct __align__(16) ForceAos { float acc[3]; float phi; int number, rank, id_max, id_min; };      // 32
+static_assert(sizeof(EpiAos) == 48 && sizeof(EpjAos) == 112 && sizeof(SpjQuadAos) == 80 &&
+              sizeof(SpjMonoAos) == 32 && sizeof(ForceAos) == 32, "reference layout");
+
+struct WorkItem { int walk, i0, ni, cfg; };
+
+struct PassParams {
+    const EpiAos *epi;            // concatenated i-particles
+    const int *epi_off;           // per walk
+    const int *adr_epj; const long long *epj_disp; const int *n_epj;
+    const int *adr_spj; const long long *spj_disp; const int *n_spj;
+    const EpjPacked *epj; const SpjPacked *spj;
+    ForceAos *force;
+    const WorkItem *items;
+    float eps2;
+    int rank_squared;
+};
+
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_d2(const void *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_f4(const void *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// pack kernels: AoS (as FDPS holds epj_sorted_/spj_sorted_) -> packed records
+// ------------------------------------------------------------------------------------------
+__global__ void pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const EpjAos &a = in[i];
+    EpjPacked o;
+    o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2];
+    o.m = (float)a.mass;
+    const float ro = (float)a.r_out, rs = (float)a.r_search;
+    o.rout2 = __fmul_rn(ro, ro);
+    o.rs2 = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
+    o.id = a.id_local; o.rank = a.myrank; o.pad = 0;
+    out[i] = o;
+}
+
+// quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
+// src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).
+__global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
+                                int quad, int trace_as_shipped, float eps2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SpjPacked o;
+    if (quad) {
+        const SpjQuadAos &a = ((const SpjQuadAos *)in)[i];
+        o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
+        const float qxx = (float)a.quad[0], qyy = (float)a.quad[1], qzz = (float)a.quad[2];
+        const float qxy = (float)a.quad[3], qzx = (float)a.quad[4], qyz = (float)a.quad[5];
+        const float tr = trace_as_shipped ? (float)(a.quad[0] + a.quad[1] + a.quad[0])
+                                          : __fadd_rn(__fadd_rn(qxx, qyy), qzz);
+        o.qxx = __fsub_rn(__fmul_rn(3.0f, qxx), tr);
+        o.qyy = __fsub_rn(__fmul_rn(3.0f, qyy), tr);
+        o.qzz = __fsub_rn(__fmul_rn(3.0f, qzz), tr);
+        o.qxy = __fmul_rn(3.0f, qxy); o.qyz = __fmul_rn(3.0f, qyz); o.qzx = __fmul_rn(3.0f, qzx);
+        o.mtr = -__fmul_rn(eps2, tr);
+    } else {
+        const SpjMonoAos &a = ((const SpjMonoAos *)in)[i];
+        o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
+        o.qxx = o.qyy = o.qzz = o.qxy = o.qyz = o.qzx = 0.0f; o.mtr = 0.0f;
+    }
+    o.pad0 = o.pad1 = 0.0f;
+    out[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory carve-up (dynamic): sized for the largest i-tile (IT_MAX)
+// ------------------------------------------------------------------------------------------
+constexpr int IT_MAX = 512;
+struct SmemLayout {
+    float4 j4[JT + JPAD];      // EP: dx,dy,dz,m      SP: dx,dy,dz,m
+    float4 q0[JT + JPAD];      // SP: Qxx,Qyy,Qzz,Qxy
+    float4 q1[JT + JPAD];      // SP: Qyz,Qzx,mtr,-
+    float rout2[JT + JPAD];
+    float rs2[JT + JPAD];
+    int id[JT + JPAD];
+    int rank[JT + JPAD];
+    float4 ipos[IT_MAX];       // xi,yi,zi,rout2_i  (later: cross-slice reduction scratch)
+    float i_rs2[IT_MAX];
+    int i_id[IT_MAX];
+    int i_rank[IT_MAX];
+    int nb_number[IT_MAX], nb_rank[IT_MAX], nb_idmax[IT_MAX], nb_idmin[IT_MAX];
+    float4 red[NT * 4];        // [slice][i] partial sums (JS*IT = NT*R <= NT*4)
+    int tmax[2];
+};
+
+template <int R, int LANES_I>
+__device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem it, SmemLayout &s)
+{
+    constexpr int JS = NT / LANES_I;     // j-slices
+    constexpr int IT = R * LANES_I;      // i-particles per tile
+    static_assert(IT <= IT_MAX && JS * UNROLL <= JPAD && JS * IT <= NT * 4, "tile shape");
+    const int tid = threadIdx.x;
+    const int slice = tid / LANES_I;
+    const int lane_i = tid % LANES_I;
+    const int w = it.walk;
+    const int ibase = p.epi_off[w] + it.i0;
+    const EpiAos *epi0 = p.epi + p.epi_off[w];
+    // FP64 origin of the group: epi[0].pos (gravity_kernel_epep.pikg:53 "xi - xi[0]")
+    const double ox = epi0->pos[0], oy = epi0->pos[1], oz = epi0->pos[2];
+    const float eps2 = p.eps2;
+
+    // ---- stage the i-tile ----
+    for (int i = tid; i < IT; i += NT) {
+        if (i < it.ni) {
+            const EpiAos &e = p.epi[ibase + i];
+            const float ro = (float)e.r_out, rs = (float)e.r_search;
+            s.ipos[i] = make_float4((float)(e.pos[0] - ox), (float)(e.pos[1] - oy), (float)(e.pos[2] - oz),
+                                    __fmul_rn(ro, ro));
+            s.i_rs2[i] = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
+            s.i_id[i] = e.id_local; s.i_rank[i] = e.myrank;
+        } else {
+            s.ipos[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s.i_rs2[i] = -1.0f; s.i_id[i] = 0; s.i_rank[i] = 0;
+        }
+        s.nb_number[i] = 0; s.nb_rank[i] = 0; s.nb_idmax[i] = -1; s.nb_idmin[i] = 2147483647;
+    }
+    if (tid < 2) s.tmax[tid] = 0;
+    __syncthreads();
+
+    float xi[R], yi[R], zi[R], ro2i[R], rs2i[R], Ti[R];
+    float ax[R], ay[R], az[R], ph[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float4 v = s.ipos[lane_i + r * LANES_I];
+        xi[r] = v.x; yi[r] = v.y; zi[r] = v.z; ro2i[r] = v.w;
+        rs2i[r] = s.i_rs2[lane_i + r * LANES_I];
+        ax[r] = ay[r] = az[r] = ph[r] = 0.0f;
+    }
+
+    // =============================== EP-EP ===============================
+    {
+        const int nj = p.n_epj[w];
+        const int *adr = p.adr_epj + p.epj_disp[w];
+        int par = 0;
+        for (int tb = 0; tb < nj; tb += JT, par ^= 1) {
+            const int n_t = min(JT, nj - tb);
+            const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;   // per-slice, padded
+            const int n_slot = jps * JS;
+            __syncthreads();                      // previous tile fully consumed
+            float wmax = 0.0f;
+            for (int sl = tid; sl < n_slot; sl += NT) {
+                if (sl < n_t) {
+                    const EpjPacked *q = p.epj + adr[tb + sl];
+                    const double2 a = ldg_d2(q);
+                    const double2 b = ldg_d2(reinterpret_cast<const char *>(q) + 16);
+                    const float4 c = ldg_f4(reinterpret_cast<const char *>(q) + 32);
+                    const float m = __int_as_float((int)(__double_as_longlong(b.y) & 0xffffffffLL));
+                    const float ro2 = __int_as_float((int)(__double_as_longlong(b.y) >> 32));
+                    s.j4[sl] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(b.x - oz), m);
+                    s.rout2[sl] = ro2;
+                    s.rs2[sl] = c.x;
+                    s.id[sl] = __float_as_int(c.y);
+                    s.rank[sl] = __float_as_int(c.z);
+                    wmax = fmaxf(wmax, c.x);
+                } else {                          // padding: massless, far away, never a candidate
+                    s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
+                    s.rout2[sl] = 0.0f; s.rs2[sl] = 0.0f; s.id[sl] = -1; s.rank[sl] = 0;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+            if ((tid & 31) == 0) atomicMax(&s.tmax[par], __float_as_int(wmax));
+            __syncthreads();
+            if (tid == 0) s.tmax[par ^ 1] = 0;
+            // conservative candidate threshold for this tile (exact test happens in the rare path)
+            const float tmax = __int_as_float(s.tmax[par]) * 1.0000153f;
+#pragma unroll
+            for (int r = 0; r < R; r++) Ti[r] = (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax);
+
+            const int jb = slice * jps;
+#pragma unroll 1
+            for (int jj = 0; jj < jps; jj += UNROLL) {
+                bool hit = false;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const float4 pj = s.j4[jb + jj + u];
+                    const float ro2 = s.rout2[jb + jj + u];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
+                        hit |= (r2 < Ti[r]);
+                        const float r2c = fmax3(r2, ro2i[r], ro2);
+                        float y = rsqrt_approx(r2c);
+                        const float t = fmaf(-r2c, y * y, 3.0f);
+                        y *= t * 0.5f;
+                        const float mr = pj.w * y;
+                        const float mr3 = (y * y) * mr;
+                        ax[r] = fmaf(mr3, dx, ax[r]);
+                        ay[r] = fmaf(mr3, dy, ay[r]);
+                        az[r] = fmaf(mr3, dz, az[r]);
+                        ph[r] -= mr;
+                    }
+                }
+                if (hit) {
+                    // exact re-test, reference evaluation order, no FMA contraction
+                    for (int u = 0; u < UNROLL; u++) {
+                        const int j = jb + jj + u;
+                        const float4 pj = s.j4[j];
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const int il = lane_i + r * LANES_I;
+                            if (rs2i[r] < 0.0f) continue;
+                            const float dx = xi[r] - pj.x, dy = yi[r] - pj.y, dz = zi[r] - pj.z;
+                            const float r2e = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
+                                                                  __fmul_rn(dz, dz)), eps2);
+                            const float rs2 = fmaxf(rs2i[r], s.rs2[j]);
+                            if (r2e < rs2) {
+                                const int idj = s.id[j], rkj = s.rank[j];
+                                const int idi = s.i_id[il], rki = s.i_rank[il];
+                                if (idi != idj || rki != rkj) {
+                                    const int dr = rki - rkj;
+                                    atomicAdd(&s.nb_number[il], 1);
+                                    atomicAdd(&s.nb_rank[il], p.rank_squared ? dr * dr : abs(dr));
+                                    atomicMax(&s.nb_idmax[il], idj);
+                                    atomicMin(&s.nb_idmin[il], idj);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // =============================== EP-SP ===============================
+    {
+        const int nj = p.n_spj[w];
+        const int *adr = p.adr_spj + p.spj_disp[w];
+        for (int tb = 0; tb < nj; tb += JT) {
+            const int n_t = min(JT, nj - tb);
+            const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;
+            const int n_slot = jps * JS;
+            __syncthreads();
+            for (int sl = tid; sl < n_slot; sl += NT) {
+                if (sl < n_t) {
+                    const SpjPacked *q = p.spj + adr[tb + sl];
+                    const double2 a = ldg_d2(q);
+                    const double2 b = ldg_d2(reinterpret_cast<const char *>(q) + 16);
+                    const float4 c = ldg_f4(reinterpret_cast<const char *>(q) + 32);
+                    const float4 d = ldg_f4(reinterpret_cast<const char *>(q) + 48);
+                    const float m = __int_as_float((int)(__double_as_longlong(b.y) & 0xffffffffLL));
+                    const float qxx = __int_as_float((int)(__double_as_longlong(b.y) >> 32));
+                    s.j4[sl] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(b.x - oz), m);
+                    s.q0[sl] = make_float4(qxx, c.x, c.y, c.z);      // Qxx Qyy Qzz Qxy
+                    s.q1[sl] = make_float4(c.w, d.x, d.y, 0.0f);     // Qyz Qzx mtr
+                } else {
+                    s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
+                    s.q0[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    s.q1[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            __syncthreads();
+            const int jb = slice * jps;
+#pragma unroll 1
+            for (int jj = 0; jj < jps; jj += UNROLL) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    const float4 pj = s.j4[jb + jj + u];
+                    const float4 qa = s.q0[jb + jj + u];
+                    const float4 qb = s.q1[jb + jj + u];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
+                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
+                        float y = rsqrt_approx(r2);
+                        const float t = fmaf(-r2, y * y, 3.0f);
+                        y *= t * 0.5f;
+                        const float y2 = y * y, y3 = y2 * y, y4 = y2 * y2, y5 = y2 * y3;
+                        const float qrx = fmaf(qb.y, dz, fmaf(qa.w, dy, qa.x * dx));   // Qxx dx + Qxy dy + Qzx dz
+                        const float qry = fmaf(qa.w, dx, fmaf(qb.x, dz, qa.y * dy));   // Qyy dy + Qyz dz + Qxy dx
+                        const float qrz = fmaf(qb.x, dy, fmaf(qb.y, dx, qa.z * dz));   // Qzz dz + Qzx dx + Qyz dy
+                        const float rqr = fmaf(qrz, dz, fmaf(qry, dy, fmaf(qrx, dx, qb.z)));
+                        const float wq = rqr * y4;
+                        const float meff = fmaf(0.5f, wq, pj.w);
+                        const float meff3 = fmaf(2.5f, wq, pj.w) * y3;
+                        ph[r] = fmaf(-meff, y, ph[r]);
+                        ax[r] = fmaf(meff3, dx, fmaf(-y5, qrx, ax[r]));
+                        ay[r] = fmaf(meff3, dy, fmaf(-y5, qry, ay[r]));
+                        az[r] = fmaf(meff3, dz, fmaf(-y5, qrz, az[r]));
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- cross-slice reduction (fixed order) and write-back: ForceGrav::clear + accumulate ----
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; r++) s.red[slice * IT + lane_i + r * LANES_I] = make_float4(ax[r], ay[r], az[r], ph[r]);
+    __syncthreads();
+    for (int i = tid; i < it.ni; i += NT) {
+        float4 a = s.red[i];
+#pragma unroll
+        for (int sl = 1; sl < JS; sl++) {
+            const float4 b = s.red[sl * IT + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
+        out[0] = a;
+        reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+    }
+}
+
+// cfg -> (R, LANES_I):  0:(1,32) 1:(2,32) 2:(2,64) 3:(2,128) 4:(4,128)
+__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : cfg == 1 ? 64 : cfg == 2 ? 128 : cfg == 3 ? 256 : 512; }
+
+__global__ void __launch_bounds__(NT, 2) force_pass_kernel(const PassParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout &s = *reinterpret_cast<SmemLayout *>(smem_raw);
+    const WorkItem it = p.items[blockIdx.x];
+    switch (it.cfg) {
+        case 0: tile_force<1, 32>(p, it, s); break;
+        case 1: tile_force<2, 32>(p, it, s); break;
+        case 2: tile_force<2, 64>(p, it, s); break;
+        case 3: tile_force<2, 128>(p, it, s); break;
+        default: tile_force<4, 128>(p, it, s); break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FP32 FMA issue-rate microbenchmark: the roofline denominator, measured on the same clocks.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, float a, float b)
+{
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = (float)(threadIdx.x + k);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = fmaf(v[k], a, b);
+    }
+    float sacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) sacc += v[k];
+    if (sacc == 123.456f) out[0] = sacc;
+}
+
+}  // namespace gb

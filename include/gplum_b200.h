@@ -1,0 +1,130 @@
+/*
+ * gplum_b200.h -- C ABI of libgplum_b200.so, the B200 (sm_100a) replacement for GPLUM's P3T
+ * soft-force interaction stage.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * What each entry point replaces in the reference (paths relative to the GPLUM tree):
+ *
+ *   gplum_b200_epep      calcForceEPEPWithSearch::operator()(epi,ni,epj,nj,force)
+ *                        src/gravity_kernel.hpp:12-23 (PIKG: CalcForceLongEPEP, generated from
+ *                        src/gravity_kernel_epep.pikg), incl. neighbour-candidate detection.
+ *   gplum_b200_epsp      calcForceEPSP::operator()(epi,ni,spj,nj,force)
+ *                        src/gravity_kernel.hpp:128-136 (src/gravity_kernel_epsp.pikg).
+ *   gplum_b200_dispatch  the accelerator "dispatch" functor of FDPS's multi-walk-index interface,
+ *   gplum_b200_retrieve  FDPS/src/tree_for_force_impl_force.hpp:78-83 (send all), :232-238
+ *                        (dispatch), :230,242 (retrieve); what PIKG's CUDA back-end generates as
+ *                        Dispatch<K>/Retrieve<K> (PIKG/src/CUDA.rb:336-349,466-494).
+ *   gplum_b200_calc_walks  one whole TreeForForce::calcForce pass
+ *                        (FDPS/src/tree_for_force_impl_force.hpp:1404-1564) over flat arrays:
+ *                        gather by index (CopyPjForForceST, tree_for_force_impl.hpp:652-693),
+ *                        ForceGrav::clear (src/particle.h:81-85), EP-EP, EP-SP, write-back.
+ *
+ * Struct layouts are the reference's, default macro set (USE_INDIVIDUAL_CUTOFF, USE_QUAD,
+ * cartesian): EPIGrav 48 B, EPJGrav 112 B, MySPJQuadrupole 80 B, MySPJMonopole 32 B,
+ * ForceGrav 32 B (src/particle.h:16-24,70-86,93-109,149-156; FDPS/src/tree.hpp:883-967).
+ *
+ * All pointers are HOST pointers owned by the caller unless a name says "dev".  The library
+ * owns device buffers and pinned staging and grows them on demand.  Every function returns 0 on
+ * success or a non-zero code (gplum_b200_last_error() describes it); nothing throws.  There is
+ * no CPU fallback: without a usable sm_100 device every compute call fails.
+ */
+#ifndef GPLUM_B200_H
+#define GPLUM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPLUM_B200_ABI_VERSION 1
+
+/* mode flags (gplum_b200_set_params) */
+#define GPLUM_B200_TRACE_AS_SHIPPED 1 /* tr = qxx+qyy+qxx, the non-PIKG branch's arithmetic
+                                         (src/gravity_kernel.hpp:177); default is the DSL's
+                                         qxx+qyy+qzz (src/gravity_kernel_epsp.pikg:75) */
+#define GPLUM_B200_RANK_SQUARED     2 /* rank += (ranki-rankj)^2 as in the DSL (.pikg:77-83);
+                                         default |ranki-rankj| (gravity_kernel.hpp:108) */
+#define GPLUM_B200_NO_ACCUMULATE    4 /* retrieve/epep/epsp overwrite instead of accumulating */
+
+/* error codes */
+#define GPLUM_B200_OK            0
+#define GPLUM_B200_ERR_CUDA      1
+#define GPLUM_B200_ERR_NO_DEVICE 2
+#define GPLUM_B200_ERR_ARG       3
+#define GPLUM_B200_ERR_STATE     4
+
+int gplum_b200_abi_version(void);
+const char *gplum_b200_last_error(void);
+
+/* Select the device, create streams, pre-size buffers for max_i i-particles and max_j list
+ * entries per dispatch (hints; buffers grow).  Idempotent for the same device. */
+int gplum_b200_init(int device, size_t max_i, size_t max_j);
+int gplum_b200_finalize(void);
+
+/* eps2: FP_t::eps2 narrowed to F32 (src/gravity_kernel.hpp:17,31); quad: 1 = MySPJQuadrupole
+ * (USE_QUAD), 0 = MySPJMonopole; flags: GPLUM_B200_* above. */
+int gplum_b200_set_params(float eps2, int quad, int flags);
+
+/* ---- per-call functor form (re-entrant; one stream + staging slot per calling thread) ---- */
+int gplum_b200_epep(const void *epi, int ni, const void *epj, int nj, void *force, float eps2);
+int gplum_b200_epsp(const void *epi, int ni, const void *spj, int ns, void *force, float eps2, int quad);
+
+/* ---- FDPS multi-walk-index form (called from the master thread) ----
+ * send_all != 0: upload epj_all / spj_all (n_walk is 0, list arguments ignored).
+ * send_all == 0: enqueue n_walk walks; returns as soon as the work is queued on the GPU.
+ * retrieve(tag, ...) waits for the dispatch with the same tag and accumulates into force[w]. */
+int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *ni,
+                        const int *const *adr_epj, const int *n_epj,
+                        const int *const *adr_spj, const int *n_spj,
+                        const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all,
+                        int send_all);
+int gplum_b200_retrieve(int tag, int n_walk, const int *ni, void *const *force);
+
+/* ---- flat form: one whole force pass, host buffers in, host forces out (synchronous) ----
+ * epi_off[w], ni[w]: slice of epi_all / force_all of walk w; adr_epj[epj_disp[w] .. +n_epj[w])
+ * index epj_all; same for spj.  clear != 0 overwrites force (FDPS clear=true), else accumulates. */
+int gplum_b200_calc_walks(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
+                          const int *adr_epj, const long long *epj_disp, const int *n_epj,
+                          const int *adr_spj, const long long *spj_disp, const int *n_spj,
+                          const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all,
+                          void *force_all, int clear);
+
+/* ---- device-resident form (bench / multi-GPU): upload once, run many times ----
+ * walks_upload copies lists + particles to HBM and builds the work list; walks_run launches the
+ * j-pack + force kernels on the library stream (asynchronous); walks_download synchronises
+ * and copies the n_epi_total forces back.  walks_time runs `iters` passes bracketed by CUDA
+ * events on the launching stream and returns the mean milliseconds per pass. */
+int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
+                            const int *adr_epj, const long long *epj_disp, const int *n_epj,
+                            const int *adr_spj, const long long *spj_disp, const int *n_spj,
+                            const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all);
+int gplum_b200_walks_run(int repack);
+int gplum_b200_walks_download(void *force_all);
+int gplum_b200_walks_time(int iters, int repack, float *ms_per_pass);
+/* Replace the packed j-arrays by caller-owned device buffers (e.g. the output of an NCCL
+ * all-gather); layouts are gplum_b200_packed_sizes().  Pass NULL to return to library buffers. */
+int gplum_b200_walks_set_packed_dev(const void *epj_packed_dev, int n_epj_all,
+                                    const void *spj_packed_dev, int n_spj_all);
+/* Pack n raw AoS j-particles already in HBM into the packed layout (device pointers; runs on
+ * the library stream): the per-rank step before the all-gather. */
+int gplum_b200_pack_epj_dev(const void *epj_aos_dev, int n, void *epj_packed_dev);
+int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev);
+void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes);
+
+/* Use an existing CUDA stream (cudaStream_t as void*) for the batched / device-resident
+ * forms, so that a caller's events on that stream bracket the kernels.  NULL = own stream. */
+int gplum_b200_set_stream(void *cuda_stream);
+int gplum_b200_synchronize(void);
+
+/* Counters since the last reset: kernels launched by this library, interactions evaluated
+ * (sum ni*(n_epj+n_spj), FDPS's n_interaction_ep_ep_local_ + n_interaction_ep_sp_local_). */
+void gplum_b200_counters(long long *kernel_launches, long long *n_epep, long long *n_epsp, int reset);
+
+/* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
+ * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */
+int gplum_b200_fp32_peak(int iters, float *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPLUM_B200_H */

@@ -1,0 +1,166 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+acc/phi: 1e-4 relative per particle (the reference kernel is FP32 -- BASELINE.json north_star);
+neighbour info (number, id_max, id_min, rank==0): bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+import synth
+from gplum_b200 import functors as F, structs as S
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    F.init(0)
+    F.set_params(0.0, True, 0)
+    yield
+
+
+def _load_walks(name):
+    z = np.load(os.path.join(GOLD, name))
+    w = O.Walks(*[z[k] for k in ("epi", "epi_off", "ni", "adr_epj", "epj_disp", "n_epj", "adr_spj",
+                                 "spj_disp", "n_spj", "epj_all", "spj_all")])
+    return w, z["force_ref"], float(z["eps2"])
+
+
+@pytest.mark.parametrize("ni,nj,ns,seed,eps2,n_rank", [
+    (1, 1, 1, 0, 0.0, 1), (24, 157, 166, 1, 0.0, 1), (64, 301, 200, 2, 0.0, 2), (31, 123, 60, 3, 1e-8, 3),
+    (403, 739, 228, 4, 0.0, 1), (5, 0, 0, 5, 0.0, 1), (17, 40, 0, 6, 0.0, 1), (1, 513, 7, 7, 0.0, 1),
+    (130, 33, 1, 8, 0.0, 4), (1000, 1479, 300, 9, 0.0, 1), (33, 257, 255, 10, 0.0, 1), (600, 64, 700, 11, 0.0, 2),
+])
+def test_functor_calls_vs_oracle(ni, nj, ns, seed, eps2, n_rank):
+    epi, epj, spj = synth.make_group(ni, nj, ns, seed=seed, n_rank=n_rank, dup_self=nj >= ni)
+    want1 = O.epep(epi, epj, eps2)
+    got1 = S.cleared_force(ni)
+    F.calcForceEPEPWithSearch(eps2)(epi, ni, epj, nj, got1)
+    synth.assert_force_close(got1, want1, RTOL, "epep")
+    want2 = O.epsp(epi, spj, eps2, force=want1)
+    got2 = got1.copy()
+    F.calcForceEPSP(eps2)(epi, ni, spj, ns, got2)
+    synth.assert_force_close(got2, want2, RTOL, "epep+epsp")
+
+
+def test_functor_accumulates_like_reference():
+    epi, epj, spj = synth.make_group(20, 90, 30, seed=11)
+    f0 = S.cleared_force(20)
+    f0["acc"] = 1.5; f0["phi"] = -2.0; f0["number"] = 3; f0["id_max"] = 10 ** 6; f0["id_min"] = 2
+    want = O.epep(epi, epj, 0.0, force=f0)
+    got = f0.copy()
+    F.calcForceEPEPWithSearch(0.0)(epi, 20, epj, 90, got)
+    synth.assert_force_close(got, want, RTOL, "accumulate")
+    assert (got["number"] == want["number"]).all() and (got["rank"] == want["rank"]).all()
+
+
+def test_monopole_spj():
+    epi, epj, spj = synth.make_group(50, 80, 120, seed=5)
+    mono = np.zeros(len(spj), dtype=S.SPJ_MONO)
+    mono["mass"] = spj["mass"]; mono["pos"] = spj["pos"]
+    want = O.epsp(epi, mono, 0.0)
+    got = S.cleared_force(50)
+    F.calcForceEPSP(0.0)(epi, 50, mono, len(mono), got)
+    synth.assert_force_close(got, want, RTOL, "mono")
+
+
+def test_golden_groups_as_shipped_mode():
+    """Against the compiled reference's outputs (fixtures), in its own arithmetic (tr = xx+yy+xx)."""
+    z = np.load(os.path.join(GOLD, "groups.npz"))
+    F.set_params(0.0, True, F.TRACE_AS_SHIPPED)
+    try:
+        for k in range(int(z["n_cases"])):
+            g = lambda nm: z["c%d_%s" % (k, nm)]
+            eps2 = float(g("eps2"))
+            f = g("f0").copy()
+            F.calcForceEPEPWithSearch(eps2)(g("epi"), len(g("epi")), g("epj"), len(g("epj")), f)
+            synth.assert_force_close(f, g("f_epep"), RTOL, "golden epep %d" % k)
+            assert (f["rank"] == g("f_epep")["rank"]).all()
+            F.calcForceEPSP(eps2)(g("epi"), len(g("epi")), g("spj"), len(g("spj")), f)
+            synth.assert_force_close(f, g("f_both"), RTOL, "golden both %d" % k)
+    finally:
+        F.set_params(0.0, True, 0)
+
+
+@pytest.mark.parametrize("name", ["init3000_g64.npz", "disk2k_g256.npz"])
+def test_golden_walks_flat_pass(name):
+    w, f_ref, eps2 = _load_walks(name)
+    F.set_params(eps2, True, F.TRACE_AS_SHIPPED)
+    try:
+        got = F.calc_walks(w)
+        synth.assert_force_close(got, f_ref, RTOL, name + " as-shipped")
+        assert (got["rank"] == f_ref["rank"]).all()
+    finally:
+        F.set_params(0.0, True, 0)
+    F.set_params(eps2, True, 0)
+    got = F.calc_walks(w)
+    want, _ = O.calc_walks(w, eps2, flags=O.CANONICAL)
+    synth.assert_force_close(got, want, RTOL, name + " canonical")
+
+
+def test_dispatch_retrieve_matches_flat_pass():
+    """FDPS multi-walk protocol: send-all, then batches of walks, retrieve accumulates."""
+    w, f_ref, eps2 = _load_walks("init3000_g64.npz")
+    F.set_params(eps2, True, 0)
+    want, _ = O.calc_walks(w, eps2)
+    force = S.cleared_force(len(w.epi))
+    F.dispatch(0, None, None, None, w.epj_all, w.spj_all, send_all=True)
+    batch = 40
+    for b0 in range(0, w.n_walk, batch):
+        ws = range(b0, min(b0 + batch, w.n_walk))
+        epi_l = [w.epi[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws]
+        ae_l = [w.adr_epj[w.epj_disp[k]:w.epj_disp[k] + w.n_epj[k]] for k in ws]
+        as_l = [w.adr_spj[w.spj_disp[k]:w.spj_disp[k] + w.n_spj[k]] for k in ws]
+        f_l = [force[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws]
+        F.dispatch(0, epi_l, ae_l, as_l, w.epj_all, w.spj_all)
+        F.retrieve(0, f_l)
+    synth.assert_force_close(force, want, RTOL, "dispatch/retrieve")
+
+
+def test_device_resident_pass_and_counters():
+    w, _, eps2 = _load_walks("disk2k_g256.npz")
+    F.set_params(eps2, True, 0)
+    F.counters(reset=True)
+    F.walks_upload(w)
+    F.walks_run(repack=True)
+    got = F.walks_download(len(w.epi))
+    want, n_int = O.calc_walks(w, eps2)
+    synth.assert_force_close(got, want, RTOL, "resident")
+    launches, n_ee, n_es = F.counters()
+    assert (n_ee, n_es) == w.n_interactions() and n_ee + n_es == n_int
+    assert launches >= 3          # 2 pack kernels (upload) + 2 (repack) + force
+    ms = F.walks_time(3)
+    assert ms > 0
+
+
+def test_empty_and_ragged_walks():
+    w, _, eps2 = _load_walks("init3000_g64.npz")
+    # zero-length lists for some walks; a walk with ni == 0
+    n_epj = w.n_epj.copy(); n_spj = w.n_spj.copy(); ni = w.ni.copy()
+    n_epj[3] = 0; n_spj[5] = 0; n_epj[7] = 0; n_spj[7] = 0; ni[9] = 0
+    w2 = O.Walks(w.epi, w.epi_off, ni, w.adr_epj, w.epj_disp, n_epj, w.adr_spj, w.spj_disp, n_spj,
+                 w.epj_all, w.spj_all)
+    F.set_params(eps2, True, 0)
+    base = S.cleared_force(len(w.epi)); base["phi"] = 7.0
+    got = F.calc_walks(w2, force=base.copy())
+    want, _ = O.calc_walks(w2, eps2, force=base.copy())
+    synth.assert_force_close(got, want, RTOL, "ragged")
+    k = 9
+    assert (got["phi"][w.epi_off[k]:w.epi_off[k] + w.ni[k]] == 7.0).all()     # untouched
+    k = 7
+    sl = slice(w.epi_off[k], w.epi_off[k] + w.ni[k])
+    assert got[sl].tobytes() == S.cleared_force(w.ni[k]).tobytes()             # cleared, nothing added
+
+
+def test_neighbour_flags_dense_field():
+    """Many candidates per particle (r_search comparable to the spacing), several ranks."""
+    epi, epj, spj = synth.make_group(200, 900, 0, seed=21, box=0.01, r_out=3.0e-3, n_rank=3)
+    want = O.epep(epi, epj, 0.0)
+    assert want["number"].mean() > 20
+    got = S.cleared_force(200)
+    F.calcForceEPEPWithSearch(0.0)(epi, 200, epj, 900, got)
+    synth.assert_force_close(got, want, RTOL, "dense")
+    assert (got["rank"] == want["rank"]).all()
