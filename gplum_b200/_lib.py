@@ -34,6 +34,9 @@ SYMBOLS = {
     "gplum_b200_set_stream": (_i, [_vp]),
     "gplum_b200_synchronize": (_i, []),
     "gplum_b200_counters": (None, [C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), _i]),
+    "gplum_b200_tree_build": (_i, [_i, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _vp]),
+    "gplum_b200_tree_copy": (_i, [_vp] * 11 + [_i, _i, _vp]),
+    "gplum_b200_tree_free": (None, []),
     "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
 }
 
