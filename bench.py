@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- soft-force interactions/s of the P3T force pass on B200 (BASELINE.json metric).
+
+A "step" is one force pass (TreeForForce::calcForce: j-pack + every walk's EP-EP + EP-SP +
+neighbour-candidate detection + force write) over the interaction lists of a synthetic
+Kokubo-Ida disk.  Workload at any N: configs[2], N=1e6 planetesimals in a 0.9-1.1 AU annulus,
+sample/parameter.dat tree parameters, n_group_limit per --group.
+
+  value     interactions/s with raw particles + lists resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the reference-facing C ABI (gplum_b200_dispatch/retrieve, the
+            FDPS multi-walk-index functors) with pinned HOST buffers: H2D of j-particles, walks
+            and lists, kernels, D2H of forces, all inside the timed region
+  roofline  dominant kernel (force_pass_kernel): algorithmic flop (30/EP-EP pair, 59/EP-SP pair,
+            SURVEY 8d) / its CUDA-event time, against the FP32 FFMA peak measured in the same run
+  cpu_baseline  the reference's own functors (oracle/_ref, AVX2+OpenMP build) on a bounded sample
+
+`--impl reference` times only the reference CPU path (all host threads) on the same config.
+N>1 (torchrun): walks are sharded by Morton-contiguous domains, packed j-data is exchanged with
+one NCCL all-gather per array per step (gplum_b200/shard.py); fixed total work => strong scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_EPEP, FLOP_EPSP = 30.0, 59.0
+METRIC = "soft-force interactions/s (EP-EP+EP-SP), N=1e6 disk"
+
+
+def make_workload(n, group, seed=0, a_in=0.9, a_out=1.1):
+    from gplum_b200 import disk, tree
+    t0 = time.time()
+    d = disk.make_disk(n, a_in=a_in, a_out=a_out, seed=seed)
+    r_out, r_search = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    w, order = tree.build_walks(d["pos"], d["mass"], r_out, r_search, theta=0.5, n_leaf_limit=8,
+                                n_group_limit=group)
+    return w, time.time() - t0
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        busy = [s for s in sm if s > 0.5 * (mx[0] if mx else 1)]
+        return {"sm_mhz": float(np.median(busy)) if busy else (float(np.median(sm)) if sm else None),
+                "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(w, eps2, budget_s, threads):
+    """The reference's functors on a bounded sample of the walks (every k-th walk)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    kind = "reference" if O.have_ref("simd") else "port"
+    lib = "simd" if kind == "reference" else "oracle"
+    # probe rate on a small sample, then size the real sample to the budget
+    def sample(stride):
+        idx = np.arange(0, w.n_walk, stride)
+        return O.Walks(w.epi, w.epi_off[idx], w.ni[idx], w.adr_epj, w.epj_disp[idx], w.n_epj[idx],
+                       w.adr_spj, w.spj_disp[idx], w.n_spj[idx], w.epj_all, w.spj_all)
+    tot = sum(w.n_interactions())
+    probe = sample(max(1, w.n_walk // 64))
+    t0 = time.time(); _, n_int = O.calc_walks(probe, eps2, lib=lib, n_threads=threads); dt = time.time() - t0
+    rate = n_int / max(dt, 1e-6)
+    stride = max(1, int(np.ceil(tot / (rate * budget_s))))
+    s = sample(stride)
+    return kind, s, O, lib
+
+
+def run_reference(args, w):
+    threads = os.cpu_count()
+    kind, s, O, lib = cpu_reference_run(w, 0.0, args.cpu_seconds / max(1, args.steps + args.warmup), threads)
+    for _ in range(args.warmup):
+        O.calc_walks(s, 0.0, lib=lib, n_threads=threads)
+    t0 = time.time()
+    n_int = 0
+    for _ in range(args.steps):
+        _, n = O.calc_walks(s, 0.0, lib=lib, n_threads=threads)
+        n_int += n
+    dt = time.time() - t0
+    val = n_int / dt
+    sample_desc = "%d of %d walks (every %d-th) of the same lists, %.3g interactions/step" % (
+        s.n_walk, w.n_walk, max(1, w.n_walk // max(1, s.n_walk)), n_int / args.steps)
+    return {"metric": METRIC, "value": val, "unit": "interactions/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, w),
+            "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": threads, "kind": kind, "sample": sample_desc},
+            "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def workload_config(args, w):
+    ee, es = w.n_interactions()
+    return {"workload": "Kokubo-Ida disk N=%d a=[0.9,1.1]AU (BASELINE configs[2]); theta=0.5 n_leaf_limit=8 "
+                        "n_group_limit=%d; individual cutoff, quadrupole SPJ" % (args.n, args.group),
+            "n_particles": args.n, "n_group_limit": args.group, "n_walks": int(w.n_walk),
+            "interactions_epep": ee, "interactions_epsp": es,
+            "l2": "per-step inputs (lists+particles) exceed L2 at N=1e6; no flush",
+            "parallelism": "i-groups sharded over %d GPU(s), j-data all-gathered" % args.gpus}
+
+
+def pinned_like(a):
+    import torch
+    t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+    b = t.numpy().view(a.dtype).reshape(a.shape)
+    b[...] = a
+    return b, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--group", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w, _ = make_workload(args.n, args.group)
+        print(json.dumps(run_reference(args, w)))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gplum_b200 import functors as F, structs as S
+    from gplum_b200._lib import lib, check
+    from gplum_b200.shard import Shard
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w, t_build = make_workload(args.n, args.group)
+    ee, es = w.n_interactions()
+    F.init(local_rank)
+    F.set_params(0.0, True, 0)
+    L = lib()
+    stream = torch.cuda.current_stream()
+    check(L.gplum_b200_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ------------------------------------------------------------------ device-resident passes
+    if world == 1:
+        F.walks_upload(w)
+        my_int = ee + es
+        def step():
+            F.walks_run(repack=True)
+    else:
+        sh = Shard(w, world, rank)
+        lw = sh.local
+        my_int = sum(lw.n_interactions())
+        eb, sb = C.c_int(0), C.c_int(0)
+        L.gplum_b200_packed_sizes(C.byref(eb), C.byref(sb))
+        d_epj_raw = torch.from_numpy(lw.epj_all.view(np.uint8).copy()).cuda()
+        d_spj_raw = torch.from_numpy(lw.spj_all.view(np.uint8).copy()).cuda()
+        send_e = torch.zeros(sh.epj_cap * eb.value, dtype=torch.uint8, device="cuda")
+        send_s = torch.zeros(sh.spj_cap * sb.value, dtype=torch.uint8, device="cuda")
+        gath_e = torch.zeros(world * sh.epj_cap * eb.value, dtype=torch.uint8, device="cuda")
+        gath_s = torch.zeros(world * sh.spj_cap * sb.value, dtype=torch.uint8, device="cuda")
+        empty_e = np.zeros(0, S.EPJ); empty_s = np.zeros(0, S.SPJ_QUAD)
+        lw_nj = type(lw)(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj, lw.spj_disp,
+                         lw.n_spj, empty_e, empty_s)
+        F.walks_upload(lw_nj)
+        check(L.gplum_b200_walks_set_packed_dev(C.c_void_p(gath_e.data_ptr()), world * sh.epj_cap,
+                                                C.c_void_p(gath_s.data_ptr()), world * sh.spj_cap))
+        def step():
+            check(L.gplum_b200_pack_epj_dev(C.c_void_p(d_epj_raw.data_ptr()), len(lw.epj_all), C.c_void_p(send_e.data_ptr())))
+            check(L.gplum_b200_pack_spj_dev(C.c_void_p(d_spj_raw.data_ptr()), len(lw.spj_all), C.c_void_p(send_s.data_ptr())))
+            dist.all_gather_into_tensor(gath_e, send_e)
+            dist.all_gather_into_tensor(gath_s, send_s)
+            F.walks_run(repack=False)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    F.counters(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches, c_ee, c_es = F.counters()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    n_int = torch.tensor([float(my_int)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_int, op=dist.ReduceOp.SUM)
+    ms_per_step = t_ms.item() / args.steps
+    value = n_int.item() / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------------ dominant kernel alone
+    barrier()
+    k_ms = F.walks_time(max(3, args.steps), repack=False)      # CUDA events on the launching stream
+    peak_tf, _ = F.fp32_peak(10)
+    my_ee, my_es = (ee, es) if world == 1 else sh.local.n_interactions()
+    flop = FLOP_EPEP * my_ee + FLOP_EPSP * my_es
+    achieved = flop / (k_ms * 1e-3) / 1e12
+    alg_bytes = (48 + 32) * (len(w.epi) if world == 1 else len(sh.local.epi)) + \
+        4 * ((len(w.adr_epj) + len(w.adr_spj)) if world == 1 else (len(sh.local.adr_epj) + len(sh.local.adr_spj)))
+    roofline = {"bound": "fp32", "kernel": "force_pass_kernel", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no CUDA-core figure); "
+                               "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "kernel_ms": k_ms, "flop_per_launch": flop,
+                "interactions_per_s_kernel_only": (my_ee + my_es) / (k_ms * 1e-3),
+                "gflops_38flop_convention": 38.0 * (my_ee + my_es) / (k_ms * 1e-3) / 1e9,
+                "list_bytes_per_launch": alg_bytes}
+
+    # ------------------------------------------------------------------ end to end via the C ABI
+    check(L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
+    if world == 1:
+        lw = w
+    else:
+        # each rank ships its own walks; j-particles of the whole system (reference: LET) from host
+        lw = type(w)(w.epi[sh.epi_range[0]:sh.epi_range[1]], sh.local.epi_off, sh.local.ni,
+                     w.adr_epj[sh.adr_epj_range[0]:sh.adr_epj_range[1]], sh.local.epj_disp, sh.local.n_epj,
+                     w.adr_spj[sh.adr_spj_range[0]:sh.adr_spj_range[1]], sh.local.spj_disp, sh.local.n_spj,
+                     w.epj_all, w.spj_all)
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    p_epi, p_epj, p_spj = pin(lw.epi), pin(lw.epj_all), pin(lw.spj_all)
+    p_ae, p_as = pin(lw.adr_epj), pin(lw.adr_spj)
+    p_force = pin(S.cleared_force(len(lw.epi)))
+    epi_l = [p_epi[lw.epi_off[k]:lw.epi_off[k] + lw.ni[k]] for k in range(lw.n_walk)]
+    ae_l = [p_ae[lw.epj_disp[k]:lw.epj_disp[k] + lw.n_epj[k]] for k in range(lw.n_walk)]
+    as_l = [p_as[lw.spj_disp[k]:lw.spj_disp[k] + lw.n_spj[k]] for k in range(lw.n_walk)]
+    f_l = [p_force[lw.epi_off[k]:lw.epi_off[k] + lw.ni[k]] for k in range(lw.n_walk)]
+    nw = lw.n_walk
+    c_epi = (C.c_void_p * nw)(*[a.ctypes.data for a in epi_l])
+    c_ae = (C.c_void_p * nw)(*[a.ctypes.data for a in ae_l])
+    c_as = (C.c_void_p * nw)(*[a.ctypes.data for a in as_l])
+    c_f = (C.c_void_p * nw)(*[a.ctypes.data for a in f_l])
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    F.set_params(0.0, True, F.NO_ACCUMULATE)     # FDPS clear=true: forces are overwritten
+
+    def e2e_step():
+        check(L.gplum_b200_dispatch(0, 0, None, None, None, None, None, None, vp(p_epj), len(p_epj), vp(p_spj), len(p_spj), 1))
+        check(L.gplum_b200_dispatch(0, nw, c_epi, vp(lw.ni), c_ae, vp(lw.n_epj), c_as, vp(lw.n_spj),
+                                    vp(p_epj), len(p_epj), vp(p_spj), len(p_spj), 0))
+        check(L.gplum_b200_retrieve(0, nw, vp(lw.ni), c_f))
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    n_e2e = max(3, args.steps // 4)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    h2d = p_epi.nbytes + p_epj.nbytes + p_spj.nbytes + p_ae.nbytes + p_as.nbytes + nw * 28
+    d2h = p_force.nbytes
+    e2e = {"value": n_int.item() / t_e2e.item(), "unit": "interactions/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e.item() * 1e3,
+           "api": "gplum_b200_dispatch(send_all) + gplum_b200_dispatch(walks) + gplum_b200_retrieve, pinned host buffers"}
+    F.set_params(0.0, True, 0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    out = {"metric": METRIC, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, w),
+           "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+           "list_build_s_host": t_build}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count()
+        kind, s, O, libname = cpu_reference_run(w, 0.0, args.cpu_seconds, threads)
+        t0 = time.time(); _, n = O.calc_walks(s, 0.0, lib=libname, n_threads=threads); dt = time.time() - t0
+        out["cpu_baseline"] = {"value": n / dt, "unit": "interactions/s", "cores": threads, "kind": kind,
+                               "sample": "%d of %d walks of the same lists (%.3g interactions, %.1f s)" % (s.n_walk, w.n_walk, n, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,69 @@
+"""Multi-GPU partition of one force pass: i-groups sharded by spatial domain, j-data exchanged by
+one all-gather (the B200 replacement of FDPS's LET exchange,
+FDPS/src/tree_for_force_impl_exlet.hpp:343-403: allGather + 2x allToAllV of EPJ/SPJ).
+
+Walks are in Morton order, so a contiguous range of walks is a compact spatial domain (what
+`dinfo.decomposeDomainAll` gives each MPI rank in the reference).  Rank r owns
+  * the i-particles / forces of walks [w0_r, w1_r)          -> no collective on the i side
+  * the j-particles of the same Morton range (its "domain") -> packed locally, all-gathered
+  * an equal slice of the tree cells (superparticles)       -> packed locally, all-gathered
+The all-gather buffer is slab-padded (every rank contributes `cap` records) so one
+`all_gather_into_tensor` moves everything; list indices are remapped once to the padded layout.
+"""
+import numpy as np
+
+from .walks import Walks
+
+
+def split_walks(w, world):
+    """Contiguous walk ranges with ~equal interaction counts.  Returns [(w0, w1)] * world."""
+    cost = w.ni.astype(np.int64) * (w.n_epj.astype(np.int64) * 20 + w.n_spj.astype(np.int64) * 38)
+    c = np.cumsum(cost)
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(c, c[-1] * r / world)))
+    bounds.append(w.n_walk)
+    for r in range(1, world + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+class Shard:
+    """Everything rank `rank` needs: its walks (re-indexed to the padded gather layout), the
+    range of j-particles / cells it packs, and the padded slab sizes."""
+
+    def __init__(self, w, world, rank):
+        self.world, self.rank = world, rank
+        ranges = split_walks(w, world)
+        # particle (EPJ) ownership = Morton range of the rank's i-particles
+        p_lo = [int(w.epi_off[a]) if a < w.n_walk else len(w.epi) for a, _ in ranges]
+        p_lo[0] = 0
+        p_hi = p_lo[1:] + [len(w.epj_all)]
+        self.epj_ranges = list(zip(p_lo, p_hi))
+        n_sp = len(w.spj_all)
+        s_lo = [(n_sp * r) // world for r in range(world)]
+        self.spj_ranges = list(zip(s_lo, s_lo[1:] + [n_sp]))
+        self.epj_cap = max(b - a for a, b in self.epj_ranges)
+        self.spj_cap = max(1, max(b - a for a, b in self.spj_ranges))
+        self.walk_range = ranges[rank]
+        w0, w1 = ranges[rank]
+        e0 = int(w.epi_off[w0]) if w0 < w.n_walk else len(w.epi)
+        e1 = int(w.epi_off[w1 - 1] + w.ni[w1 - 1]) if w1 > w0 else e0
+        self.epi_range = (e0, e1)
+        a0 = int(w.epj_disp[w0]) if w1 > w0 else 0
+        a1 = int(w.epj_disp[w1 - 1] + w.n_epj[w1 - 1]) if w1 > w0 else 0
+        s0 = int(w.spj_disp[w0]) if w1 > w0 else 0
+        s1 = int(w.spj_disp[w1 - 1] + w.n_spj[w1 - 1]) if w1 > w0 else 0
+        self.adr_epj_range, self.adr_spj_range = (a0, a1), (s0, s1)
+        self.local = Walks(w.epi[e0:e1], w.epi_off[w0:w1] - e0, w.ni[w0:w1],
+                           self.remap(w.adr_epj[a0:a1], self.epj_ranges, self.epj_cap), w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
+                           self.remap(w.adr_spj[s0:s1], self.spj_ranges, self.spj_cap), w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
+                           w.epj_all[self.epj_ranges[rank][0]:self.epj_ranges[rank][1]],
+                           w.spj_all[self.spj_ranges[rank][0]:self.spj_ranges[rank][1]])
+
+    @staticmethod
+    def remap(adr, ranges, cap):
+        """global index -> index in the slab-padded all-gather buffer (rank r's slab at r*cap)."""
+        lo = np.array([a for a, _ in ranges], dtype=np.int64)
+        owner = np.searchsorted(lo, adr, side="right") - 1
+        return (adr - lo[owner] + owner * cap).astype(np.int32)
