@@ -176,7 +176,8 @@ def main():
     F.init(local_rank)
     F.set_params(0.0, True, 0)
     L = lib()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: library kernels, NCCL and the
+    torch.cuda.set_stream(stream)         # timing events all go through it
     check(L.gplum_b200_set_stream(C.c_void_p(stream.cuda_stream)))
 
     def barrier():

@@ -136,15 +136,11 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
         const double cost_j = 20.0 * n_epj[w] + 38.0 * n_spj[w] + 64.0;
         while (rem > 0) {
             int cfg;
-            if (rem >= 512) cfg = 4;
-            else if (rem > 256 && rem > 448) cfg = 4;
-            else if (rem >= 256) cfg = 3;
-            else if (rem > 224) cfg = 3;
-            else if (rem >= 128) cfg = 2;
-            else if (rem > 96) cfg = 2;
-            else if (rem >= 64) cfg = 1;
-            else if (rem > 32) cfg = 1;
-            else cfg = 0;
+            if (rem > 224) cfg = 3;            // 256-wide tile (also used repeatedly for big groups)
+            else if (rem > 96) cfg = 2;        // 128
+            else if (rem > 32) cfg = 1;        // 64
+            else cfg = 0;                      // 32
+            if (rem > 128 && rem <= 160) cfg = 2;   // 128 + a 32-wide remainder beats one 256
             const int tile = cfg_tile(cfg);
             const int n = std::min(rem, tile);
             tmp.push_back({cost_j * tile, WorkItem{w, i0, n, cfg}});

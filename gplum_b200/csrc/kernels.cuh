@@ -23,7 +23,6 @@ namespace gb {
 
 constexpr int NT = 256;        // threads per CTA
 constexpr int JT = 256;        // j-particles staged per tile
-constexpr int JPAD = 64;       // slack for per-slice round-up
 constexpr int UNROLL = 4;
 
 // ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
@@ -137,32 +136,50 @@ __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *_
 }
 
 // ------------------------------------------------------------------------------------------
-// shared-memory carve-up (dynamic): sized for the largest i-tile (IT_MAX)
+// force pass: shared-memory layout (dynamic), sized for the largest i-tile
 // ------------------------------------------------------------------------------------------
-constexpr int IT_MAX = 512;
+constexpr int IT_MAX = 256;
+struct JTile {                 // one staged j-tile, FP32, already shifted by the group origin
+    float4 j4[JT];             // dx,dy,dz,m
+    union {
+        struct { float rout2[JT]; float rs2[JT]; int id[JT]; int rank[JT]; } ep;
+        struct { float4 q0[JT]; float4 q1[JT]; } sp;   // Qxx,Qyy,Qzz,Qxy | Qyz,Qzx,mtr,-
+    };
+    float wmax[NT / 32];       // per-warp max of rs2 over the tile (EP)
+    int pad_[8];
+};
 struct SmemLayout {
-    float4 j4[JT + JPAD];      // EP: dx,dy,dz,m      SP: dx,dy,dz,m
-    float4 q0[JT + JPAD];      // SP: Qxx,Qyy,Qzz,Qxy
-    float4 q1[JT + JPAD];      // SP: Qyz,Qzx,mtr,-
-    float rout2[JT + JPAD];
-    float rs2[JT + JPAD];
-    int id[JT + JPAD];
-    int rank[JT + JPAD];
-    float4 ipos[IT_MAX];       // xi,yi,zi,rout2_i  (later: cross-slice reduction scratch)
+    JTile tile[2];             // double buffer: compute on one while the next is staged
+    float4 raw[JT * 4];        // cp.async landing zone: the packed 48/64-byte records of the next tile
+    float4 ipos[IT_MAX];       // xi,yi,zi,rout2_i
     float i_rs2[IT_MAX];
     int i_id[IT_MAX];
     int i_rank[IT_MAX];
     int nb_number[IT_MAX], nb_rank[IT_MAX], nb_idmax[IT_MAX], nb_idmin[IT_MAX];
-    float4 red[NT * 4];        // [slice][i] partial sums (JS*IT = NT*R <= NT*4)
-    int tmax[2];
 };
+// the cross-slice reduction scratch ([slice][i] float4, JS*IT = NT*R <= 512 entries) aliases tile[]
+static_assert(sizeof(JTile) * 2 >= sizeof(float4) * NT * 2, "reduction scratch must fit in the tile buffers");
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// One work item: an i-tile of one walk against the walk's EP list, then its SP list.
+// Threads: LANES_I lanes x R i-particles each form one j-slice; NT/LANES_I slices split every j-tile.
+// Staging pipeline per j-tile t (EP tiles first, then SP tiles, one sequence):
+//   cp.async(records of tile t+1 -> raw)  |  compute tile t  |  wait, convert raw -> tile[(t+1)&1], sync
 template <int R, int LANES_I>
 __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem it, SmemLayout &s)
 {
     constexpr int JS = NT / LANES_I;     // j-slices
     constexpr int IT = R * LANES_I;      // i-particles per tile
-    static_assert(IT <= IT_MAX && JS * UNROLL <= JPAD && JS * IT <= NT * 4, "tile shape");
+    static_assert(IT <= IT_MAX && (JT / JS) % UNROLL == 0, "tile shape");
     const int tid = threadIdx.x;
     const int slice = tid / LANES_I;
     const int lane_i = tid % LANES_I;
@@ -172,8 +189,71 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
     // FP64 origin of the group: epi[0].pos (gravity_kernel_epep.pikg:53 "xi - xi[0]")
     const double ox = epi0->pos[0], oy = epi0->pos[1], oz = epi0->pos[2];
     const float eps2 = p.eps2;
+    const int nj_ep = p.n_epj[w], nj_sp = p.n_spj[w];
+    const int *adr_ep = p.adr_epj + p.epj_disp[w];
+    const int *adr_sp = p.adr_spj + p.spj_disp[w];
+    const int nt_ep = (nj_ep + JT - 1) / JT, nt_sp = (nj_sp + JT - 1) / JT;
+    const int nt = nt_ep + nt_sp;
 
-    // ---- stage the i-tile ----
+    // index of this thread's slot in tile t (or -1: padding)
+    auto slot_index = [&](int t) -> int {
+        if (t < nt_ep) { const int j = t * JT + tid; return j < nj_ep ? adr_ep[j] : -1; }
+        if (t < nt) { const int j = (t - nt_ep) * JT + tid; return j < nj_sp ? adr_sp[j] : -1; }
+        return -1;
+    };
+    auto issue = [&](int t, int idx) {      // async copy of the packed record into raw[tid*4..]
+        if (idx < 0) return;
+        if (t < nt_ep) {
+            const char *q = reinterpret_cast<const char *>(p.epj + idx);
+            cp_async16(&s.raw[tid * 4 + 0], q); cp_async16(&s.raw[tid * 4 + 1], q + 16); cp_async16(&s.raw[tid * 4 + 2], q + 32);
+        } else {
+            const char *q = reinterpret_cast<const char *>(p.spj + idx);
+            cp_async16(&s.raw[tid * 4 + 0], q); cp_async16(&s.raw[tid * 4 + 1], q + 16);
+            cp_async16(&s.raw[tid * 4 + 2], q + 32); cp_async16(&s.raw[tid * 4 + 3], q + 48);
+        }
+    };
+    auto convert = [&](int t, int idx) {    // raw record -> FP32 tile entry, shifted by the origin in FP64
+        JTile &T = s.tile[t & 1];
+        if (t < nt_ep) {
+            float rs2v = 0.0f;
+            if (idx >= 0) {
+                const double2 a = *reinterpret_cast<const double2 *>(&s.raw[tid * 4 + 0]);
+                const float4 bq = s.raw[tid * 4 + 1];
+                const float4 c = s.raw[tid * 4 + 2];
+                const double z = __hiloint2double(__float_as_int(bq.y), __float_as_int(bq.x));
+                T.j4[tid] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(z - oz), bq.z);
+                T.ep.rout2[tid] = bq.w; T.ep.rs2[tid] = c.x;
+                T.ep.id[tid] = __float_as_int(c.y); T.ep.rank[tid] = __float_as_int(c.z);
+                rs2v = c.x;
+            } else {                          // padding: massless, far away, never a candidate
+                T.j4[tid] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
+                T.ep.rout2[tid] = 0.0f; T.ep.rs2[tid] = 0.0f; T.ep.id[tid] = -1; T.ep.rank[tid] = 0;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rs2v = fmaxf(rs2v, __shfl_xor_sync(0xffffffffu, rs2v, o));
+            if ((tid & 31) == 0) T.wmax[tid >> 5] = rs2v;
+        } else {
+            if (idx >= 0) {
+                const double2 a = *reinterpret_cast<const double2 *>(&s.raw[tid * 4 + 0]);
+                const float4 bq = s.raw[tid * 4 + 1];
+                const float4 c = s.raw[tid * 4 + 2];
+                const float4 d = s.raw[tid * 4 + 3];
+                const double z = __hiloint2double(__float_as_int(bq.y), __float_as_int(bq.x));
+                T.j4[tid] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(z - oz), bq.z);
+                T.sp.q0[tid] = make_float4(bq.w, c.x, c.y, c.z);   // Qxx Qyy Qzz Qxy
+                T.sp.q1[tid] = make_float4(c.w, d.x, d.y, 0.0f);   // Qyz Qzx mtr
+            } else {
+                T.j4[tid] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
+                T.sp.q0[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                T.sp.q1[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+
+    // ---- prologue: start the first j-tile, stage the i-tile meanwhile ----
+    int idx_cur = slot_index(0);
+    issue(0, idx_cur);
+    int idx_nxt = slot_index(1);
     for (int i = tid; i < IT; i += NT) {
         if (i < it.ni) {
             const EpiAos &e = p.epi[ibase + i];
@@ -188,10 +268,11 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
         }
         s.nb_number[i] = 0; s.nb_rank[i] = 0; s.nb_idmax[i] = -1; s.nb_idmin[i] = 2147483647;
     }
-    if (tid < 2) s.tmax[tid] = 0;
+    cp_async_commit_wait_all();
+    if (nt > 0) convert(0, idx_cur);
     __syncthreads();
 
-    float xi[R], yi[R], zi[R], ro2i[R], rs2i[R], Ti[R];
+    float xi[R], yi[R], zi[R], ro2i[R], rs2i[R];
     float ax[R], ay[R], az[R], ph[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -201,54 +282,32 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
         ax[r] = ay[r] = az[r] = ph[r] = 0.0f;
     }
 
-    // =============================== EP-EP ===============================
-    {
-        const int nj = p.n_epj[w];
-        const int *adr = p.adr_epj + p.epj_disp[w];
-        int par = 0;
-        for (int tb = 0; tb < nj; tb += JT, par ^= 1) {
-            const int n_t = min(JT, nj - tb);
-            const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;   // per-slice, padded
-            const int n_slot = jps * JS;
-            __syncthreads();                      // previous tile fully consumed
-            float wmax = 0.0f;
-            for (int sl = tid; sl < n_slot; sl += NT) {
-                if (sl < n_t) {
-                    const EpjPacked *q = p.epj + adr[tb + sl];
-                    const double2 a = ldg_d2(q);
-                    const double2 b = ldg_d2(reinterpret_cast<const char *>(q) + 16);
-                    const float4 c = ldg_f4(reinterpret_cast<const char *>(q) + 32);
-                    const float m = __int_as_float((int)(__double_as_longlong(b.y) & 0xffffffffLL));
-                    const float ro2 = __int_as_float((int)(__double_as_longlong(b.y) >> 32));
-                    s.j4[sl] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(b.x - oz), m);
-                    s.rout2[sl] = ro2;
-                    s.rs2[sl] = c.x;
-                    s.id[sl] = __float_as_int(c.y);
-                    s.rank[sl] = __float_as_int(c.z);
-                    wmax = fmaxf(wmax, c.x);
-                } else {                          // padding: massless, far away, never a candidate
-                    s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
-                    s.rout2[sl] = 0.0f; s.rs2[sl] = 0.0f; s.id[sl] = -1; s.rank[sl] = 0;
-                }
-            }
+    for (int t = 0; t < nt; t++) {
+        // stage tile t+1 while computing tile t
+        idx_cur = idx_nxt;
+        issue(t + 1, idx_cur);
+        idx_nxt = slot_index(t + 2);
+        const JTile &T = s.tile[t & 1];
+        const bool is_ep = t < nt_ep;
+        const int n_t = is_ep ? min(JT, nj_ep - t * JT) : min(JT, nj_sp - (t - nt_ep) * JT);
+        const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;   // per-slice count, padded
+        const int jb = slice * jps;
+        if (is_ep) {
+            // =============================== EP-EP ===============================
+            float tmax = 0.0f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-            if ((tid & 31) == 0) atomicMax(&s.tmax[par], __float_as_int(wmax));
-            __syncthreads();
-            if (tid == 0) s.tmax[par ^ 1] = 0;
-            // conservative candidate threshold for this tile (exact test happens in the rare path)
-            const float tmax = __int_as_float(s.tmax[par]) * 1.0000153f;
+            for (int k = 0; k < NT / 32; k++) tmax = fmaxf(tmax, T.wmax[k]);
+            tmax *= 1.0000153f;           // conservative candidate threshold (exact test in the rare path)
+            float Ti[R];
 #pragma unroll
             for (int r = 0; r < R; r++) Ti[r] = (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax);
-
-            const int jb = slice * jps;
 #pragma unroll 1
             for (int jj = 0; jj < jps; jj += UNROLL) {
                 bool hit = false;
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    const float4 pj = s.j4[jb + jj + u];
-                    const float ro2 = s.rout2[jb + jj + u];
+                    const float4 pj = T.j4[jb + jj + u];
+                    const float ro2 = T.ep.rout2[jb + jj + u];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
@@ -256,8 +315,8 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                         hit |= (r2 < Ti[r]);
                         const float r2c = fmax3(r2, ro2i[r], ro2);
                         float y = rsqrt_approx(r2c);
-                        const float t = fmaf(-r2c, y * y, 3.0f);
-                        y *= t * 0.5f;
+                        const float tt = fmaf(-r2c, y * y, 3.0f);
+                        y *= tt * 0.5f;
                         const float mr = pj.w * y;
                         const float mr3 = (y * y) * mr;
                         ax[r] = fmaf(mr3, dx, ax[r]);
@@ -266,21 +325,20 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                         ph[r] -= mr;
                     }
                 }
-                if (hit) {
+                if (__any_sync(0xffffffffu, hit)) {
                     // exact re-test, reference evaluation order, no FMA contraction
                     for (int u = 0; u < UNROLL; u++) {
                         const int j = jb + jj + u;
-                        const float4 pj = s.j4[j];
+                        const float4 pj = T.j4[j];
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const int il = lane_i + r * LANES_I;
-                            if (rs2i[r] < 0.0f) continue;
                             const float dx = xi[r] - pj.x, dy = yi[r] - pj.y, dz = zi[r] - pj.z;
                             const float r2e = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
                                                                   __fmul_rn(dz, dz)), eps2);
-                            const float rs2 = fmaxf(rs2i[r], s.rs2[j]);
-                            if (r2e < rs2) {
-                                const int idj = s.id[j], rkj = s.rank[j];
+                            const float rs2 = fmaxf(rs2i[r], T.ep.rs2[j]);
+                            if (rs2i[r] >= 0.0f && r2e < rs2) {
+                                const int idj = T.ep.id[j], rkj = T.ep.rank[j];
                                 const int idi = s.i_id[il], rki = s.i_rank[il];
                                 if (idi != idj || rki != rkj) {
                                     const int dr = rki - rkj;
@@ -294,52 +352,22 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                     }
                 }
             }
-        }
-    }
-
-    // =============================== EP-SP ===============================
-    {
-        const int nj = p.n_spj[w];
-        const int *adr = p.adr_spj + p.spj_disp[w];
-        for (int tb = 0; tb < nj; tb += JT) {
-            const int n_t = min(JT, nj - tb);
-            const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;
-            const int n_slot = jps * JS;
-            __syncthreads();
-            for (int sl = tid; sl < n_slot; sl += NT) {
-                if (sl < n_t) {
-                    const SpjPacked *q = p.spj + adr[tb + sl];
-                    const double2 a = ldg_d2(q);
-                    const double2 b = ldg_d2(reinterpret_cast<const char *>(q) + 16);
-                    const float4 c = ldg_f4(reinterpret_cast<const char *>(q) + 32);
-                    const float4 d = ldg_f4(reinterpret_cast<const char *>(q) + 48);
-                    const float m = __int_as_float((int)(__double_as_longlong(b.y) & 0xffffffffLL));
-                    const float qxx = __int_as_float((int)(__double_as_longlong(b.y) >> 32));
-                    s.j4[sl] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(b.x - oz), m);
-                    s.q0[sl] = make_float4(qxx, c.x, c.y, c.z);      // Qxx Qyy Qzz Qxy
-                    s.q1[sl] = make_float4(c.w, d.x, d.y, 0.0f);     // Qyz Qzx mtr
-                } else {
-                    s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
-                    s.q0[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    s.q1[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            __syncthreads();
-            const int jb = slice * jps;
+        } else {
+            // =============================== EP-SP ===============================
 #pragma unroll 1
             for (int jj = 0; jj < jps; jj += UNROLL) {
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    const float4 pj = s.j4[jb + jj + u];
-                    const float4 qa = s.q0[jb + jj + u];
-                    const float4 qb = s.q1[jb + jj + u];
+                    const float4 pj = T.j4[jb + jj + u];
+                    const float4 qa = T.sp.q0[jb + jj + u];
+                    const float4 qb = T.sp.q1[jb + jj + u];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
                         float y = rsqrt_approx(r2);
-                        const float t = fmaf(-r2, y * y, 3.0f);
-                        y *= t * 0.5f;
+                        const float tt = fmaf(-r2, y * y, 3.0f);
+                        y *= tt * 0.5f;
                         const float y2 = y * y, y3 = y2 * y, y4 = y2 * y2, y5 = y2 * y3;
                         const float qrx = fmaf(qb.y, dz, fmaf(qa.w, dy, qa.x * dx));   // Qxx dx + Qxy dy + Qzx dz
                         const float qry = fmaf(qa.w, dx, fmaf(qb.x, dz, qa.y * dy));   // Qyy dy + Qyz dz + Qxy dx
@@ -356,18 +384,22 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                 }
             }
         }
+        // tile t+1 has landed in raw (it had the whole compute phase to do so): convert it
+        cp_async_commit_wait_all();
+        if (t + 1 < nt) convert(t + 1, idx_cur);
+        __syncthreads();
     }
 
     // ---- cross-slice reduction (fixed order) and write-back: ForceGrav::clear + accumulate ----
-    __syncthreads();
+    float4 *red = reinterpret_cast<float4 *>(&s.tile[0]);
 #pragma unroll
-    for (int r = 0; r < R; r++) s.red[slice * IT + lane_i + r * LANES_I] = make_float4(ax[r], ay[r], az[r], ph[r]);
+    for (int r = 0; r < R; r++) red[slice * IT + lane_i + r * LANES_I] = make_float4(ax[r], ay[r], az[r], ph[r]);
     __syncthreads();
     for (int i = tid; i < it.ni; i += NT) {
-        float4 a = s.red[i];
+        float4 a = red[i];
 #pragma unroll
         for (int sl = 1; sl < JS; sl++) {
-            const float4 b = s.red[sl * IT + i];
+            const float4 b = red[sl * IT + i];
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
         float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
@@ -376,10 +408,10 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
     }
 }
 
-// cfg -> (R, LANES_I):  0:(1,32) 1:(2,32) 2:(2,64) 3:(2,128) 4:(4,128)
-__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : cfg == 1 ? 64 : cfg == 2 ? 128 : cfg == 3 ? 256 : 512; }
+// cfg -> (R, LANES_I):  0:(1,32) 1:(2,32) 2:(2,64) 3:(2,128)
+__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : cfg == 1 ? 64 : cfg == 2 ? 128 : 256; }
 
-__global__ void __launch_bounds__(NT, 2) force_pass_kernel(const PassParams p)
+__global__ void __launch_bounds__(NT, 3) force_pass_kernel(const PassParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout &s = *reinterpret_cast<SmemLayout *>(smem_raw);
@@ -388,8 +420,7 @@ __global__ void __launch_bounds__(NT, 2) force_pass_kernel(const PassParams p)
         case 0: tile_force<1, 32>(p, it, s); break;
         case 1: tile_force<2, 32>(p, it, s); break;
         case 2: tile_force<2, 64>(p, it, s); break;
-        case 3: tile_force<2, 128>(p, it, s); break;
-        default: tile_force<4, 128>(p, it, s); break;
+        default: tile_force<2, 128>(p, it, s); break;
     }
 }
 
