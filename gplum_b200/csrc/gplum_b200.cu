@@ -135,12 +135,7 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
         int rem = ni[w], i0 = 0;
         const double cost_j = 20.0 * n_epj[w] + 38.0 * n_spj[w] + 64.0;
         while (rem > 0) {
-            int cfg;
-            if (rem > 224) cfg = 3;            // 256-wide tile (also used repeatedly for big groups)
-            else if (rem > 96) cfg = 2;        // 128
-            else if (rem > 32) cfg = 1;        // 64
-            else cfg = 0;                      // 32
-            if (rem > 128 && rem <= 160) cfg = 2;   // 128 + a 32-wide remainder beats one 256
+            const int cfg = rem > 32 ? 1 : 0;   // one warp: 64 i-particles (R=2) or <=32 (R=1)
             const int tile = cfg_tile(cfg);
             const int n = std::min(rem, tile);
             tmp.push_back({cost_j * tile, WorkItem{w, i0, n, cfg}});
@@ -165,7 +160,7 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
     p.items = (const WorkItem *)ws.items.p;
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
-    force_pass_kernel<<<ws.n_items, NT, g.smem_bytes, st>>>(p);
+    force_pass_kernel<<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
     CU(cudaGetLastError());
     g.launches++;
     g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp;
@@ -339,7 +334,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.items = (const WorkItem *)(dm + sizeof(Meta));
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
-    force_pass_kernel<<<(int)items.size(), NT, g.smem_bytes, s.st>>>(p);
+    force_pass_kernel<<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     CU(cudaGetLastError());
     g.launches++;
     if (which == 0) g.n_epep += (long long)ni * nj; else g.n_epsp += (long long)ni * nj;
@@ -375,7 +370,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
         return fail(GPLUM_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    g.smem_bytes = (int)sizeof(SmemLayout);
+    g.smem_bytes = (int)sizeof(WarpSmem) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
     g.device = device;
     if (max_i) {

@@ -21,8 +21,6 @@
 
 namespace gb {
 
-constexpr int NT = 256;        // threads per CTA
-constexpr int JT = 256;        // j-particles staged per tile
 constexpr int UNROLL = 4;
 
 // ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
@@ -136,29 +134,28 @@ __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *_
 }
 
 // ------------------------------------------------------------------------------------------
-// force pass: shared-memory layout (dynamic), sized for the largest i-tile
+// force pass.  Every WARP is independent: it owns up to 32*R i-particles of one walk (one per
+// lane and register slot), streams that walk's EP list and then its SP list through a private
+// shared-memory tile of JW j-particles, and writes its forces.  No block-level barrier exists
+// in the kernel; a CTA is only a container of WPB warps.
+//   staging pipeline per j-tile t (EP tiles first, then SP tiles, one sequence):
+//     cp.async(packed records of tile t+1 -> raw)  |  compute tile t  |  wait, convert raw -> tile
+//   convert = FP64 subtract of the group origin, narrow to FP32 (gravity_kernel_epep.pikg:53-64)
 // ------------------------------------------------------------------------------------------
-constexpr int IT_MAX = 256;
-struct JTile {                 // one staged j-tile, FP32, already shifted by the group origin
-    float4 j4[JT];             // dx,dy,dz,m
+constexpr int WPB = 4;         // warps per CTA
+constexpr int JW = 64;         // j-particles per warp tile (2 per lane)
+constexpr int IW = 64;         // max i-particles per warp (R = 2)
+struct WarpSmem {
+    float4 raw[JW * 4];        // cp.async landing zone: 64 B per j (EP records use 48)
+    float4 j4[JW];             // dx,dy,dz,m
     union {
-        struct { float rout2[JT]; float rs2[JT]; int id[JT]; int rank[JT]; } ep;
-        struct { float4 q0[JT]; float4 q1[JT]; } sp;   // Qxx,Qyy,Qzz,Qxy | Qyz,Qzx,mtr,-
+        struct { float rout2[JW]; float rs2[JW]; int id[JW]; int rank[JW]; } ep;
+        struct { float4 q0[JW]; float4 q1[JW]; } sp;   // Qxx,Qyy,Qzz,Qxy | Qyz,Qzx,mtr,-
     };
-    float wmax[NT / 32];       // per-warp max of rs2 over the tile (EP)
-    int pad_[8];
+    float i_rs2[IW];
+    int i_id[IW], i_rank[IW];
+    int nb_number[IW], nb_rank[IW], nb_idmax[IW], nb_idmin[IW];
 };
-struct SmemLayout {
-    JTile tile[2];             // double buffer: compute on one while the next is staged
-    float4 raw[JT * 4];        // cp.async landing zone: the packed 48/64-byte records of the next tile
-    float4 ipos[IT_MAX];       // xi,yi,zi,rout2_i
-    float i_rs2[IT_MAX];
-    int i_id[IT_MAX];
-    int i_rank[IT_MAX];
-    int nb_number[IT_MAX], nb_rank[IT_MAX], nb_idmax[IT_MAX], nb_idmin[IT_MAX];
-};
-// the cross-slice reduction scratch ([slice][i] float4, JS*IT = NT*R <= 512 entries) aliases tile[]
-static_assert(sizeof(JTile) * 2 >= sizeof(float4) * NT * 2, "reduction scratch must fit in the tile buffers");
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 {
@@ -170,19 +167,10 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// One work item: an i-tile of one walk against the walk's EP list, then its SP list.
-// Threads: LANES_I lanes x R i-particles each form one j-slice; NT/LANES_I slices split every j-tile.
-// Staging pipeline per j-tile t (EP tiles first, then SP tiles, one sequence):
-//   cp.async(records of tile t+1 -> raw)  |  compute tile t  |  wait, convert raw -> tile[(t+1)&1], sync
-template <int R, int LANES_I>
-__device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem it, SmemLayout &s)
+template <int R>
+__device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem it, WarpSmem &s)
 {
-    constexpr int JS = NT / LANES_I;     // j-slices
-    constexpr int IT = R * LANES_I;      // i-particles per tile
-    static_assert(IT <= IT_MAX && (JT / JS) % UNROLL == 0, "tile shape");
-    const int tid = threadIdx.x;
-    const int slice = tid / LANES_I;
-    const int lane_i = tid % LANES_I;
+    const int lane = threadIdx.x & 31;
     const int w = it.walk;
     const int ibase = p.epi_off[w] + it.i0;
     const EpiAos *epi0 = p.epi + p.epi_off[w];
@@ -192,122 +180,107 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
     const int nj_ep = p.n_epj[w], nj_sp = p.n_spj[w];
     const int *adr_ep = p.adr_epj + p.epj_disp[w];
     const int *adr_sp = p.adr_spj + p.spj_disp[w];
-    const int nt_ep = (nj_ep + JT - 1) / JT, nt_sp = (nj_sp + JT - 1) / JT;
+    const int nt_ep = (nj_ep + JW - 1) / JW, nt_sp = (nj_sp + JW - 1) / JW;
     const int nt = nt_ep + nt_sp;
 
-    // index of this thread's slot in tile t (or -1: padding)
-    auto slot_index = [&](int t) -> int {
-        if (t < nt_ep) { const int j = t * JT + tid; return j < nj_ep ? adr_ep[j] : -1; }
-        if (t < nt) { const int j = (t - nt_ep) * JT + tid; return j < nj_sp ? adr_sp[j] : -1; }
+    // list index of slot (lane + 32k) of tile t, or -1 for padding
+    auto slot_index = [&](int t, int k) -> int {
+        if (t < nt_ep) { const int j = t * JW + lane + 32 * k; return j < nj_ep ? adr_ep[j] : -1; }
+        if (t < nt) { const int j = (t - nt_ep) * JW + lane + 32 * k; return j < nj_sp ? adr_sp[j] : -1; }
         return -1;
     };
-    auto issue = [&](int t, int idx) {      // async copy of the packed record into raw[tid*4..]
+    auto issue = [&](int t, int k, int idx) {
         if (idx < 0) return;
+        float4 *dst = &s.raw[(lane + 32 * k) * 4];
         if (t < nt_ep) {
             const char *q = reinterpret_cast<const char *>(p.epj + idx);
-            cp_async16(&s.raw[tid * 4 + 0], q); cp_async16(&s.raw[tid * 4 + 1], q + 16); cp_async16(&s.raw[tid * 4 + 2], q + 32);
+            cp_async16(dst + 0, q); cp_async16(dst + 1, q + 16); cp_async16(dst + 2, q + 32);
         } else {
             const char *q = reinterpret_cast<const char *>(p.spj + idx);
-            cp_async16(&s.raw[tid * 4 + 0], q); cp_async16(&s.raw[tid * 4 + 1], q + 16);
-            cp_async16(&s.raw[tid * 4 + 2], q + 32); cp_async16(&s.raw[tid * 4 + 3], q + 48);
+            cp_async16(dst + 0, q); cp_async16(dst + 1, q + 16); cp_async16(dst + 2, q + 32); cp_async16(dst + 3, q + 48);
         }
     };
-    auto convert = [&](int t, int idx) {    // raw record -> FP32 tile entry, shifted by the origin in FP64
-        JTile &T = s.tile[t & 1];
-        if (t < nt_ep) {
-            float rs2v = 0.0f;
-            if (idx >= 0) {
-                const double2 a = *reinterpret_cast<const double2 *>(&s.raw[tid * 4 + 0]);
-                const float4 bq = s.raw[tid * 4 + 1];
-                const float4 c = s.raw[tid * 4 + 2];
-                const double z = __hiloint2double(__float_as_int(bq.y), __float_as_int(bq.x));
-                T.j4[tid] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(z - oz), bq.z);
-                T.ep.rout2[tid] = bq.w; T.ep.rs2[tid] = c.x;
-                T.ep.id[tid] = __float_as_int(c.y); T.ep.rank[tid] = __float_as_int(c.z);
-                rs2v = c.x;
-            } else {                          // padding: massless, far away, never a candidate
-                T.j4[tid] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
-                T.ep.rout2[tid] = 0.0f; T.ep.rs2[tid] = 0.0f; T.ep.id[tid] = -1; T.ep.rank[tid] = 0;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) rs2v = fmaxf(rs2v, __shfl_xor_sync(0xffffffffu, rs2v, o));
-            if ((tid & 31) == 0) T.wmax[tid >> 5] = rs2v;
-        } else {
-            if (idx >= 0) {
-                const double2 a = *reinterpret_cast<const double2 *>(&s.raw[tid * 4 + 0]);
-                const float4 bq = s.raw[tid * 4 + 1];
-                const float4 c = s.raw[tid * 4 + 2];
-                const float4 d = s.raw[tid * 4 + 3];
-                const double z = __hiloint2double(__float_as_int(bq.y), __float_as_int(bq.x));
-                T.j4[tid] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(z - oz), bq.z);
-                T.sp.q0[tid] = make_float4(bq.w, c.x, c.y, c.z);   // Qxx Qyy Qzz Qxy
-                T.sp.q1[tid] = make_float4(c.w, d.x, d.y, 0.0f);   // Qyz Qzx mtr
-            } else {
-                T.j4[tid] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
-                T.sp.q0[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                T.sp.q1[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+    // raw record -> FP32 tile entry; returns rs2 of the entry (EP) for the tile's candidate threshold
+    auto convert = [&](int t, int k, int idx) -> float {
+        const int sl = lane + 32 * k;
+        const float4 *src = &s.raw[sl * 4];
+        if (idx < 0) {                        // padding: massless, far away, never a candidate
+            s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
+            if (t < nt_ep) { s.ep.rout2[sl] = 0.0f; s.ep.rs2[sl] = 0.0f; s.ep.id[sl] = -1; s.ep.rank[sl] = 0; }
+            else { s.sp.q0[sl] = make_float4(0.f, 0.f, 0.f, 0.f); s.sp.q1[sl] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            return 0.0f;
         }
+        const double2 a = *reinterpret_cast<const double2 *>(src);
+        const float4 bq = src[1];
+        const float4 c = src[2];
+        const double z = __hiloint2double(__float_as_int(bq.y), __float_as_int(bq.x));
+        s.j4[sl] = make_float4((float)(a.x - ox), (float)(a.y - oy), (float)(z - oz), bq.z);
+        if (t < nt_ep) {
+            s.ep.rout2[sl] = bq.w; s.ep.rs2[sl] = c.x;
+            s.ep.id[sl] = __float_as_int(c.y); s.ep.rank[sl] = __float_as_int(c.z);
+            return c.x;
+        }
+        const float4 d = src[3];
+        s.sp.q0[sl] = make_float4(bq.w, c.x, c.y, c.z);   // Qxx Qyy Qzz Qxy
+        s.sp.q1[sl] = make_float4(c.w, d.x, d.y, 0.0f);   // Qyz Qzx mtr
+        return 0.0f;
     };
 
-    // ---- prologue: start the first j-tile, stage the i-tile meanwhile ----
-    int idx_cur = slot_index(0);
-    issue(0, idx_cur);
-    int idx_nxt = slot_index(1);
-    for (int i = tid; i < IT; i += NT) {
-        if (i < it.ni) {
-            const EpiAos &e = p.epi[ibase + i];
-            const float ro = (float)e.r_out, rs = (float)e.r_search;
-            s.ipos[i] = make_float4((float)(e.pos[0] - ox), (float)(e.pos[1] - oy), (float)(e.pos[2] - oz),
-                                    __fmul_rn(ro, ro));
-            s.i_rs2[i] = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
-            s.i_id[i] = e.id_local; s.i_rank[i] = e.myrank;
-        } else {
-            s.ipos[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            s.i_rs2[i] = -1.0f; s.i_id[i] = 0; s.i_rank[i] = 0;
-        }
-        s.nb_number[i] = 0; s.nb_rank[i] = 0; s.nb_idmax[i] = -1; s.nb_idmin[i] = 2147483647;
-    }
-    cp_async_commit_wait_all();
-    if (nt > 0) convert(0, idx_cur);
-    __syncthreads();
+    // ---- prologue: start tile 0, load this warp's i-particles meanwhile ----
+    int idx0 = slot_index(0, 0), idx1 = slot_index(0, 1);
+    issue(0, 0, idx0); issue(0, 1, idx1);
+    int nidx0 = slot_index(1, 0), nidx1 = slot_index(1, 1);
 
     float xi[R], yi[R], zi[R], ro2i[R], rs2i[R];
     float ax[R], ay[R], az[R], ph[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const float4 v = s.ipos[lane_i + r * LANES_I];
-        xi[r] = v.x; yi[r] = v.y; zi[r] = v.z; ro2i[r] = v.w;
-        rs2i[r] = s.i_rs2[lane_i + r * LANES_I];
+        const int i = lane + 32 * r;
+        if (i < it.ni) {
+            const EpiAos &e = p.epi[ibase + i];
+            const float ro = (float)e.r_out, rs = (float)e.r_search;
+            xi[r] = (float)(e.pos[0] - ox); yi[r] = (float)(e.pos[1] - oy); zi[r] = (float)(e.pos[2] - oz);
+            ro2i[r] = __fmul_rn(ro, ro);
+            rs2i[r] = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
+            s.i_id[i] = e.id_local; s.i_rank[i] = e.myrank;
+        } else {
+            xi[r] = yi[r] = zi[r] = 0.0f; ro2i[r] = 0.0f; rs2i[r] = -1.0f;
+            s.i_id[i] = 0; s.i_rank[i] = 0;
+        }
+        s.i_rs2[i] = rs2i[r];
+        s.nb_number[i] = 0; s.nb_rank[i] = 0; s.nb_idmax[i] = -1; s.nb_idmin[i] = 2147483647;
         ax[r] = ay[r] = az[r] = ph[r] = 0.0f;
     }
+    float tmax = 0.0f;
+    cp_async_commit_wait_all();
+    if (nt > 0) tmax = fmaxf(convert(0, 0, idx0), convert(0, 1, idx1));
+    __syncwarp();
 
     for (int t = 0; t < nt; t++) {
         // stage tile t+1 while computing tile t
-        idx_cur = idx_nxt;
-        issue(t + 1, idx_cur);
-        idx_nxt = slot_index(t + 2);
-        const JTile &T = s.tile[t & 1];
+        idx0 = nidx0; idx1 = nidx1;
+        issue(t + 1, 0, idx0); issue(t + 1, 1, idx1);
+        nidx0 = slot_index(t + 2, 0); nidx1 = slot_index(t + 2, 1);
         const bool is_ep = t < nt_ep;
-        const int n_t = is_ep ? min(JT, nj_ep - t * JT) : min(JT, nj_sp - (t - nt_ep) * JT);
-        const int jps = ((n_t + JS - 1) / JS + UNROLL - 1) / UNROLL * UNROLL;   // per-slice count, padded
-        const int jb = slice * jps;
+        const int n_t = is_ep ? min(JW, nj_ep - t * JW) : min(JW, nj_sp - (t - nt_ep) * JW);
+        const int n_pad = (n_t + UNROLL - 1) / UNROLL * UNROLL;
         if (is_ep) {
             // =============================== EP-EP ===============================
-            float tmax = 0.0f;
 #pragma unroll
-            for (int k = 0; k < NT / 32; k++) tmax = fmaxf(tmax, T.wmax[k]);
+            for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
             tmax *= 1.0000153f;           // conservative candidate threshold (exact test in the rare path)
             float Ti[R];
 #pragma unroll
             for (int r = 0; r < R; r++) Ti[r] = (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax);
 #pragma unroll 1
-            for (int jj = 0; jj < jps; jj += UNROLL) {
+            for (int jj = 0; jj < n_pad; jj += UNROLL) {
                 bool hit = false;
+                const float4 ro2v = *reinterpret_cast<const float4 *>(&s.ep.rout2[jj]);
+                const float ro2a[4] = {ro2v.x, ro2v.y, ro2v.z, ro2v.w};
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    const float4 pj = T.j4[jb + jj + u];
-                    const float ro2 = T.ep.rout2[jb + jj + u];
+                    const float4 pj = s.j4[jj + u];
+                    const float ro2 = ro2a[u];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
@@ -328,24 +301,24 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                 if (__any_sync(0xffffffffu, hit)) {
                     // exact re-test, reference evaluation order, no FMA contraction
                     for (int u = 0; u < UNROLL; u++) {
-                        const int j = jb + jj + u;
-                        const float4 pj = T.j4[j];
+                        const int j = jj + u;
+                        const float4 pj = s.j4[j];
 #pragma unroll
                         for (int r = 0; r < R; r++) {
-                            const int il = lane_i + r * LANES_I;
+                            const int il = lane + 32 * r;
                             const float dx = xi[r] - pj.x, dy = yi[r] - pj.y, dz = zi[r] - pj.z;
                             const float r2e = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
                                                                   __fmul_rn(dz, dz)), eps2);
-                            const float rs2 = fmaxf(rs2i[r], T.ep.rs2[j]);
+                            const float rs2 = fmaxf(rs2i[r], s.ep.rs2[j]);
                             if (rs2i[r] >= 0.0f && r2e < rs2) {
-                                const int idj = T.ep.id[j], rkj = T.ep.rank[j];
+                                const int idj = s.ep.id[j], rkj = s.ep.rank[j];
                                 const int idi = s.i_id[il], rki = s.i_rank[il];
-                                if (idi != idj || rki != rkj) {
+                                if (idi != idj || rki != rkj) {     // only this lane touches entry il
                                     const int dr = rki - rkj;
-                                    atomicAdd(&s.nb_number[il], 1);
-                                    atomicAdd(&s.nb_rank[il], p.rank_squared ? dr * dr : abs(dr));
-                                    atomicMax(&s.nb_idmax[il], idj);
-                                    atomicMin(&s.nb_idmin[il], idj);
+                                    s.nb_number[il] += 1;
+                                    s.nb_rank[il] += p.rank_squared ? dr * dr : abs(dr);
+                                    s.nb_idmax[il] = max(s.nb_idmax[il], idj);
+                                    s.nb_idmin[il] = min(s.nb_idmin[il], idj);
                                 }
                             }
                         }
@@ -355,12 +328,12 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
         } else {
             // =============================== EP-SP ===============================
 #pragma unroll 1
-            for (int jj = 0; jj < jps; jj += UNROLL) {
+            for (int jj = 0; jj < n_pad; jj += UNROLL) {
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
-                    const float4 pj = T.j4[jb + jj + u];
-                    const float4 qa = T.sp.q0[jb + jj + u];
-                    const float4 qb = T.sp.q1[jb + jj + u];
+                    const float4 pj = s.j4[jj + u];
+                    const float4 qa = s.sp.q0[jj + u];
+                    const float4 qb = s.sp.q1[jj + u];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
@@ -384,44 +357,39 @@ __device__ __forceinline__ void tile_force(const PassParams &p, const WorkItem i
                 }
             }
         }
-        // tile t+1 has landed in raw (it had the whole compute phase to do so): convert it
+        // tile t+1 has landed in raw (it had the whole compute phase to do so): convert it in place
         cp_async_commit_wait_all();
-        if (t + 1 < nt) convert(t + 1, idx_cur);
-        __syncthreads();
+        __syncwarp();                     // every lane is done reading tile t
+        tmax = 0.0f;
+        if (t + 1 < nt) tmax = fmaxf(convert(t + 1, 0, idx0), convert(t + 1, 1, idx1));
+        __syncwarp();
     }
 
-    // ---- cross-slice reduction (fixed order) and write-back: ForceGrav::clear + accumulate ----
-    float4 *red = reinterpret_cast<float4 *>(&s.tile[0]);
+    // ---- write-back: ForceGrav::clear + this pass's sums (a4 + a7 fused) ----
 #pragma unroll
-    for (int r = 0; r < R; r++) red[slice * IT + lane_i + r * LANES_I] = make_float4(ax[r], ay[r], az[r], ph[r]);
-    __syncthreads();
-    for (int i = tid; i < it.ni; i += NT) {
-        float4 a = red[i];
-#pragma unroll
-        for (int sl = 1; sl < JS; sl++) {
-            const float4 b = red[sl * IT + i];
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    for (int r = 0; r < R; r++) {
+        const int i = lane + 32 * r;
+        if (i < it.ni) {
+            float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
+            out[0] = make_float4(ax[r], ay[r], az[r], ph[r]);
+            reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
         }
-        float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
-        out[0] = a;
-        reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
     }
 }
 
-// cfg -> (R, LANES_I):  0:(1,32) 1:(2,32) 2:(2,64) 3:(2,128)
-__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : cfg == 1 ? 64 : cfg == 2 ? 128 : 256; }
+// work item = up to 64 i-particles of one walk (cfg: 0 -> R=1 (<=32), 1 -> R=2)
+__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : 64; }
 
-__global__ void __launch_bounds__(NT, 3) force_pass_kernel(const PassParams p)
+__global__ void __launch_bounds__(WPB * 32, 6) force_pass_kernel(const PassParams p, int n_items)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemLayout &s = *reinterpret_cast<SmemLayout *>(smem_raw);
-    const WorkItem it = p.items[blockIdx.x];
-    switch (it.cfg) {
-        case 0: tile_force<1, 32>(p, it, s); break;
-        case 1: tile_force<2, 32>(p, it, s); break;
-        case 2: tile_force<2, 64>(p, it, s); break;
-        default: tile_force<2, 128>(p, it, s); break;
-    }
+    const int wid = threadIdx.x >> 5;
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_raw)[wid];
+    const int item = blockIdx.x * WPB + wid;
+    if (item >= n_items) return;
+    const WorkItem it = p.items[item];
+    if (it.cfg == 0) warp_force<1>(p, it, s);
+    else warp_force<2>(p, it, s);
 }
 
 // ------------------------------------------------------------------------------------------
