@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgplum_b200.so")
+LIB_PATH = os.environ.get("GPLUM_B200_LIB", os.path.join(_HERE, "libgplum_b200.so"))
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 

@@ -115,6 +115,7 @@ struct Ctx {
     std::atomic<long long> launches{0}, n_epep{0}, n_epsp{0};
     std::mutex mu;
     int smem_bytes = 0;
+    int rmax = 2;               // i-particles per lane (GPLUM_B200_RMAX = 2 or 4)
 };
 Ctx g;
 
@@ -135,9 +136,9 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
         int rem = ni[w], i0 = 0;
         const double cost_j = 20.0 * n_epj[w] + 38.0 * n_spj[w] + 64.0;
         while (rem > 0) {
-            const int cfg = rem > 32 ? 1 : 0;   // one warp: 64 i-particles (R=2) or <=32 (R=1)
-            const int tile = cfg_tile(cfg);
-            const int n = std::min(rem, tile);
+            const int n = std::min(rem, 32 * g.rmax);     // one warp: up to 32*RMAX i-particles
+            const int cfg = (n + 31) / 32 - 1;            // register slots per lane - 1
+            const int tile = 32 * (cfg + 1);
             tmp.push_back({cost_j * tile, WorkItem{w, i0, n, cfg}});
             rem -= n; i0 += n;
         }
@@ -160,7 +161,8 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
     p.items = (const WorkItem *)ws.items.p;
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
-    force_pass_kernel<<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
+    if (g.rmax <= 2) force_pass_kernel<2><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
+    else force_pass_kernel<4><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
     CU(cudaGetLastError());
     g.launches++;
     g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp;
@@ -334,7 +336,8 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.items = (const WorkItem *)(dm + sizeof(Meta));
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
-    force_pass_kernel<<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
+    if (g.rmax <= 2) force_pass_kernel<2><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
+    else force_pass_kernel<4><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     CU(cudaGetLastError());
     g.launches++;
     if (which == 0) g.n_epep += (long long)ni * nj; else g.n_epsp += (long long)ni * nj;
@@ -370,8 +373,10 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
         return fail(GPLUM_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    g.smem_bytes = (int)sizeof(WarpSmem) * WPB;
-    CU(cudaFuncSetAttribute(force_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_bytes));
+    if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : 2;
+    g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
+    CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
+    CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
     g.device = device;
     if (max_i) {
         if (int r = g.slots[0].epi.reserve(max_i * sizeof(EpiAos))) return r;

@@ -21,7 +21,13 @@
 
 namespace gb {
 
-constexpr int UNROLL = 4;
+#ifndef GB_UNROLL
+#define GB_UNROLL 4
+#endif
+#ifndef GB_MINB2
+#define GB_MINB2 6
+#endif
+constexpr int UNROLL = GB_UNROLL;
 
 // ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
 struct __align__(16) EpjPacked {   // 48 B
@@ -144,7 +150,7 @@ __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *_
 // ------------------------------------------------------------------------------------------
 constexpr int WPB = 4;         // warps per CTA
 constexpr int JW = 64;         // j-particles per warp tile (2 per lane)
-constexpr int IW = 64;         // max i-particles per warp (R = 2)
+template <int IW>              // IW = max i-particles per warp (32 * RMAX)
 struct WarpSmem {
     float4 raw[JW * 4];        // cp.async landing zone: 64 B per j (EP records use 48)
     float4 j4[JW];             // dx,dy,dz,m
@@ -167,8 +173,8 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int R>
-__device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem it, WarpSmem &s)
+template <int R, class Smem>
+__device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem it, Smem &s)
 {
     const int lane = threadIdx.x & 31;
     const int w = it.walk;
@@ -377,19 +383,30 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     }
 }
 
-// work item = up to 64 i-particles of one walk (cfg: 0 -> R=1 (<=32), 1 -> R=2)
-__host__ __device__ constexpr int cfg_tile(int cfg) { return cfg == 0 ? 32 : 64; }
-
-__global__ void __launch_bounds__(WPB * 32, 6) force_pass_kernel(const PassParams p, int n_items)
+// work item = up to 32*RMAX i-particles of one walk, handled by one warp with R = cfg+1 register
+// slots per lane.  RMAX = 2: 80 registers, 24 warps/SM.  RMAX = 4: fewer shared-memory reads and
+// less loop overhead per pair at 16 warps/SM.
+template <int RMAX>
+__global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass_kernel(const PassParams p, int n_items)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = threadIdx.x >> 5;
-    WarpSmem &s = reinterpret_cast<WarpSmem *>(smem_raw)[wid];
+    using Smem = WarpSmem<32 * RMAX>;
+    Smem &s = reinterpret_cast<Smem *>(smem_raw)[wid];
     const int item = blockIdx.x * WPB + wid;
     if (item >= n_items) return;
     const WorkItem it = p.items[item];
-    if (it.cfg == 0) warp_force<1>(p, it, s);
-    else warp_force<2>(p, it, s);
+    if (RMAX <= 2) {
+        if (it.cfg == 0) warp_force<1>(p, it, s);
+        else warp_force<2>(p, it, s);
+    } else {
+        switch (it.cfg) {
+            case 0: warp_force<1>(p, it, s); break;
+            case 1: warp_force<2>(p, it, s); break;
+            case 2: warp_force<3>(p, it, s); break;
+            default: warp_force<4>(p, it, s); break;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
