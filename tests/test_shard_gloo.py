@@ -1,0 +1,81 @@
+"""N>1 host logic on CPU (gloo, world_size 2 and 3): walk sharding by domain, slab-padded
+all-gather of j-data, index remap.  Each rank evaluates only its own walks (with the oracle
+standing in for the kernel) on the GATHERED j-arrays; the union must equal the single-rank
+pass bit-for-bit -- i.e. the partition changes nothing but who computes what."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_api as O
+from gplum_b200 import disk, structs as S, tree
+from gplum_b200.shard import Shard, split_walks
+
+
+def _workload():
+    d = disk.make_disk(3000, a_in=0.97, a_out=1.03, seed=12)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=64)
+    return w
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = _workload()
+    sh = Shard(w, world, rank)
+    lw = sh.local
+    # "pack" = this rank's own j-records, padded to the slab size; all-gather the slabs
+    def gather(local, cap, dtype):
+        send = np.zeros(cap, dtype=dtype); send[:len(local)] = local
+        t_send = torch.from_numpy(send.view(np.uint8).copy())
+        t_all = torch.zeros(world * t_send.numel(), dtype=torch.uint8)
+        dist.all_gather_into_tensor(t_all, t_send)
+        return t_all.numpy().view(dtype)
+    epj_g = gather(lw.epj_all, sh.epj_cap, S.EPJ)
+    spj_g = gather(lw.spj_all, sh.spj_cap, S.SPJ_QUAD)
+    # remapped lists address the same particles as the global lists
+    a0, a1 = sh.adr_epj_range; s0, s1 = sh.adr_spj_range
+    assert (epj_g[lw.adr_epj].tobytes() == w.epj_all[w.adr_epj[a0:a1]].tobytes())
+    assert (spj_g[lw.adr_spj].tobytes() == w.spj_all[w.adr_spj[s0:s1]].tobytes())
+    mine = O.Walks(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj, lw.spj_disp,
+                   lw.n_spj, epj_g, spj_g)
+    f, n_int = O.calc_walks(mine, 0.0)
+    np.save(os.path.join(out_dir, "f%d.npy" % rank), f)
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array(list(sh.epi_range) + [n_int]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pass_equals_single_rank(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    w = _workload()
+    want, n_tot = O.calc_walks(w, 0.0)
+    got = S.cleared_force(len(w.epi)); covered = 0; n_sum = 0
+    for r in range(world):
+        f = np.load(tmp_path / ("f%d.npy" % r)); e0, e1, n_int = np.load(tmp_path / ("r%d.npy" % r))
+        assert len(f) == e1 - e0
+        got[e0:e1] = f; covered += e1 - e0; n_sum += n_int
+    assert covered == len(w.epi) and n_sum == n_tot
+    assert got.tobytes() == want.tobytes()
+
+
+def test_split_is_contiguous_and_balanced():
+    w = _workload()
+    for world in (1, 2, 4, 8):
+        r = split_walks(w, world)
+        assert r[0][0] == 0 and r[-1][1] == w.n_walk and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        cost = w.ni.astype(np.int64) * (w.n_epj * 20 + w.n_spj * 38)
+        per = [cost[a:b].sum() for a, b in r]
+        assert max(per) <= 1.35 * (sum(per) / world) + cost.max()
