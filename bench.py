@@ -16,7 +16,8 @@ sample/parameter.dat tree parameters, n_group_limit per --group.
 
 `--impl reference` times only the reference CPU path (all host threads) on the same config.
 N>1 (torchrun): walks are sharded by Morton-contiguous domains, packed j-data is exchanged with
-one NCCL all-gather per array per step (gplum_b200/shard.py); fixed total work => strong scaling.
+one in-place NCCL all-gather per step that overlaps the interior walks (gplum_b200/shard.py);
+fixed total work => strong scaling.
 """
 import argparse
 import json
@@ -200,24 +201,28 @@ def main():
         my_int = sum(lw.n_interactions())
         eb, sb = C.c_int(0), C.c_int(0)
         L.gplum_b200_packed_sizes(C.byref(eb), C.byref(sb))
+        # raw AoS particles of this rank's own domain, resident in HBM (inputs of the step)
         d_epj_raw = torch.from_numpy(lw.epj_all.view(np.uint8).copy()).cuda()
-        d_spj_raw = torch.from_numpy(lw.spj_all.view(np.uint8).copy()).cuda()
-        send_e = torch.zeros(sh.epj_cap * eb.value, dtype=torch.uint8, device="cuda")
-        send_s = torch.zeros(sh.spj_cap * sb.value, dtype=torch.uint8, device="cuda")
+        # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
         gath_e = torch.zeros(world * sh.epj_cap * eb.value, dtype=torch.uint8, device="cuda")
-        gath_s = torch.zeros(world * sh.spj_cap * sb.value, dtype=torch.uint8, device="cuda")
-        empty_e = np.zeros(0, S.EPJ); empty_s = np.zeros(0, S.SPJ_QUAD)
-        lw_nj = type(lw)(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj, lw.spj_disp,
-                         lw.n_spj, empty_e, empty_s)
-        F.walks_upload(lw_nj)
-        check(L.gplum_b200_walks_set_packed_dev(C.c_void_p(gath_e.data_ptr()), world * sh.epj_cap,
-                                                C.c_void_p(gath_s.data_ptr()), world * sh.spj_cap))
+        my_slab = gath_e[rank * sh.epj_cap * eb.value:(rank + 1) * sh.epj_cap * eb.value]
+        empty_e = np.zeros(0, S.EPJ)
+        wi, wb = sh.walks_interior, sh.walks_boundary
+        # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
+        F.walks_select(0)
+        F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
+                                wi.spj_disp, wi.n_spj, empty_e, w.spj_all))
+        F.walks_select(1)
+        F.walks_upload(wb, with_j=False)
+        check(L.gplum_b200_walks_set_packed_dev(C.c_void_p(gath_e.data_ptr()), world * sh.epj_cap, None, 0))
         def step():
-            check(L.gplum_b200_pack_epj_dev(C.c_void_p(d_epj_raw.data_ptr()), len(lw.epj_all), C.c_void_p(send_e.data_ptr())))
-            check(L.gplum_b200_pack_spj_dev(C.c_void_p(d_spj_raw.data_ptr()), len(lw.spj_all), C.c_void_p(send_s.data_ptr())))
-            dist.all_gather_into_tensor(gath_e, send_e)
-            dist.all_gather_into_tensor(gath_s, send_s)
-            F.walks_run(repack=False)
+            check(L.gplum_b200_pack_epj_dev(C.c_void_p(d_epj_raw.data_ptr()), len(lw.epj_all), C.c_void_p(my_slab.data_ptr())))
+            work = dist.all_gather_into_tensor(gath_e, my_slab, async_op=True)   # NVLink, in place
+            F.walks_select(0)
+            F.walks_run(repack=True)       # SPJ pack + interior walks: overlap the all-gather
+            work.wait()
+            F.walks_select(1)
+            F.walks_run(repack=False)      # boundary walks need the other ranks' particles
 
     for _ in range(args.warmup):
         step()
@@ -241,7 +246,11 @@ def main():
 
     # ------------------------------------------------------------------ dominant kernel alone
     barrier()
-    k_ms = F.walks_time(max(3, args.steps), repack=False)      # CUDA events on the launching stream
+    if world == 1:
+        k_ms = F.walks_time(max(3, args.steps), repack=False)      # CUDA events on the launching stream
+    else:
+        F.walks_select(0); k_ms = F.walks_time(max(3, args.steps), repack=False)
+        F.walks_select(1); k_ms += F.walks_time(max(3, args.steps), repack=False)
     peak_tf, _ = F.fp32_peak(10)
     my_ee, my_es = (ee, es) if world == 1 else sh.local.n_interactions()
     flop = FLOP_EPEP * my_ee + FLOP_EPSP * my_es
@@ -259,6 +268,7 @@ def main():
 
     # ------------------------------------------------------------------ end to end via the C ABI
     check(L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
+    F.walks_select(0)
     if world == 1:
         lw = w
     else:

@@ -24,6 +24,7 @@ SYMBOLS = {
     "gplum_b200_retrieve": (_i, [_i, _i, _vp, _vp]),
     "gplum_b200_calc_walks": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i, _vp, _i]),
     "gplum_b200_walks_upload": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i]),
+    "gplum_b200_walks_select": (_i, [_i]),
     "gplum_b200_walks_run": (_i, [_i]),
     "gplum_b200_walks_download": (_i, [_vp]),
     "gplum_b200_walks_time": (_i, [_i, _i, C.POINTER(_f)]),

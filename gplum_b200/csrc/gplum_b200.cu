@@ -116,6 +116,7 @@ struct Ctx {
     std::mutex mu;
     int smem_bytes = 0;
     int rmax = 2;               // i-particles per lane (GPLUM_B200_RMAX = 2 or 4)
+    int cur = 0;                // resident walk set used by the walks_* calls
 };
 Ctx g;
 
@@ -561,6 +562,13 @@ int gplum_b200_retrieve(int tag, int n_walk, const int *ni, void *const *force)
 }
 
 // ---- device-resident form ----
+int gplum_b200_walks_select(int slot)
+{
+    if (slot < 0 || slot >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "slot %d out of range [0,%d)", slot, N_TAG);
+    g.cur = slot;
+    return 0;
+}
+
 int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
                             const int *adr_epj, const long long *epj_disp, const int *n_epj,
                             const int *adr_spj, const long long *spj_disp, const int *n_spj,
@@ -569,9 +577,11 @@ int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off,
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
     cudaStream_t st = g.stream;
-    if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
-    if (int r = pack_j(st, g.eps2)) return r;
-    if (int r = upload_walks(g.slots[0], n_walk, epi_all, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, st)) return r;
+    if (epj_all || spj_all) {          // NULL, NULL: keep the current j-set (another slot / external arrays)
+        if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
+        if (int r = pack_j(st, g.eps2)) return r;
+    }
+    if (int r = upload_walks(g.slots[g.cur], n_walk, epi_all, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, st)) return r;
     CU(cudaStreamSynchronize(st));
     return 0;
 }
@@ -581,14 +591,14 @@ int gplum_b200_walks_run(int repack)
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
     if (repack) if (int r = pack_j(g.stream, g.eps2)) return r;
-    return launch_pass(g.slots[0], g.stream, g.eps2);
+    return launch_pass(g.slots[g.cur], g.stream, g.eps2);
 }
 
 int gplum_b200_walks_download(void *force_all)
 {
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
-    WalkSet &ws = g.slots[0];
+    WalkSet &ws = g.slots[g.cur];
     CU(cudaStreamSynchronize(g.stream));
     if (ws.n_epi) CU(cudaMemcpy(force_all, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost));
     return 0;
@@ -605,7 +615,7 @@ int gplum_b200_walks_time(int iters, int repack, float *ms_per_pass)
     CU(cudaEventRecord(e0, g.stream));
     for (int i = 0; i < iters; i++) {
         if (repack) if (int r = pack_j(g.stream, g.eps2)) return r;
-        if (int r = launch_pass(g.slots[0], g.stream, g.eps2)) return r;
+        if (int r = launch_pass(g.slots[g.cur], g.stream, g.eps2)) return r;
     }
     CU(cudaEventRecord(e1, g.stream));
     CU(cudaEventSynchronize(e1));

@@ -93,8 +93,16 @@ def calc_walks(w, force=None, clear=True):
     return f
 
 
-def walks_upload(w):
-    check(lib().gplum_b200_walks_upload(*_walk_args(w)))
+def walks_select(slot):
+    check(lib().gplum_b200_walks_select(int(slot)))
+
+
+def walks_upload(w, with_j=True):
+    """with_j=False: upload only the walks (lists + i-particles); the j-set stays as it is."""
+    a = _walk_args(w)
+    if not with_j:
+        a[10], a[11], a[12], a[13] = None, 0, None, 0
+    check(lib().gplum_b200_walks_upload(*a))
 
 
 def walks_run(repack=True):

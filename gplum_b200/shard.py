@@ -6,9 +6,12 @@ Walks are in Morton order, so a contiguous range of walks is a compact spatial d
 `dinfo.decomposeDomainAll` gives each MPI rank in the reference).  Rank r owns
   * the i-particles / forces of walks [w0_r, w1_r)          -> no collective on the i side
   * the j-particles of the same Morton range (its "domain") -> packed locally, all-gathered
-  * an equal slice of the tree cells (superparticles)       -> packed locally, all-gathered
-The all-gather buffer is slab-padded (every rank contributes `cap` records) so one
-`all_gather_into_tensor` moves everything; list indices are remapped once to the padded layout.
+Superparticles are derived data (moments of the tree over the gathered particles): every rank
+holds / rebuilds them itself, so only EPJ cross NVLink.
+The all-gather buffer is slab-padded (every rank contributes `cap` records) so one in-place
+`all_gather_into_tensor` moves everything; EP list indices are remapped once to the padded layout.
+Walks whose EP list lies entirely inside the rank's own slab ("interior") can be evaluated while
+the all-gather is in flight; the remaining "boundary" walks wait for it.
 """
 import numpy as np
 
@@ -40,11 +43,7 @@ class Shard:
         p_lo[0] = 0
         p_hi = p_lo[1:] + [len(w.epj_all)]
         self.epj_ranges = list(zip(p_lo, p_hi))
-        n_sp = len(w.spj_all)
-        s_lo = [(n_sp * r) // world for r in range(world)]
-        self.spj_ranges = list(zip(s_lo, s_lo[1:] + [n_sp]))
         self.epj_cap = max(b - a for a, b in self.epj_ranges)
-        self.spj_cap = max(1, max(b - a for a, b in self.spj_ranges))
         self.walk_range = ranges[rank]
         w0, w1 = ranges[rank]
         e0 = int(w.epi_off[w0]) if w0 < w.n_walk else len(w.epi)
@@ -55,11 +54,26 @@ class Shard:
         s0 = int(w.spj_disp[w0]) if w1 > w0 else 0
         s1 = int(w.spj_disp[w1 - 1] + w.n_spj[w1 - 1]) if w1 > w0 else 0
         self.adr_epj_range, self.adr_spj_range = (a0, a1), (s0, s1)
+        adr_e = self.remap(w.adr_epj[a0:a1], self.epj_ranges, self.epj_cap)
         self.local = Walks(w.epi[e0:e1], w.epi_off[w0:w1] - e0, w.ni[w0:w1],
-                           self.remap(w.adr_epj[a0:a1], self.epj_ranges, self.epj_cap), w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
-                           self.remap(w.adr_spj[s0:s1], self.spj_ranges, self.spj_cap), w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
-                           w.epj_all[self.epj_ranges[rank][0]:self.epj_ranges[rank][1]],
-                           w.spj_all[self.spj_ranges[rank][0]:self.spj_ranges[rank][1]])
+                           adr_e, w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
+                           w.adr_spj[s0:s1], w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
+                           w.epj_all[self.epj_ranges[rank][0]:self.epj_ranges[rank][1]], w.spj_all)
+        # interior walks: every EP index inside this rank's own slab of the gather buffer
+        lo, hi = rank * self.epj_cap, rank * self.epj_cap + (self.epj_ranges[rank][1] - self.epj_ranges[rank][0])
+        lw = self.local
+        inside = ((adr_e >= lo) & (adr_e < hi)).astype(np.int64)
+        c = np.concatenate([[0], np.cumsum(inside)])
+        d0 = lw.epj_disp
+        self.interior = (c[d0 + lw.n_epj] - c[d0]) == lw.n_epj
+        self.walks_interior = self.subset(np.nonzero(self.interior)[0])
+        self.walks_boundary = self.subset(np.nonzero(~self.interior)[0])
+
+    def subset(self, idx):
+        """The walks `idx` of the local set, sharing its epi / list arrays (force indexing unchanged)."""
+        lw = self.local
+        return Walks(lw.epi, lw.epi_off[idx], lw.ni[idx], lw.adr_epj, lw.epj_disp[idx], lw.n_epj[idx],
+                     lw.adr_spj, lw.spj_disp[idx], lw.n_spj[idx], lw.epj_all, lw.spj_all)
 
     @staticmethod
     def remap(adr, ranges, cap):

@@ -94,6 +94,10 @@ int gplum_b200_calc_walks(int n_walk, const void *epi_all, const int *epi_off, c
  * j-pack + force kernels on the library stream (asynchronous); walks_download synchronises
  * and copies the n_epi_total forces back.  walks_time runs `iters` passes bracketed by CUDA
  * events on the launching stream and returns the mean milliseconds per pass. */
+/* Up to 4 resident walk sets (e.g. interior / boundary walks of a domain); walks_upload, _run,
+ * _download and _time act on the selected one.  walks_upload with epj_all == spj_all == NULL
+ * keeps the current j-set. */
+int gplum_b200_walks_select(int slot);
 int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
                             const int *adr_epj, const long long *epj_disp, const int *n_epj,
                             const int *adr_spj, const long long *spj_disp, const int *n_spj,

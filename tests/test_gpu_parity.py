@@ -164,3 +164,27 @@ def test_neighbour_flags_dense_field():
     F.calcForceEPEPWithSearch(0.0)(epi, 200, epj, 900, got)
     synth.assert_force_close(got, want, RTOL, "dense")
     assert (got["rank"] == want["rank"]).all()
+
+
+def test_two_resident_walk_sets_share_one_j_set():
+    """Interior/boundary split of the multi-GPU path on one GPU: two walk sets, one j upload."""
+    w, _, eps2 = _load_walks("init3000_g64.npz")
+    F.set_params(eps2, True, 0)
+    want, _ = O.calc_walks(w, eps2)
+    idx_a = np.arange(0, w.n_walk, 2); idx_b = np.arange(1, w.n_walk, 2)
+    sub = lambda idx: O.Walks(w.epi, w.epi_off[idx], w.ni[idx], w.adr_epj, w.epj_disp[idx], w.n_epj[idx],
+                              w.adr_spj, w.spj_disp[idx], w.n_spj[idx], w.epj_all, w.spj_all)
+    wa, wb = sub(idx_a), sub(idx_b)
+    try:
+        F.walks_select(0); F.walks_upload(wa)
+        F.walks_select(1); F.walks_upload(wb, with_j=False)
+        F.walks_select(0); F.walks_run(repack=True); fa = F.walks_download(int((wa.epi_off + wa.ni).max()))
+        F.walks_select(1); F.walks_run(repack=False); fb = F.walks_download(int((wb.epi_off + wb.ni).max()))
+    finally:
+        F.walks_select(0)
+    got = S.cleared_force(len(w.epi))
+    for ws, f in ((wa, fa), (wb, fb)):
+        for k in range(ws.n_walk):
+            sl = slice(ws.epi_off[k], ws.epi_off[k] + ws.ni[k])
+            got[sl] = f[sl]
+    synth.assert_force_close(got, want, RTOL, "two sets")

@@ -43,14 +43,19 @@ def _worker(rank, world, port, out_dir):
         dist.all_gather_into_tensor(t_all, t_send)
         return t_all.numpy().view(dtype)
     epj_g = gather(lw.epj_all, sh.epj_cap, S.EPJ)
-    spj_g = gather(lw.spj_all, sh.spj_cap, S.SPJ_QUAD)
     # remapped lists address the same particles as the global lists
-    a0, a1 = sh.adr_epj_range; s0, s1 = sh.adr_spj_range
+    a0, a1 = sh.adr_epj_range
     assert (epj_g[lw.adr_epj].tobytes() == w.epj_all[w.adr_epj[a0:a1]].tobytes())
-    assert (spj_g[lw.adr_spj].tobytes() == w.spj_all[w.adr_spj[s0:s1]].tobytes())
-    mine = O.Walks(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj, lw.spj_disp,
-                   lw.n_spj, epj_g, spj_g)
-    f, n_int = O.calc_walks(mine, 0.0)
+    # interior walks need nothing from other ranks: evaluate them on the rank's OWN slab only
+    own = np.zeros_like(epj_g); lo = rank * sh.epj_cap
+    own[lo:lo + len(lw.epj_all)] = lw.epj_all
+    f = S.cleared_force(len(lw.epi)); n_int = 0
+    for part, jarr in ((sh.walks_interior, own), (sh.walks_boundary, epj_g)):
+        pw = O.Walks(part.epi, part.epi_off, part.ni, part.adr_epj, part.epj_disp, part.n_epj, part.adr_spj,
+                     part.spj_disp, part.n_spj, jarr, w.spj_all)
+        f, n = O.calc_walks(pw, 0.0, force=f)
+        n_int += n
+    assert sh.interior.sum() + (~sh.interior).sum() == lw.n_walk and (world == 1 or (~sh.interior).any())
     np.save(os.path.join(out_dir, "f%d.npy" % rank), f)
     np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array(list(sh.epi_range) + [n_int]))
     dist.barrier()
