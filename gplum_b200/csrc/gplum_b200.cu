@@ -375,6 +375,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : 2;
+    if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
@@ -407,7 +408,8 @@ int gplum_b200_finalize(void)
 
 int gplum_b200_set_params(float eps2, int quad, int flags)
 {
-    g.eps2 = eps2; g.quad = quad ? 1 : 0; g.flags = flags;
+    g.eps2 = eps2; g.quad = quad ? 1 : 0;
+    if (flags >= 0) g.flags = flags;      // flags < 0: keep the current ones (e.g. GPLUM_B200_FLAGS)
     return 0;
 }
 

@@ -62,7 +62,8 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j);
 int gplum_b200_finalize(void);
 
 /* eps2: FP_t::eps2 narrowed to F32 (src/gravity_kernel.hpp:17,31); quad: 1 = MySPJQuadrupole
- * (USE_QUAD), 0 = MySPJMonopole; flags: GPLUM_B200_* above. */
+ * (USE_QUAD), 0 = MySPJMonopole; flags: GPLUM_B200_* above, or < 0 to keep the current flags
+ * (initialised from the environment variable GPLUM_B200_FLAGS, default 0). */
 int gplum_b200_set_params(float eps2, int quad, int flags);
 
 /* ---- per-call functor form (re-entrant; one stream + staging slot per calling thread) ---- */
