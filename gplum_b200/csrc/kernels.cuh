@@ -6,15 +6,17 @@
 // packed j-arrays resident in HBM.  Arithmetic follows src/gravity_kernel_epep.pikg:53-97 and
 // src/gravity_kernel_epsp.pikg:47-100: FP64 shift by the group's first i-particle, then FP32.
 //
-// Per pair, EP-EP (hot loop, 20 issue slots for the DSL's 30 flop + rsqrt):
-//   d = xj-xi (3 FADD); r2 = d.d+eps2 (3 FFMA); hit |= r2 < T_i (FSETP);
+// Per pair, EP-EP (hot loop, 18.5 issue slots for the DSL's 30 flop + rsqrt):
+//   d = xj-xi (3 FADD); r2 = d.d+eps2 (3 FFMA); rmin = min3(rmin, r2[i0], r2[i1]) (FMNMX3 per 2 pairs);
 //   r2c = max3(r2, rout2_i, rout2_j) (FMNMX3; max(a,b)^2 == max(a^2,b^2) exactly in FP);
-//   y = MUFU.RSQ(r2c) + the DSL's Newton step (4); mr = m*y; mr3 = y*y*mr (3);
-//   acc += mr3*d (3 FFMA); phi -= mr (FADD).
-// Neighbour candidates: the hot loop only evaluates a conservative filter (r2 < T_i with
-// T_i >= rsearch2 of the pair, widened by 2^-16); pairs that pass (rare: self + true
-// candidates) are re-tested in the reference's exact, non-fused evaluation order
-// (src/gravity_kernel.hpp:94,104-111) so number/rank/id_max/id_min are bit-exact.
+//   y = MUFU.RSQ(r2c); Newton step of the DSL as a = y*(3 - r2c*y*y) = 2*y' (3; the DSL's *0.5 is
+//   a power of two and is carried exactly in the accumulators' scale: phi2 = 2*phi, acc8 = 8*acc,
+//   undone at the write -- bit-identical results); t = m*a; v = (a*a)*t (3);
+//   acc8 += v*d (3 FFMA); phi2 -= t (FADD).
+// Neighbour candidates: the hot loop only evaluates a conservative filter (min r2 < T with
+// T >= rsearch2 of every pair of the lane and tile, widened by 2^-16); j-groups that pass
+// (rare: self + true candidates) are re-tested in the reference's exact, non-fused evaluation
+// order (src/gravity_kernel.hpp:94,104-111) so number/rank/id_max/id_min are bit-exact.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,7 +37,8 @@ struct __align__(16) EpjPacked {   // 48 B
     double z; float m, rout2;
     float rs2; int id; int rank; int pad;
 };
-struct __align__(16) SpjPacked {   // 64 B; Q = 3q - tr*I, mtr = -(eps2*tr) hoisted (j-only terms)
+struct __align__(16) SpjPacked {   // 64 B; Q = (3q - tr*I)/4, mtr = -(eps2*tr)/4 hoisted (j-only terms;
+                                   // the exact power-of-two scale pairs with a = 2*y' in the pair loop)
     double x, y;
     double z; float m, qxx;
     float qyy, qzz, qxy, qyz;
@@ -77,6 +80,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c)
 {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
 __device__ __forceinline__ double2 ldg_d2(const void *p)
@@ -125,11 +134,11 @@ __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *_
         const float qxy = (float)a.quad[3], qzx = (float)a.quad[4], qyz = (float)a.quad[5];
         const float tr = trace_as_shipped ? (float)(a.quad[0] + a.quad[1] + a.quad[0])
                                           : __fadd_rn(__fadd_rn(qxx, qyy), qzz);
-        o.qxx = __fsub_rn(__fmul_rn(3.0f, qxx), tr);
-        o.qyy = __fsub_rn(__fmul_rn(3.0f, qyy), tr);
-        o.qzz = __fsub_rn(__fmul_rn(3.0f, qzz), tr);
-        o.qxy = __fmul_rn(3.0f, qxy); o.qyz = __fmul_rn(3.0f, qyz); o.qzx = __fmul_rn(3.0f, qzx);
-        o.mtr = -__fmul_rn(eps2, tr);
+        o.qxx = 0.25f * __fsub_rn(__fmul_rn(3.0f, qxx), tr);
+        o.qyy = 0.25f * __fsub_rn(__fmul_rn(3.0f, qyy), tr);
+        o.qzz = 0.25f * __fsub_rn(__fmul_rn(3.0f, qzz), tr);
+        o.qxy = 0.25f * __fmul_rn(3.0f, qxy); o.qyz = 0.25f * __fmul_rn(3.0f, qyz); o.qzx = 0.25f * __fmul_rn(3.0f, qzx);
+        o.mtr = -0.25f * __fmul_rn(eps2, tr);
     } else {
         const SpjMonoAos &a = ((const SpjMonoAos *)in)[i];
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
@@ -250,7 +259,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
             rs2i[r] = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
             s.i_id[i] = e.id_local; s.i_rank[i] = e.myrank;
         } else {
-            xi[r] = yi[r] = zi[r] = 0.0f; ro2i[r] = 0.0f; rs2i[r] = -1.0f;
+            xi[r] = yi[r] = zi[r] = -1.0e10f; ro2i[r] = 0.0f; rs2i[r] = -1.0f;   // far from everything: never a candidate
             s.i_id[i] = 0; s.i_rank[i] = 0;
         }
         s.i_rs2[i] = rs2i[r];
@@ -275,35 +284,45 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
             tmax *= 1.0000153f;           // conservative candidate threshold (exact test in the rare path)
-            float Ti[R];
+            float T = -1.0f;                       // one threshold per lane: max over its i-slots and the tile's j
 #pragma unroll
-            for (int r = 0; r < R; r++) Ti[r] = (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax);
+            for (int r = 0; r < R; r++) T = fmaxf(T, (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax));
 #pragma unroll 1
             for (int jj = 0; jj < n_pad; jj += UNROLL) {
-                bool hit = false;
-                const float4 ro2v = *reinterpret_cast<const float4 *>(&s.ep.rout2[jj]);
-                const float ro2a[4] = {ro2v.x, ro2v.y, ro2v.z, ro2v.w};
+                float rmin = 3.0e38f;
+                float ro2a[UNROLL];
+#pragma unroll
+                for (int q = 0; q < UNROLL / 4; q++) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(&s.ep.rout2[jj + 4 * q]);
+                    ro2a[4 * q] = v4.x; ro2a[4 * q + 1] = v4.y; ro2a[4 * q + 2] = v4.z; ro2a[4 * q + 3] = v4.w;
+                }
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     const float4 pj = s.j4[jj + u];
                     const float ro2 = ro2a[u];
+                    float r2[R];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
-                        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
-                        hit |= (r2 < Ti[r]);
-                        const float r2c = fmax3(r2, ro2i[r], ro2);
-                        float y = rsqrt_approx(r2c);
-                        const float tt = fmaf(-r2c, y * y, 3.0f);
-                        y *= tt * 0.5f;
-                        const float mr = pj.w * y;
-                        const float mr3 = (y * y) * mr;
-                        ax[r] = fmaf(mr3, dx, ax[r]);
-                        ay[r] = fmaf(mr3, dy, ay[r]);
-                        az[r] = fmaf(mr3, dz, az[r]);
-                        ph[r] -= mr;
+                        r2[r] = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
+                        const float r2c = fmax3(r2[r], ro2i[r], ro2);
+                        const float y = rsqrt_approx(r2c);
+                        const float a = y * fmaf(-r2c, y * y, 3.0f);      // 2*y'
+                        const float t = pj.w * a;                          // 2*m*y'
+                        const float v = (a * a) * t;                       // 8*m*y'^3
+                        ax[r] = fmaf(v, dx, ax[r]);
+                        ay[r] = fmaf(v, dy, ay[r]);
+                        az[r] = fmaf(v, dz, az[r]);
+                        ph[r] -= t;
+                    }
+                    if (R == 1) rmin = fminf(rmin, r2[0]);
+                    else if (R == 2) rmin = fmin3(rmin, r2[0], r2[1]);
+                    else {
+#pragma unroll
+                        for (int r = 0; r < R; r++) rmin = fminf(rmin, r2[r]);
                     }
                 }
+                const bool hit = rmin < T;
                 if (__any_sync(0xffffffffu, hit)) {
                     // exact re-test, reference evaluation order, no FMA contraction
                     for (int u = 0; u < UNROLL; u++) {
@@ -344,21 +363,20 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
-                        float y = rsqrt_approx(r2);
-                        const float tt = fmaf(-r2, y * y, 3.0f);
-                        y *= tt * 0.5f;
-                        const float y2 = y * y, y3 = y2 * y, y4 = y2 * y2, y5 = y2 * y3;
-                        const float qrx = fmaf(qb.y, dz, fmaf(qa.w, dy, qa.x * dx));   // Qxx dx + Qxy dy + Qzx dz
-                        const float qry = fmaf(qa.w, dx, fmaf(qb.x, dz, qa.y * dy));   // Qyy dy + Qyz dz + Qxy dx
-                        const float qrz = fmaf(qb.x, dy, fmaf(qb.y, dx, qa.z * dz));   // Qzz dz + Qzx dx + Qyz dy
+                        const float y = rsqrt_approx(r2);
+                        const float a = y * fmaf(-r2, y * y, 3.0f);                    // 2*y'
+                        const float a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a2 * a3; // 4y'^2 8y'^3 16y'^4 32y'^5
+                        const float qrx = fmaf(qb.y, dz, fmaf(qa.w, dy, qa.x * dx));   // (Qxx dx + Qxy dy + Qzx dz)/4
+                        const float qry = fmaf(qa.w, dx, fmaf(qb.x, dz, qa.y * dy));   // (Qyy dy + Qyz dz + Qxy dx)/4
+                        const float qrz = fmaf(qb.x, dy, fmaf(qb.y, dx, qa.z * dz));   // (Qzz dz + Qzx dx + Qyz dy)/4
                         const float rqr = fmaf(qrz, dz, fmaf(qry, dy, fmaf(qrx, dx, qb.z)));
-                        const float wq = rqr * y4;
-                        const float meff = fmaf(0.5f, wq, pj.w);
-                        const float meff3 = fmaf(2.5f, wq, pj.w) * y3;
-                        ph[r] = fmaf(-meff, y, ph[r]);
-                        ax[r] = fmaf(meff3, dx, fmaf(-y5, qrx, ax[r]));
-                        ay[r] = fmaf(meff3, dy, fmaf(-y5, qry, ay[r]));
-                        az[r] = fmaf(meff3, dz, fmaf(-y5, qrz, az[r]));
+                        const float wq = rqr * a4;                                      // 4 * rqr*y'^4
+                        const float meff = fmaf(0.125f, wq, pj.w);                      // m + 0.5 rqr y'^4
+                        const float meff3 = fmaf(0.625f, wq, pj.w) * a3;                // 8 (m + 2.5 rqr y'^4) y'^3
+                        ph[r] = fmaf(-meff, a, ph[r]);
+                        ax[r] = fmaf(meff3, dx, fmaf(-a5, qrx, ax[r]));
+                        ay[r] = fmaf(meff3, dy, fmaf(-a5, qry, ay[r]));
+                        az[r] = fmaf(meff3, dz, fmaf(-a5, qrz, az[r]));
                     }
                 }
             }
@@ -377,7 +395,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         const int i = lane + 32 * r;
         if (i < it.ni) {
             float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
-            out[0] = make_float4(ax[r], ay[r], az[r], ph[r]);
+            out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
             reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
         }
     }
