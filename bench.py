@@ -215,14 +215,26 @@ def main():
         F.walks_select(1)
         F.walks_upload(wb, with_j=False)
         check(L.gplum_b200_walks_set_packed_dev(C.c_void_p(gath_e.data_ptr()), world * sh.epj_cap, None, 0))
+        side = torch.cuda.Stream()         # boundary walks: start when the gather lands, co-run with the interior tail
+        ev_side, ev_pack = torch.cuda.Event(), torch.cuda.Event()
+        sp = lambda st: check(L.gplum_b200_set_stream(C.c_void_p(st.cuda_stream)))
+
         def step():
             check(L.gplum_b200_pack_epj_dev(C.c_void_p(d_epj_raw.data_ptr()), len(lw.epj_all), C.c_void_p(my_slab.data_ptr())))
             work = dist.all_gather_into_tensor(gath_e, my_slab, async_op=True)   # NVLink, in place
+            check(L.gplum_b200_walks_pack())           # SPJ pack (every rank holds the cells itself)
+            ev_pack.record(stream)
             F.walks_select(0)
-            F.walks_run(repack=True)       # SPJ pack + interior walks: overlap the all-gather
-            work.wait()
-            F.walks_select(1)
-            F.walks_run(repack=False)      # boundary walks need the other ranks' particles
+            F.walks_run(repack=False)      # interior walks: overlap the all-gather
+            with torch.cuda.stream(side):
+                work.wait()                # the side stream waits for NCCL ...
+                side.wait_event(ev_pack)   # ... and for the packed SPJ
+                sp(side)
+                F.walks_select(1)
+                F.walks_run(repack=False)  # boundary walks need the other ranks' particles
+                ev_side.record(side)
+            sp(stream)
+            stream.wait_event(ev_side)
 
     for _ in range(args.warmup):
         step()

@@ -26,6 +26,7 @@ SYMBOLS = {
     "gplum_b200_walks_upload": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i]),
     "gplum_b200_walks_select": (_i, [_i]),
     "gplum_b200_walks_run": (_i, [_i]),
+    "gplum_b200_walks_pack": (_i, []),
     "gplum_b200_walks_download": (_i, [_vp]),
     "gplum_b200_walks_time": (_i, [_i, _i, C.POINTER(_f)]),
     "gplum_b200_walks_set_packed_dev": (_i, [_vp, _i, _vp, _i]),

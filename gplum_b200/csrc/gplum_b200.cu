@@ -84,8 +84,10 @@ struct WalkSet {
     std::vector<int> ni_host;                    // for retrieve()
     std::vector<long long> epi_off_host;
     bool pending = false;
+    cudaEvent_t done = nullptr;                  // recorded after the D2H of a dispatch: retrieve(tag) waits on it only
     void release()
     {
+        if (done) { cudaEventDestroy(done); done = nullptr; }
         for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force})
             b->release();
         h_force.release(); h_stage.release();
@@ -117,6 +119,7 @@ struct Ctx {
     int smem_bytes = 0;
     int rmax = 2;               // i-particles per lane (GPLUM_B200_RMAX = 2 or 4)
     int cur = 0;                // resident walk set used by the walks_* calls
+    int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
 };
 Ctx g;
 
@@ -133,15 +136,36 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     items.clear();
     std::vector<std::pair<double, WorkItem>> tmp;
     tmp.reserve((size_t)n_walk * 2);
+    // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
+    const bool split = g.jsplit != 0;
     for (int w = 0; w < n_walk; w++) {
         int rem = ni[w], i0 = 0;
-        const double cost_j = 20.0 * n_epj[w] + 38.0 * n_spj[w] + 64.0;
-        while (rem > 0) {
-            const int n = std::min(rem, 32 * g.rmax);     // one warp: up to 32*RMAX i-particles
-            const int cfg = (n + 31) / 32 - 1;            // register slots per lane - 1
-            const int tile = 32 * (cfg + 1);
-            tmp.push_back({cost_j * tile, WorkItem{w, i0, n, cfg}});
+        const double cost_j = 18.5 * n_epj[w] + 37.0 * n_spj[w];
+        const double cost_tiles = 90.0 * ((n_epj[w] + 63) / 64 + (n_spj[w] + 63) / 64) + 200.0;
+        auto push = [&](int n, int cfg, double cost) {
+            tmp.push_back({cost, WorkItem{w, i0, n, cfg}});
             rem -= n; i0 += n;
+        };
+        // tile shapes: 64 (two i per lane), 32, and for a short tail (<= 16) one j-split tile whose
+        // G = 2/4/8 lane groups share the i's and split the j's.  Finer decompositions (e.g. 20 ->
+        // 16 + 4) were measured slower at n_group_limit = 64: every extra item pays its own staging.
+        while (rem > 0) {
+            if (g.rmax >= 3 && rem > 64) {                   // RMAX = 4 build: up to 128 i-particles per warp
+                const int n = std::min(rem, 128);
+                const int cfg = (n + 31) / 32 - 1;
+                push(n, cfg, cost_j * (cfg + 1) + cost_tiles);
+                continue;
+            }
+            if (g.rmax >= 2 && (rem >= 64 || (rem > 32 && (!split || rem > 48)))) {
+                push(std::min(rem, 64), 1, 2.0 * cost_j + cost_tiles);      // two i-particles per lane
+                continue;
+            }
+            if (rem >= 32 || !split || rem > 16) {
+                push(std::min(rem, 32), 0, cost_j + cost_tiles);            // one i-particle per lane
+                continue;
+            }
+            const int k = rem > 8 ? 1 : (rem > 4 ? 2 : 3);                   // G = 2, 4, 8
+            push(rem, 8 + k, cost_j / (1 << k) + cost_tiles);
         }
     }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
@@ -374,8 +398,9 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
         return fail(GPLUM_B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : 2;
+    if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : (atoi(e) <= 1 ? 1 : 2);
     if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
@@ -537,6 +562,8 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
     if (int r = launch_pass(ws, st, g.eps2)) return r;
     if (int r = ws.h_force.reserve((size_t)std::max<long long>(ws.n_epi, 1) * sizeof(ForceAos))) return r;
     if (ws.n_epi) CU(cudaMemcpyAsync(ws.h_force.p, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost, st));
+    if (!ws.done) CU(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
+    CU(cudaEventRecord(ws.done, st));
     ws.pending = true;
     return 0;
 }
@@ -549,7 +576,7 @@ int gplum_b200_retrieve(int tag, int n_walk, const int *ni, void *const *force)
     if (!ws.pending) return fail(GPLUM_B200_ERR_STATE, "retrieve(tag=%d) without dispatch", tag);
     if (n_walk != ws.n_walk) return fail(GPLUM_B200_ERR_ARG, "retrieve n_walk %d != dispatched %d", n_walk, ws.n_walk);
     CU(cudaSetDevice(g.device));
-    CU(cudaStreamSynchronize(g.stream));
+    CU(cudaEventSynchronize(ws.done));      // later dispatches (other tags) keep running
     ws.pending = false;
     const bool overwrite = (g.flags & GPLUM_B200_NO_ACCUMULATE) != 0;
     const ForceAos *src = (const ForceAos *)ws.h_force.p;
@@ -594,6 +621,13 @@ int gplum_b200_walks_run(int repack)
     CU(cudaSetDevice(g.device));
     if (repack) if (int r = pack_j(g.stream, g.eps2)) return r;
     return launch_pass(g.slots[g.cur], g.stream, g.eps2);
+}
+
+int gplum_b200_walks_pack(void)
+{
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    return pack_j(g.stream, g.eps2);
 }
 
 int gplum_b200_walks_download(void *force_all)

@@ -182,7 +182,10 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-template <int R, class Smem>
+// R = i-particles per lane; G = j-split: for short i-tiles (ni <= 32/G, R == 1) the warp is cut into
+// G lane groups that hold the SAME i-particles and each take every G-th block of UNROLL j's of a
+// tile; their partial sums are combined by shuffles before the write.
+template <int R, int G, class Smem>
 __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem it, Smem &s)
 {
     const int lane = threadIdx.x & 31;
@@ -248,22 +251,26 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
 
     float xi[R], yi[R], zi[R], ro2i[R], rs2i[R];
     float ax[R], ay[R], az[R], ph[R];
+    static_assert(G == 1 || R == 1, "j-split tiles hold one i-particle per lane");
+    constexpr int W = 32 / G;                 // i-particles per lane group
+    const int phase = lane / W;               // which j-blocks this lane takes (0 when G == 1)
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int i = lane + 32 * r;
+        const int il = lane + 32 * r;         // per-lane slot in the warp's shared arrays
+        const int i = (G == 1) ? il : lane % W;
         if (i < it.ni) {
             const EpiAos &e = p.epi[ibase + i];
             const float ro = (float)e.r_out, rs = (float)e.r_search;
             xi[r] = (float)(e.pos[0] - ox); yi[r] = (float)(e.pos[1] - oy); zi[r] = (float)(e.pos[2] - oz);
             ro2i[r] = __fmul_rn(ro, ro);
             rs2i[r] = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
-            s.i_id[i] = e.id_local; s.i_rank[i] = e.myrank;
+            s.i_id[il] = e.id_local; s.i_rank[il] = e.myrank;
         } else {
             xi[r] = yi[r] = zi[r] = -1.0e10f; ro2i[r] = 0.0f; rs2i[r] = -1.0f;   // far from everything: never a candidate
-            s.i_id[i] = 0; s.i_rank[i] = 0;
+            s.i_id[il] = 0; s.i_rank[il] = 0;
         }
-        s.i_rs2[i] = rs2i[r];
-        s.nb_number[i] = 0; s.nb_rank[i] = 0; s.nb_idmax[i] = -1; s.nb_idmin[i] = 2147483647;
+        s.i_rs2[il] = rs2i[r];
+        s.nb_number[il] = 0; s.nb_rank[il] = 0; s.nb_idmax[il] = -1; s.nb_idmin[il] = 2147483647;
         ax[r] = ay[r] = az[r] = ph[r] = 0.0f;
     }
     float tmax = 0.0f;
@@ -278,7 +285,8 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         nidx0 = slot_index(t + 2, 0); nidx1 = slot_index(t + 2, 1);
         const bool is_ep = t < nt_ep;
         const int n_t = is_ep ? min(JW, nj_ep - t * JW) : min(JW, nj_sp - (t - nt_ep) * JW);
-        const int n_pad = (n_t + UNROLL - 1) / UNROLL * UNROLL;
+        const int n_pad = (n_t + UNROLL * G - 1) / (UNROLL * G) * (UNROLL * G);   // every slot of the tile is initialised
+        const int j_first = phase * UNROLL;
         if (is_ep) {
             // =============================== EP-EP ===============================
 #pragma unroll
@@ -288,7 +296,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
 #pragma unroll
             for (int r = 0; r < R; r++) T = fmaxf(T, (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax));
 #pragma unroll 1
-            for (int jj = 0; jj < n_pad; jj += UNROLL) {
+            for (int jj = j_first; jj < n_pad; jj += UNROLL * G) {
                 float rmin = 3.0e38f;
                 float ro2a[UNROLL];
 #pragma unroll
@@ -353,7 +361,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         } else {
             // =============================== EP-SP ===============================
 #pragma unroll 1
-            for (int jj = 0; jj < n_pad; jj += UNROLL) {
+            for (int jj = j_first; jj < n_pad; jj += UNROLL * G) {
 #pragma unroll
                 for (int u = 0; u < UNROLL; u++) {
                     const float4 pj = s.j4[jj + u];
@@ -390,13 +398,31 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     }
 
     // ---- write-back: ForceGrav::clear + this pass's sums (a4 + a7 fused) ----
+    __syncwarp();
+    if (G > 1) {
+        // combine the lane groups' partial results (same i in lanes l, l+W, l+2W, ...)
+        int nn = s.nb_number[lane], nr = s.nb_rank[lane], nmax = s.nb_idmax[lane], nmin = s.nb_idmin[lane];
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int i = lane + 32 * r;
-        if (i < it.ni) {
-            float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
-            out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
-            reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+        for (int o = W; o < 32; o <<= 1) {
+            ax[0] += __shfl_xor_sync(0xffffffffu, ax[0], o); ay[0] += __shfl_xor_sync(0xffffffffu, ay[0], o);
+            az[0] += __shfl_xor_sync(0xffffffffu, az[0], o); ph[0] += __shfl_xor_sync(0xffffffffu, ph[0], o);
+            nn += __shfl_xor_sync(0xffffffffu, nn, o); nr += __shfl_xor_sync(0xffffffffu, nr, o);
+            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+        }
+        if (lane < W && lane < it.ni) {
+            float4 *out = reinterpret_cast<float4 *>(p.force + ibase + lane);
+            out[0] = make_float4(0.125f * ax[0], 0.125f * ay[0], 0.125f * az[0], 0.5f * ph[0]);   // undo the exact scales
+            reinterpret_cast<int4 *>(out)[1] = make_int4(nn, nr, nmax, nmin);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane + 32 * r;
+            if (i < it.ni) {
+                float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
+                out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
+                reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+            }
         }
     }
 }
@@ -414,15 +440,24 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
     const int item = blockIdx.x * WPB + wid;
     if (item >= n_items) return;
     const WorkItem it = p.items[item];
+    // cfg: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = j-split tile, G = 2^k lane groups
+    if (it.cfg >= 8) {
+        switch (it.cfg) {
+            case 9: warp_force<1, 2>(p, it, s); break;
+            case 10: warp_force<1, 4>(p, it, s); break;
+            default: warp_force<1, 8>(p, it, s); break;
+        }
+        return;
+    }
     if (RMAX <= 2) {
-        if (it.cfg == 0) warp_force<1>(p, it, s);
-        else warp_force<2>(p, it, s);
+        if (it.cfg == 0) warp_force<1, 1>(p, it, s);
+        else warp_force<2, 1>(p, it, s);
     } else {
         switch (it.cfg) {
-            case 0: warp_force<1>(p, it, s); break;
-            case 1: warp_force<2>(p, it, s); break;
-            case 2: warp_force<3>(p, it, s); break;
-            default: warp_force<4>(p, it, s); break;
+            case 0: warp_force<1, 1>(p, it, s); break;
+            case 1: warp_force<2, 1>(p, it, s); break;
+            case 2: warp_force<3, 1>(p, it, s); break;
+            default: warp_force<4, 1>(p, it, s); break;
         }
     }
 }

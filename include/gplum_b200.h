@@ -104,6 +104,7 @@ int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off,
                             const int *adr_spj, const long long *spj_disp, const int *n_spj,
                             const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all);
 int gplum_b200_walks_run(int repack);
+int gplum_b200_walks_pack(void);          /* only the j-pack kernels of walks_run(repack=1) */
 int gplum_b200_walks_download(void *force_all);
 int gplum_b200_walks_time(int iters, int repack, float *ms_per_pass);
 /* Replace the packed j-arrays by caller-owned device buffers (e.g. the output of an NCCL

@@ -46,6 +46,22 @@ def test_functor_calls_vs_oracle(ni, nj, ns, seed, eps2, n_rank):
     synth.assert_force_close(got2, want2, RTOL, "epep+epsp")
 
 
+@pytest.mark.parametrize("ni", [1, 2, 3, 4, 5, 8, 9, 15, 16, 17, 31, 32, 33, 36, 40, 47, 48, 49, 63, 64, 65, 68, 73, 80, 97, 129])
+def test_every_tile_shape_incl_j_split_tails(ni):
+    """i-tiles of 64 (two per lane), 32, and short tails whose j-lists are split over 2/4/8 lane
+    groups (gplum_b200.cu build_items): forces and neighbour info must not depend on the shape.
+    Dense field so that candidates fall into every lane group."""
+    nj, ns = 333, 77
+    epi, epj, spj = synth.make_group(ni, nj, ns, seed=100 + ni, box=0.02, r_out=2.0e-3, n_rank=2, dup_self=True)
+    want = O.epsp(epi, spj, 0.0, force=O.epep(epi, epj, 0.0))
+    assert want["number"].sum() > 0
+    got = S.cleared_force(ni)
+    F.calcForceEPEPWithSearch(0.0)(epi, ni, epj, nj, got)
+    F.calcForceEPSP(0.0)(epi, ni, spj, ns, got)
+    synth.assert_force_close(got, want, RTOL, "tile shapes ni=%d" % ni)
+    assert (got["rank"] == want["rank"]).all()
+
+
 def test_functor_accumulates_like_reference():
     epi, epj, spj = synth.make_group(20, 90, 30, seed=11)
     f0 = S.cleared_force(20)
