@@ -15,9 +15,11 @@ sample/parameter.dat tree parameters, n_group_limit per --group.
   cpu_baseline  the reference's own functors (oracle/_ref, AVX2+OpenMP build) on a bounded sample
 
 `--impl reference` times only the reference CPU path (all host threads) on the same config.
-N>1 (torchrun): walks are sharded by Morton-contiguous domains, packed j-data is exchanged with
-one in-place NCCL all-gather per step that overlaps the interior walks (gplum_b200/shard.py);
-fixed total work => strong scaling.
+N>1 (torchrun): walks are sharded by Morton-contiguous domains; per step every rank packs its own
+j-particles and one NCCL all-to-all moves only the records other ranks' boundary walks need (the
+reference's LET exchange; `--exchange allgather` moves everything instead).  The exchange overlaps
+the interior walks; boundary walks run on a second stream when it lands (gplum_b200/shard.py).
+Fixed total work => strong scaling.
 """
 import argparse
 import json
@@ -128,7 +130,7 @@ def workload_config(args, w):
             "n_particles": args.n, "n_group_limit": args.group, "n_walks": int(w.n_walk),
             "interactions_epep": ee, "interactions_epsp": es,
             "l2": "per-step inputs (lists+particles) exceed L2 at N=1e6; no flush",
-            "parallelism": "i-groups sharded over %d GPU(s), j-data all-gathered" % args.gpus}
+            "parallelism": "i-groups sharded over %d GPU(s), EPJ exchange: %s" % (args.gpus, getattr(args, "exchange", "halo"))}
 
 
 def pinned_like(a):
@@ -149,6 +151,8 @@ def main():
     ap.add_argument("--group", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
+                    help="N>1: trimmed halo all-to-all (the reference's LET idea) or a full all-gather of the packed EPJ")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -166,7 +170,7 @@ def main():
     import torch.distributed as dist
     from gplum_b200 import functors as F, structs as S
     from gplum_b200._lib import lib, check
-    from gplum_b200.shard import Shard
+    from gplum_b200.multigpu import MultiGpuPass
     import ctypes as C
 
     torch.cuda.set_device(local_rank)
@@ -196,45 +200,11 @@ def main():
         def step():
             F.walks_run(repack=True)
     else:
-        sh = Shard(w, world, rank)
-        lw = sh.local
-        my_int = sum(lw.n_interactions())
-        eb, sb = C.c_int(0), C.c_int(0)
-        L.gplum_b200_packed_sizes(C.byref(eb), C.byref(sb))
-        # raw AoS particles of this rank's own domain, resident in HBM (inputs of the step)
-        d_epj_raw = torch.from_numpy(lw.epj_all.view(np.uint8).copy()).cuda()
-        # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
-        gath_e = torch.zeros(world * sh.epj_cap * eb.value, dtype=torch.uint8, device="cuda")
-        my_slab = gath_e[rank * sh.epj_cap * eb.value:(rank + 1) * sh.epj_cap * eb.value]
-        empty_e = np.zeros(0, S.EPJ)
+        mg = MultiGpuPass(w, world, rank, stream, exchange=args.exchange)
+        sh, lw = mg.sh, mg.lw
         wi, wb = sh.walks_interior, sh.walks_boundary
-        # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
-        F.walks_select(0)
-        F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
-                                wi.spj_disp, wi.n_spj, empty_e, w.spj_all))
-        F.walks_select(1)
-        F.walks_upload(wb, with_j=False)
-        check(L.gplum_b200_walks_set_packed_dev(C.c_void_p(gath_e.data_ptr()), world * sh.epj_cap, None, 0))
-        side = torch.cuda.Stream()         # boundary walks: start when the gather lands, co-run with the interior tail
-        ev_side, ev_pack = torch.cuda.Event(), torch.cuda.Event()
-        sp = lambda st: check(L.gplum_b200_set_stream(C.c_void_p(st.cuda_stream)))
-
-        def step():
-            check(L.gplum_b200_pack_epj_dev(C.c_void_p(d_epj_raw.data_ptr()), len(lw.epj_all), C.c_void_p(my_slab.data_ptr())))
-            work = dist.all_gather_into_tensor(gath_e, my_slab, async_op=True)   # NVLink, in place
-            check(L.gplum_b200_walks_pack())           # SPJ pack (every rank holds the cells itself)
-            ev_pack.record(stream)
-            F.walks_select(0)
-            F.walks_run(repack=False)      # interior walks: overlap the all-gather
-            with torch.cuda.stream(side):
-                work.wait()                # the side stream waits for NCCL ...
-                side.wait_event(ev_pack)   # ... and for the packed SPJ
-                sp(side)
-                F.walks_select(1)
-                F.walks_run(repack=False)  # boundary walks need the other ranks' particles
-                ev_side.record(side)
-            sp(stream)
-            stream.wait_event(ev_side)
+        my_int = sum(lw.n_interactions())
+        step, exchange, exch_bytes = mg.step, mg.exchange, mg.exchange_bytes
 
     for _ in range(args.warmup):
         step()
@@ -261,8 +231,20 @@ def main():
     if world == 1:
         k_ms = F.walks_time(max(3, args.steps), repack=False)      # CUDA events on the launching stream
     else:
-        F.walks_select(0); k_ms = F.walks_time(max(3, args.steps), repack=False)
-        F.walks_select(1); k_ms += F.walks_time(max(3, args.steps), repack=False)
+        F.walks_select(0); k_int = F.walks_time(max(3, args.steps), repack=False)
+        F.walks_select(1); k_bnd = F.walks_time(max(3, args.steps), repack=False)
+        k_ms = k_int + k_bnd
+        # phase timings (this rank), for the scaling analysis: the all-gather alone, the two kernels alone
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ea.record(stream)
+        for _ in range(10):
+            exchange().wait()
+        eb.record(stream)
+        torch.cuda.synchronize()
+        phases = {"exchange": args.exchange, "exchange_ms": ea.elapsed_time(eb) / 10, "interior_kernel_ms": k_int, "boundary_kernel_ms": k_bnd,
+                  "interior_walks": int(wi.n_walk), "boundary_walks": int(wb.n_walk),
+                  "exchange_bytes": int(exch_bytes)}
     peak_tf, _ = F.fp32_peak(10)
     my_ee, my_es = (ee, es) if world == 1 else sh.local.n_interactions()
     flop = FLOP_EPEP * my_ee + FLOP_EPSP * my_es
@@ -343,6 +325,8 @@ def main():
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, w),
            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
            "list_build_s_host": t_build}
+    if world > 1:
+        out["phases_rank0"] = phases
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count()
         kind, s, O, libname = cpu_reference_run(w, 0.0, args.cpu_seconds, threads)

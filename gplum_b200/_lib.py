@@ -32,6 +32,7 @@ SYMBOLS = {
     "gplum_b200_walks_set_packed_dev": (_i, [_vp, _i, _vp, _i]),
     "gplum_b200_pack_epj_dev": (_i, [_vp, _i, _vp]),
     "gplum_b200_pack_spj_dev": (_i, [_vp, _i, _vp]),
+    "gplum_b200_gather_epj_packed_dev": (_i, [_vp, _vp, _i, _vp]),
     "gplum_b200_packed_sizes": (None, [C.POINTER(_i), C.POINTER(_i)]),
     "gplum_b200_set_stream": (_i, [_vp]),
     "gplum_b200_synchronize": (_i, []),

@@ -119,6 +119,7 @@ struct Ctx {
     int smem_bytes = 0;
     int rmax = 2;               // i-particles per lane (GPLUM_B200_RMAX = 2 or 4)
     int cur = 0;                // resident walk set used by the walks_* calls
+    long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
 };
 Ctx g;
@@ -138,6 +139,19 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     tmp.reserve((size_t)n_walk * 2);
     // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
     const bool split = g.jsplit != 0;
+    // Tile capacity: 64 i-particles per warp is the most efficient shape, but one such item is a
+    // serial chain of ~1e5 issue slots; when a pass has too few of them to fill the GPU twice
+    // (small per-GPU shards, boundary sets) use 32, or j-split tiles of 16 / 8 / 4, instead.
+    int cap = g.rmax >= 2 ? 64 : 32;
+    if (split && g.rmax <= 2) {
+        const long long target = 2LL * g.warp_slots;
+        for (; cap > 4; cap >>= 1) {
+            long long n_it = 0;
+            for (int w = 0; w < n_walk; w++) n_it += (ni[w] + cap - 1) / cap;
+            if (n_it >= target) break;
+        }
+    }
+    auto cfg_of = [](int c) { return c == 64 ? 1 : c == 32 ? 0 : c == 16 ? 9 : c == 8 ? 10 : 11; };
     for (int w = 0; w < n_walk; w++) {
         int rem = ni[w], i0 = 0;
         const double cost_j = 18.5 * n_epj[w] + 37.0 * n_spj[w];
@@ -146,9 +160,9 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
             tmp.push_back({cost, WorkItem{w, i0, n, cfg}});
             rem -= n; i0 += n;
         };
-        // tile shapes: 64 (two i per lane), 32, and for a short tail (<= 16) one j-split tile whose
-        // G = 2/4/8 lane groups share the i's and split the j's.  Finer decompositions (e.g. 20 ->
-        // 16 + 4) were measured slower at n_group_limit = 64: every extra item pays its own staging.
+        auto push_shape = [&](int n, int c) { push(n, cfg_of(c), cost_j * c / 32.0 + cost_tiles); };
+        // Finer decompositions of a remainder (e.g. 20 -> 16 + 4) were measured slower at
+        // n_group_limit = 64: every extra item pays its own staging.
         while (rem > 0) {
             if (g.rmax >= 3 && rem > 64) {                   // RMAX = 4 build: up to 128 i-particles per warp
                 const int n = std::min(rem, 128);
@@ -156,16 +170,10 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
                 push(n, cfg, cost_j * (cfg + 1) + cost_tiles);
                 continue;
             }
-            if (g.rmax >= 2 && (rem >= 64 || (rem > 32 && (!split || rem > 48)))) {
-                push(std::min(rem, 64), 1, 2.0 * cost_j + cost_tiles);      // two i-particles per lane
-                continue;
-            }
-            if (rem >= 32 || !split || rem > 16) {
-                push(std::min(rem, 32), 0, cost_j + cost_tiles);            // one i-particle per lane
-                continue;
-            }
-            const int k = rem > 8 ? 1 : (rem > 4 ? 2 : 3);                   // G = 2, 4, 8
-            push(rem, 8 + k, cost_j / (1 << k) + cost_tiles);
+            if (rem >= cap) { push_shape(cap, cap); continue; }
+            if (!split) { push_shape(rem, rem > 32 ? 64 : 32); continue; }
+            if (rem > 32 && rem <= 48) { push_shape(32, 32); continue; }     // 32 + a j-split tail beats a half-empty 64
+            push_shape(rem, rem > 32 ? 64 : rem > 16 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4);
         }
     }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
@@ -404,6 +412,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
+    g.warp_slots = (long long)prop.multiProcessorCount * 24;      // 6 CTAs x 4 warps per SM (80 registers)
     g.device = device;
     if (max_i) {
         if (int r = g.slots[0].epi.reserve(max_i * sizeof(EpiAos))) return r;
@@ -677,6 +686,17 @@ int gplum_b200_pack_epj_dev(const void *epj_aos_dev, int n, void *epj_packed_dev
     if (n <= 0) return 0;
     CU(cudaSetDevice(g.device));
     pack_epj_kernel<<<(n + 255) / 256, 256, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)epj_packed_dev);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_gather_epj_packed_dev(const void *src_packed_dev, const int *idx_dev, int n, void *dst_packed_dev)
+{
+    if (int r = ensure_init()) return r;
+    if (n <= 0) return 0;
+    CU(cudaSetDevice(g.device));
+    gather_epj_packed_kernel<<<(3 * n + 255) / 256, 256, 0, g.stream>>>((const uint4 *)src_packed_dev, idx_dev, n, (uint4 *)dst_packed_dev);
     CU(cudaGetLastError());
     g.launches++;
     return 0;

@@ -119,6 +119,16 @@ __global__ void pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked 
     out[i] = o;
 }
 
+// Halo send staging of the multi-GPU step: dst[k] = src[idx[k]] for 48 B packed EP records,
+// one 16 B chunk per thread (the trimmed LET exchange, FDPS/src/tree_for_force_impl_exlet.hpp:343-403).
+__global__ void gather_epj_packed_kernel(const uint4 *__restrict__ src, const int *__restrict__ idx, int n, uint4 *__restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const int k = t / 3, c = t - 3 * k;
+    dst[3 * (size_t)k + c] = src[3 * (size_t)idx[k] + c];
+}
+
 // quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
 // src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).
 __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,

@@ -1,0 +1,112 @@
+"""One rank's share of a multi-GPU force pass: i-groups sharded by domain, EPJ exchanged
+over NCCL, interior walks overlapped with the exchange, boundary walks on a second stream.
+
+Replaces FDPS's LET exchange + per-rank calcForce (FDPS/src/tree_for_force_impl_exlet.hpp:343-403,
+tree_for_force_impl_force.hpp:1404-1564).  torch / torch.distributed are plumbing (streams, NCCL);
+every kernel on the path is libgplum_b200's.  Used by bench.py and tests/test_multi_gpu.py.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import functors as F, structs as S
+from ._lib import check, lib
+from .shard import HaloShard, Shard
+
+
+class MultiGpuPass:
+    """`exchange` = "halo": one all-to-all of only the records other ranks' boundary walks read;
+    "allgather": in-place all-gather of every rank's packed slab."""
+
+    def __init__(self, w, world, rank, stream, exchange="halo"):
+        L = lib()
+        self.L, self.stream, self.exchange_kind = L, stream, exchange
+        halo = exchange == "halo"
+        self.sh = sh = (HaloShard if halo else Shard)(w, world, rank)
+        self.lw = lw = sh.local
+        eb, sb = C.c_int(0), C.c_int(0)
+        L.gplum_b200_packed_sizes(C.byref(eb), C.byref(sb))
+        EB = eb.value
+        # raw AoS particles of this rank's own domain, resident in HBM (inputs of the step)
+        self.d_epj_raw = torch.from_numpy(lw.epj_all.view(np.uint8).copy()).cuda()
+        wi, wb = sh.walks_interior, sh.walks_boundary
+        self.n_interior, self.n_boundary = wi.n_walk, wb.n_walk
+        # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
+        F.walks_select(0)
+        F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
+                                wi.spj_disp, wi.n_spj, np.zeros(0, S.EPJ), w.spj_all))
+        F.walks_select(1)
+        F.walks_upload(wb, with_j=False)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        if halo:
+            # local j-array = [own | halo]: own particles are packed in place, the halo region is the
+            # receive buffer of one all-to-all of the records other ranks' boundary walks need (LET)
+            n_own, n_halo, n_send = sh.n_own, sh.n_halo, len(sh.send_idx)
+            self.jbuf = torch.zeros((n_own + n_halo) * EB + 16, dtype=torch.uint8, device="cuda")
+            self.my_slab = self.jbuf[:n_own * EB]
+            self.halo_rows = self.jbuf[n_own * EB:(n_own + n_halo) * EB].view(n_halo, EB)
+            self.send_rows = torch.zeros((max(n_send, 1), EB), dtype=torch.uint8, device="cuda")[:n_send]
+            self.d_send_idx = torch.from_numpy(np.ascontiguousarray(sh.send_idx)).cuda()
+            check(L.gplum_b200_walks_set_packed_dev(vp(self.jbuf), n_own + n_halo, None, 0))
+            self.exchange_bytes = (n_send + n_halo) * EB
+        else:
+            # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
+            self.jbuf = torch.zeros(world * sh.epj_cap * EB, dtype=torch.uint8, device="cuda")
+            self.my_slab = self.jbuf[rank * sh.epj_cap * EB:(rank + 1) * sh.epj_cap * EB]
+            check(L.gplum_b200_walks_set_packed_dev(vp(self.jbuf), world * sh.epj_cap, None, 0))
+            self.exchange_bytes = int(self.jbuf.numel())
+        self.side = torch.cuda.Stream()    # boundary walks: start when the exchange lands, co-run with the interior tail
+        self.ev_side, self.ev_pack = torch.cuda.Event(), torch.cuda.Event()
+
+    def _use(self, st):
+        check(self.L.gplum_b200_set_stream(C.c_void_p(st.cuda_stream)))
+
+    def exchange(self):
+        """Pack own EPJ, start the NCCL exchange; returns the async work handle."""
+        L, vp = self.L, (lambda t: C.c_void_p(t.data_ptr()))
+        check(L.gplum_b200_pack_epj_dev(vp(self.d_epj_raw), len(self.lw.epj_all), vp(self.my_slab)))
+        if self.exchange_kind == "halo":
+            check(L.gplum_b200_gather_epj_packed_dev(vp(self.my_slab), vp(self.d_send_idx), len(self.sh.send_idx),
+                                                     vp(self.send_rows)))
+            return dist.all_to_all_single(self.halo_rows, self.send_rows, self.sh.recv_counts, self.sh.send_counts,
+                                          async_op=True)
+        return dist.all_gather_into_tensor(self.jbuf, self.my_slab, async_op=True)
+
+    def step(self):
+        stream, side = self.stream, self.side
+        work = self.exchange()
+        check(self.L.gplum_b200_walks_pack())      # SPJ pack (every rank holds the cells itself)
+        self.ev_pack.record(stream)
+        F.walks_select(0)
+        F.walks_run(repack=False)          # interior walks: overlap the exchange
+        with torch.cuda.stream(side):
+            work.wait()                    # the side stream waits for NCCL ...
+            side.wait_event(self.ev_pack)  # ... and for the packed SPJ
+            self._use(side)
+            F.walks_select(1)
+            F.walks_run(repack=False)      # boundary walks read the other ranks' particles
+            self.ev_side.record(side)
+        self._use(stream)
+        stream.wait_event(self.ev_side)
+
+    def forces(self):
+        """This rank's forces (host, ForceGrav[ len(local.epi) ]) after step()."""
+        torch.cuda.synchronize()
+        n = len(self.lw.epi)
+        out = S.cleared_force(n)
+        for slot, ws in ((0, self.sh.walks_interior), (1, self.sh.walks_boundary)):
+            if ws.n_walk == 0:
+                continue
+            F.walks_select(slot)
+            f = F.walks_download(int((ws.epi_off + ws.ni).max()))
+            for k in range(ws.n_walk):
+                sl = slice(int(ws.epi_off[k]), int(ws.epi_off[k] + ws.ni[k]))
+                out[sl] = f[sl]
+        F.walks_select(0)
+        return out
+
+    def close(self):
+        check(self.L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
+        F.walks_select(0)

@@ -81,3 +81,80 @@ class Shard:
         lo = np.array([a for a, _ in ranges], dtype=np.int64)
         owner = np.searchsorted(lo, adr, side="right") - 1
         return (adr - lo[owner] + owner * cap).astype(np.int32)
+
+
+class HaloShard:
+    """Same partition as `Shard`, but the exchange is trimmed to what is needed -- the LET idea of
+    the reference (FDPS/src/tree_for_force_impl_exlet.hpp:343-403: every rank sends each other
+    rank only the EPJ that rank's walks can touch) instead of a full all-gather.
+
+    Local j-array of rank r:  [ own particles (n_own) | halo from rank 0 | halo from rank 1 | ... ]
+    where "halo from s" are the particles owned by s that appear in r's EP lists, in ascending
+    global order.  Per step: pack own particles in place, gather `send_idx` into a send buffer,
+    one all-to-all (`send_counts` / `recv_counts` records), then the boundary walks.  Interior
+    walks (all EP indices own) run while the exchange is in flight.
+    """
+
+    def __init__(self, w, world, rank):
+        self.world, self.rank = world, rank
+        ranges = split_walks(w, world)
+        p_lo = [int(w.epi_off[a]) if a < w.n_walk else len(w.epi) for a, _ in ranges]
+        p_lo[0] = 0
+        p_hi = p_lo[1:] + [len(w.epj_all)]
+        self.epj_ranges = list(zip(p_lo, p_hi))
+        lo = np.array(p_lo, dtype=np.int64)
+
+        def lists_of(r):
+            w0, w1 = ranges[r]
+            if w1 <= w0:
+                return 0, 0, np.zeros(0, np.int32)
+            a0 = int(w.epj_disp[w0]); a1 = int(w.epj_disp[w1 - 1] + w.n_epj[w1 - 1])
+            return a0, a1, w.adr_epj[a0:a1]
+
+        def needs_of(r):
+            """Sorted global indices rank r reads from other ranks."""
+            _, _, adr = lists_of(r)
+            q0, q1 = self.epj_ranges[r]
+            return np.unique(adr[(adr < q0) | (adr >= q1)])
+
+        p0, p1 = self.epj_ranges[rank]
+        self.n_own = p1 - p0
+        need = needs_of(rank)
+        owner = np.searchsorted(lo, need, side="right") - 1
+        self.recv_counts = [int((owner == s).sum()) for s in range(world)]
+        self.n_halo = len(need)
+        send_idx, self.send_counts = [], []
+        for d in range(world):
+            if d == rank:
+                self.send_counts.append(0)
+                continue
+            nd = needs_of(d)
+            mine = nd[(nd >= p0) & (nd < p1)] - p0
+            send_idx.append(mine.astype(np.int32))
+            self.send_counts.append(len(mine))
+        self.send_idx = np.concatenate(send_idx) if send_idx else np.zeros(0, np.int32)
+
+        w0, w1 = ranges[rank]
+        self.walk_range = (w0, w1)
+        e0 = int(w.epi_off[w0]) if w0 < w.n_walk else len(w.epi)
+        e1 = int(w.epi_off[w1 - 1] + w.ni[w1 - 1]) if w1 > w0 else e0
+        self.epi_range = (e0, e1)
+        a0, a1, adr = lists_of(rank)
+        s0 = int(w.spj_disp[w0]) if w1 > w0 else 0
+        s1 = int(w.spj_disp[w1 - 1] + w.n_spj[w1 - 1]) if w1 > w0 else 0
+        self.adr_epj_range, self.adr_spj_range = (a0, a1), (s0, s1)
+        own = (adr >= p0) & (adr < p1)
+        adr_l = np.where(own, adr - p0, self.n_own + np.searchsorted(need, adr)).astype(np.int32)
+        self.need = need
+        self.local = Walks(w.epi[e0:e1], w.epi_off[w0:w1] - e0, w.ni[w0:w1],
+                           adr_l, w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
+                           w.adr_spj[s0:s1], w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
+                           w.epj_all[p0:p1], w.spj_all)
+        lw = self.local
+        c = np.concatenate([[0], np.cumsum(own.astype(np.int64))])
+        d0 = lw.epj_disp
+        self.interior = (c[d0 + lw.n_epj] - c[d0]) == lw.n_epj
+        self.walks_interior = self.subset(np.nonzero(self.interior)[0])
+        self.walks_boundary = self.subset(np.nonzero(~self.interior)[0])
+
+    subset = Shard.subset

@@ -115,6 +115,9 @@ int gplum_b200_walks_set_packed_dev(const void *epj_packed_dev, int n_epj_all,
  * the library stream): the per-rank step before the all-gather. */
 int gplum_b200_pack_epj_dev(const void *epj_aos_dev, int n, void *epj_packed_dev);
 int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev);
+/* dst[k] = src[idx[k]] on packed EP records (device pointers): stages the particles another rank's
+ * boundary walks need (the trimmed LET exchange) before an all-to-all. */
+int gplum_b200_gather_epj_packed_dev(const void *src_packed_dev, const int *idx_dev, int n, void *dst_packed_dev);
 void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes);
 
 /* Use an existing CUDA stream (cudaStream_t as void*) for the batched / device-resident

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 import oracle_api as O
 from gplum_b200 import disk, structs as S, tree
-from gplum_b200.shard import Shard, split_walks
+from gplum_b200.shard import HaloShard, Shard, split_walks
 
 
 def _workload():
@@ -62,9 +62,38 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_pass_equals_single_rank(world, tmp_path):
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+def _worker_halo(rank, world, port, out_dir):
+    """Trimmed exchange: own particles + one all-to-all of the records other ranks' walks need."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = _workload()
+    sh = HaloShard(w, world, rank)
+    lw = sh.local
+    nb = S.EPJ.itemsize
+    send = torch.from_numpy(lw.epj_all[sh.send_idx].view(np.uint8).reshape(-1, nb).copy())
+    recv = torch.zeros((sh.n_halo, nb), dtype=torch.uint8)
+    dist.all_to_all_single(recv, send, sh.recv_counts, sh.send_counts)
+    jl = np.concatenate([lw.epj_all, recv.numpy().reshape(-1).view(S.EPJ)])
+    a0, a1 = sh.adr_epj_range
+    assert jl[lw.adr_epj].tobytes() == w.epj_all[w.adr_epj[a0:a1]].tobytes()
+    assert sum(sh.recv_counts) == sh.n_halo and sh.n_halo < len(w.epj_all) - sh.n_own   # trimmed, not everything
+    own_only = jl.copy(); own_only[sh.n_own:] = 0                 # interior walks must not touch the halo
+    f = S.cleared_force(len(lw.epi)); n_int = 0
+    for part, jarr in ((sh.walks_interior, own_only), (sh.walks_boundary, jl)):
+        pw = O.Walks(part.epi, part.epi_off, part.ni, part.adr_epj, part.epj_disp, part.n_epj, part.adr_spj,
+                     part.spj_disp, part.n_spj, jarr, w.spj_all)
+        f, n = O.calc_walks(pw, 0.0, force=f)
+        n_int += n
+    np.save(os.path.join(out_dir, "f%d.npy" % rank), f)
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array(list(sh.epi_range) + [n_int]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,worker", [(2, _worker), (3, _worker), (2, _worker_halo), (3, _worker_halo)])
+def test_sharded_pass_equals_single_rank(world, worker, tmp_path):
+    mp.spawn(worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     w = _workload()
     want, n_tot = O.calc_walks(w, 0.0)
     got = S.cleared_force(len(w.epi)); covered = 0; n_sum = 0
