@@ -151,8 +151,10 @@ def main():
     ap.add_argument("--group", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="halo", choices=["halo", "allgather"],
-                    help="N>1: trimmed halo all-to-all (the reference's LET idea) or a full all-gather of the packed EPJ")
+    ap.add_argument("--boundary-cap", type=int, default=32, help="N>1: i-particles per work item of the boundary walks")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "allgather"],
+                    help="N>1: boundary walks read peer HBM over NVLink inside the kernel (CUDA IPC), or a trimmed "
+                         "halo all-to-all (the reference's LET idea), or a full all-gather of the packed EPJ")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -200,7 +202,7 @@ def main():
         def step():
             F.walks_run(repack=True)
     else:
-        mg = MultiGpuPass(w, world, rank, stream, exchange=args.exchange)
+        mg = MultiGpuPass(w, world, rank, stream, exchange=args.exchange, boundary_cap=args.boundary_cap)
         sh, lw = mg.sh, mg.lw
         wi, wb = sh.walks_interior, sh.walks_boundary
         my_int = sum(lw.n_interactions())
@@ -242,7 +244,17 @@ def main():
             exchange().wait()
         eb.record(stream)
         torch.cuda.synchronize()
-        phases = {"exchange": args.exchange, "exchange_ms": ea.elapsed_time(eb) / 10, "interior_kernel_ms": k_int, "boundary_kernel_ms": k_bnd,
+        my_step_ms = ms / args.steps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            step()
+        host_ms = (time.perf_counter() - t0) / 10 * 1e3          # host enqueue time per step (no sync inside)
+        barrier()
+        tr = {}
+        mg.step(trace=tr)
+        timeline = mg.trace_ms(tr)
+        phases = {"rank": rank, "step_ms": my_step_ms, "host_enqueue_ms": host_ms, "timeline_ms": timeline, "exchange": args.exchange, "exchange_ms": ea.elapsed_time(eb) / 10, "interior_kernel_ms": k_int, "boundary_kernel_ms": k_bnd,
                   "interior_walks": int(wi.n_walk), "boundary_walks": int(wb.n_walk),
                   "exchange_bytes": int(exch_bytes)}
     peak_tf, _ = F.fp32_peak(10)
@@ -261,7 +273,8 @@ def main():
                 "list_bytes_per_launch": alg_bytes}
 
     # ------------------------------------------------------------------ end to end via the C ABI
-    check(L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
+    if world > 1:
+        mg.close()
     F.walks_select(0)
     if world == 1:
         lw = w
@@ -315,6 +328,12 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    all_phases = None
+    if world > 1:
+        all_phases = [None] * world
+        dist.all_gather_object(all_phases, {k: (round(v, 4) if isinstance(v, float) else v) for k, v in phases.items()
+                                            if k in ("rank", "step_ms", "host_enqueue_ms", "timeline_ms", "exchange_ms", "interior_kernel_ms", "boundary_kernel_ms",
+                                                     "interior_walks", "boundary_walks")})
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -327,6 +346,7 @@ def main():
            "list_build_s_host": t_build}
     if world > 1:
         out["phases_rank0"] = phases
+        out["phases_all"] = all_phases
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count()
         kind, s, O, libname = cpu_reference_run(w, 0.0, args.cpu_seconds, threads)

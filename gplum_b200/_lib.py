@@ -25,6 +25,7 @@ SYMBOLS = {
     "gplum_b200_calc_walks": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i, _vp, _i]),
     "gplum_b200_walks_upload": (_i, [_i] + [_vp] * 10 + [_i, _vp, _i]),
     "gplum_b200_walks_select": (_i, [_i]),
+    "gplum_b200_set_tile_cap": (_i, [_i]),
     "gplum_b200_walks_run": (_i, [_i]),
     "gplum_b200_walks_pack": (_i, []),
     "gplum_b200_walks_download": (_i, [_vp]),
@@ -33,6 +34,11 @@ SYMBOLS = {
     "gplum_b200_pack_epj_dev": (_i, [_vp, _i, _vp]),
     "gplum_b200_pack_spj_dev": (_i, [_vp, _i, _vp]),
     "gplum_b200_gather_epj_packed_dev": (_i, [_vp, _vp, _i, _vp]),
+    "gplum_b200_peer_setup": (_i, [_i, _i, _i, _vp]),
+    "gplum_b200_peer_open": (_i, [_vp]),
+    "gplum_b200_peer_pack": (_i, [_vp, _i]),
+    "gplum_b200_peer_close": (_i, []),
+    "gplum_b200_peer_free": (_i, []),
     "gplum_b200_packed_sizes": (None, [C.POINTER(_i), C.POINTER(_i)]),
     "gplum_b200_set_stream": (_i, [_vp]),
     "gplum_b200_synchronize": (_i, []),

@@ -105,6 +105,17 @@ struct JSet {
 };
 
 constexpr int N_TAG = 4;
+constexpr int MAX_PEERS = 16;
+
+// Multi-GPU peer mode: every rank owns two slabs (double buffer) of packed EP records; the other
+// ranks' slabs are mapped with CUDA IPC, so boundary walks read them straight over NVLink.
+struct Peer {
+    bool on = false;
+    int world = 0, rank = 0, shift = 0, parity = 0;
+    void *slab[2] = {nullptr, nullptr};               // this rank's own slabs (cudaMalloc)
+    void *mapped[2][MAX_PEERS] = {};                    // every rank's slabs in this process' address space
+    DevBuf table[2];                                    // device copies of mapped[b][0..world)
+};
 
 struct Ctx {
     bool ready = false;
@@ -113,6 +124,7 @@ struct Ctx {
     float eps2 = 0.0f;
     int quad = 1, flags = 0;
     JSet jset;
+    Peer peer;
     WalkSet slots[N_TAG];
     std::atomic<long long> launches{0}, n_epep{0}, n_epsp{0};
     std::mutex mu;
@@ -120,6 +132,7 @@ struct Ctx {
     int rmax = 2;               // i-particles per lane (GPLUM_B200_RMAX = 2 or 4)
     int cur = 0;                // resident walk set used by the walks_* calls
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
+    int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
 };
 Ctx g;
@@ -139,12 +152,14 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     tmp.reserve((size_t)n_walk * 2);
     // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
     const bool split = g.jsplit != 0;
-    // Tile capacity: 64 i-particles per warp is the most efficient shape, but one such item is a
-    // serial chain of ~1e5 issue slots; when a pass has too few of them to fill the GPU twice
-    // (small per-GPU shards, boundary sets) use 32, or j-split tiles of 16 / 8 / 4, instead.
+    // Tile capacity: 64 i-particles per warp is the most efficient shape (staging is amortised over
+    // the most pairs), and measured on 1/4- and 1/8-size shards it stays the fastest even at 0.6 waves.
+    // Only a pass that cannot give every fourth warp slot an item (per-call functor form, a small
+    // boundary set) is latency-bound on one item's serial chain: there use 32, or j-split tiles.
     int cap = g.rmax >= 2 ? 64 : 32;
-    if (split && g.rmax <= 2) {
-        const long long target = 2LL * g.warp_slots;
+    if (g.tile_cap > 0) cap = std::min(cap, g.tile_cap);
+    else if (split && g.rmax <= 2) {
+        const long long target = g.warp_slots / 4;
         for (; cap > 4; cap >>= 1) {
             long long n_it = 0;
             for (int w = 0; w < n_walk; w++) n_it += (ni[w] + cap - 1) / cap;
@@ -190,6 +205,8 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
     p.adr_epj = (const int *)ws.adr_epj.p; p.epj_disp = (const long long *)ws.epj_disp.p; p.n_epj = (const int *)ws.n_epj.p;
     p.adr_spj = (const int *)ws.adr_spj.p; p.spj_disp = (const long long *)ws.spj_disp.p; p.n_spj = (const int *)ws.n_spj.p;
     p.epj = g.jset.epj(); p.spj = g.jset.spj();
+    p.peer_epj = g.peer.on ? (const EpjPacked *const *)g.peer.table[g.peer.parity].p : nullptr;
+    p.peer_shift = g.peer.shift;
     p.force = (ForceAos *)ws.force.p;
     p.items = (const WorkItem *)ws.items.p;
     p.eps2 = eps2;
@@ -365,6 +382,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.spj_disp = (const long long *)(dm + offsetof(Meta, spj_disp));
     p.adr_epj = (const int *)s.iota.p; p.adr_spj = (const int *)s.iota.p;
     p.epj = (const EpjPacked *)s.jpacked.p; p.spj = (const SpjPacked *)s.jpacked.p;
+    p.peer_epj = nullptr; p.peer_shift = 0;
     p.force = (ForceAos *)s.force.p;
     p.items = (const WorkItem *)(dm + sizeof(Meta));
     p.eps2 = eps2;
@@ -431,6 +449,8 @@ int gplum_b200_finalize(void)
     if (!g.ready) return 0;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
+    gplum_b200_peer_close();
+    gplum_b200_peer_free();
     g.jset.release();
     for (auto &s : g.slots) s.release();
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
@@ -444,6 +464,14 @@ int gplum_b200_set_params(float eps2, int quad, int flags)
 {
     g.eps2 = eps2; g.quad = quad ? 1 : 0;
     if (flags >= 0) g.flags = flags;      // flags < 0: keep the current ones (e.g. GPLUM_B200_FLAGS)
+    return 0;
+}
+
+int gplum_b200_set_tile_cap(int cap)
+{
+    if (cap != 0 && cap != 64 && cap != 32 && cap != 16 && cap != 8 && cap != 4)
+        return fail(GPLUM_B200_ERR_ARG, "tile cap %d not in {0, 64, 32, 16, 8, 4}", cap);
+    g.tile_cap = cap;
     return 0;
 }
 
@@ -699,6 +727,87 @@ int gplum_b200_gather_epj_packed_dev(const void *src_packed_dev, const int *idx_
     gather_epj_packed_kernel<<<(3 * n + 255) / 256, 256, 0, g.stream>>>((const uint4 *)src_packed_dev, idx_dev, n, (uint4 *)dst_packed_dev);
     CU(cudaGetLastError());
     g.launches++;
+    return 0;
+}
+
+// ---- multi-GPU peer mode ----
+int gplum_b200_peer_setup(int world, int rank, int shift, void *handles_out)
+{
+    if (int r = ensure_init()) return r;
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world || shift < 1 || shift > 30 || !handles_out)
+        return fail(GPLUM_B200_ERR_ARG, "peer_setup(world=%d, rank=%d, shift=%d)", world, rank, shift);
+    if ((long long)world << shift > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "world << shift overflows the int index space");
+    CU(cudaSetDevice(g.device));
+    Peer &pe = g.peer;
+    if (pe.slab[0]) return fail(GPLUM_B200_ERR_STATE, "peer mode already set up");
+    pe.world = world; pe.rank = rank; pe.shift = shift; pe.parity = 0;
+    for (int b = 0; b < 2; b++) {
+        CU(cudaMalloc(&pe.slab[b], ((size_t)1 << shift) * sizeof(EpjPacked)));
+        CU(cudaMemset(pe.slab[b], 0, ((size_t)1 << shift) * sizeof(EpjPacked)));
+        CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handles_out + b, pe.slab[b]));
+    }
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+int gplum_b200_peer_open(const void *all_handles)
+{
+    if (int r = ensure_init()) return r;
+    Peer &pe = g.peer;
+    if (!pe.slab[0] || !all_handles) return fail(GPLUM_B200_ERR_STATE, "peer_open before peer_setup");
+    CU(cudaSetDevice(g.device));
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)all_handles;
+    for (int b = 0; b < 2; b++) {
+        for (int q = 0; q < pe.world; q++) {
+            if (q == pe.rank) { pe.mapped[b][q] = pe.slab[b]; continue; }
+            CU(cudaIpcOpenMemHandle(&pe.mapped[b][q], h[2 * q + b], cudaIpcMemLazyEnablePeerAccess));
+        }
+        if (int r = pe.table[b].reserve(sizeof(void *) * MAX_PEERS)) return r;
+        CU(cudaMemcpy(pe.table[b].p, pe.mapped[b], sizeof(void *) * pe.world, cudaMemcpyHostToDevice));
+    }
+    pe.on = true;
+    return 0;
+}
+
+int gplum_b200_peer_pack(const void *epj_aos_dev, int n)
+{
+    if (int r = ensure_init()) return r;
+    Peer &pe = g.peer;
+    if (!pe.on) return fail(GPLUM_B200_ERR_STATE, "peer_pack without peer_open");
+    if (n < 0 || n > (1 << pe.shift)) return fail(GPLUM_B200_ERR_ARG, "peer_pack n=%d exceeds the slab (%d)", n, 1 << pe.shift);
+    CU(cudaSetDevice(g.device));
+    pe.parity ^= 1;                  // peers may still be reading the slab of the previous step
+    if (n > 0) {
+        pack_epj_kernel<<<(n + 255) / 256, 256, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)pe.slab[pe.parity]);
+        CU(cudaGetLastError());
+        g.launches++;
+    }
+    return 0;
+}
+
+int gplum_b200_peer_close(void)
+{
+    Peer &pe = g.peer;
+    if (!pe.slab[0]) return 0;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    for (int b = 0; b < 2; b++) {
+        for (int q = 0; q < pe.world; q++)
+            if (pe.on && q != pe.rank && pe.mapped[b][q]) cudaIpcCloseMemHandle(pe.mapped[b][q]);
+        pe.table[b].release();
+    }
+    // the slabs themselves are freed by the caller's barrier-then-free protocol: peers must have
+    // closed their mappings first (see gplum_b200/multigpu.py)
+    pe.on = false;
+    return 0;
+}
+
+int gplum_b200_peer_free(void)
+{
+    Peer &pe = g.peer;
+    cudaSetDevice(g.device);
+    for (int b = 0; b < 2; b++) { if (pe.slab[b]) cudaFree(pe.slab[b]); pe.slab[b] = nullptr; }
+    pe = Peer();
     return 0;
 }
 

@@ -64,6 +64,9 @@ struct PassParams {
     const int *adr_epj; const long long *epj_disp; const int *n_epj;
     const int *adr_spj; const long long *spj_disp; const int *n_spj;
     const EpjPacked *epj; const SpjPacked *spj;
+    // multi-GPU peer mode: EP index = (owner rank << peer_shift) | index in the owner's slab; slabs of
+    // the other ranks are their HBM, mapped through CUDA IPC and read over NVLink by the same cp.async
+    const EpjPacked *const *peer_epj; int peer_shift;
     ForceAos *force;
     const WorkItem *items;
     float eps2;
@@ -104,11 +107,29 @@ __device__ __forceinline__ float4 ldg_f4(const void *p)
 // ------------------------------------------------------------------------------------------
 // pack kernels: AoS (as FDPS holds epj_sorted_/spj_sorted_) -> packed records
 // ------------------------------------------------------------------------------------------
-__global__ void pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
+// A block's 256 AoS records are first copied to shared memory with coalesced 16 B loads (a thread
+// reading its own 112 B / 80 B record straight from HBM touches 4-5 sectors per load instruction);
+// each thread then picks its fields from shared memory.  `in` must be 16 B aligned.
+constexpr int PACK_BLOCK = 256;
+template <int REC>
+__device__ __forceinline__ void stage_records(const void *__restrict__ in, int n, unsigned char *sm)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    static_assert(REC % 16 == 0, "record size");
+    const int first = blockIdx.x * PACK_BLOCK;
+    const int cnt = min(PACK_BLOCK, n - first);
+    const int n16 = cnt * (REC / 16);
+    const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(in) + (size_t)first * REC);
+    for (int k = threadIdx.x; k < n16; k += PACK_BLOCK) reinterpret_cast<uint4 *>(sm)[k] = __ldg(src + k);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PACK_BLOCK) pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
+{
+    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(EpjAos)];
+    stage_records<sizeof(EpjAos)>(in, n, sm);
+    const int i = blockIdx.x * PACK_BLOCK + threadIdx.x;
     if (i >= n) return;
-    const EpjAos &a = in[i];
+    const EpjAos &a = reinterpret_cast<const EpjAos *>(sm)[threadIdx.x];
     EpjPacked o;
     o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2];
     o.m = (float)a.mass;
@@ -131,14 +152,17 @@ __global__ void gather_epj_packed_kernel(const uint4 *__restrict__ src, const in
 
 // quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
 // src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).
-__global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
+__global__ void __launch_bounds__(PACK_BLOCK) pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
                                 int quad, int trace_as_shipped, float eps2)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(SpjQuadAos)];
+    if (quad) stage_records<sizeof(SpjQuadAos)>(in, n, sm);
+    else stage_records<sizeof(SpjMonoAos)>(in, n, sm);
+    const int i = blockIdx.x * PACK_BLOCK + threadIdx.x;
     if (i >= n) return;
     SpjPacked o;
     if (quad) {
-        const SpjQuadAos &a = ((const SpjQuadAos *)in)[i];
+        const SpjQuadAos &a = reinterpret_cast<const SpjQuadAos *>(sm)[threadIdx.x];
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
         const float qxx = (float)a.quad[0], qyy = (float)a.quad[1], qzz = (float)a.quad[2];
         const float qxy = (float)a.quad[3], qzx = (float)a.quad[4], qyz = (float)a.quad[5];
@@ -150,7 +174,7 @@ __global__ void pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *_
         o.qxy = 0.25f * __fmul_rn(3.0f, qxy); o.qyz = 0.25f * __fmul_rn(3.0f, qyz); o.qzx = 0.25f * __fmul_rn(3.0f, qzx);
         o.mtr = -0.25f * __fmul_rn(eps2, tr);
     } else {
-        const SpjMonoAos &a = ((const SpjMonoAos *)in)[i];
+        const SpjMonoAos &a = reinterpret_cast<const SpjMonoAos *>(sm)[threadIdx.x];
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
         o.qxx = o.qyy = o.qzz = o.qxy = o.qyz = o.qzx = 0.0f; o.mtr = 0.0f;
     }
@@ -221,7 +245,8 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         if (idx < 0) return;
         float4 *dst = &s.raw[(lane + 32 * k) * 4];
         if (t < nt_ep) {
-            const char *q = reinterpret_cast<const char *>(p.epj + idx);
+            const EpjPacked *rec = p.peer_epj ? p.peer_epj[idx >> p.peer_shift] + (idx & ((1 << p.peer_shift) - 1)) : p.epj + idx;
+            const char *q = reinterpret_cast<const char *>(rec);
             cp_async16(dst + 0, q); cp_async16(dst + 1, q + 16); cp_async16(dst + 2, q + 32);
         } else {
             const char *q = reinterpret_cast<const char *>(p.spj + idx);

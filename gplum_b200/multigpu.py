@@ -17,14 +17,21 @@ from .shard import HaloShard, Shard
 
 
 class MultiGpuPass:
-    """`exchange` = "halo": one all-to-all of only the records other ranks' boundary walks read;
-    "allgather": in-place all-gather of every rank's packed slab."""
+    """`exchange` =
+    "peer"      no data moves ahead of time: every rank packs into its own slab, the slabs are
+                mapped into every process with CUDA IPC and boundary walks gather the records they
+                need straight from the owner's HBM over NVLink, tile by tile, inside the force
+                kernel; the only collective is one tiny all-reduce per step that orders "all slabs
+                packed" before "boundary walks start" (slabs are double-buffered, so one barrier
+                per step also covers the write-after-read hazard);
+    "halo"      one all-to-all of only the records other ranks' boundary walks read;
+    "allgather" in-place all-gather of every rank's packed slab."""
 
-    def __init__(self, w, world, rank, stream, exchange="halo"):
+    def __init__(self, w, world, rank, stream, exchange="peer", boundary_cap=32):
         L = lib()
         self.L, self.stream, self.exchange_kind = L, stream, exchange
-        halo = exchange == "halo"
-        self.sh = sh = (HaloShard if halo else Shard)(w, world, rank)
+        halo, peer = exchange == "halo", exchange == "peer"
+        self.sh = sh = HaloShard(w, world, rank) if halo else Shard(w, world, rank, pow2_cap=peer)
         self.lw = lw = sh.local
         eb, sb = C.c_int(0), C.c_int(0)
         L.gplum_b200_packed_sizes(C.byref(eb), C.byref(sb))
@@ -36,9 +43,13 @@ class MultiGpuPass:
         # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
         F.walks_select(0)
         F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
-                                wi.spj_disp, wi.n_spj, np.zeros(0, S.EPJ), w.spj_all))
+                                wi.spj_disp, wi.n_spj, np.zeros(0, S.EPJ), lw.spj_all))
         F.walks_select(1)
+        # the boundary set is small, but it co-runs with the interior kernel on a busy GPU: throughput,
+        # not one item's latency, is what counts -> full-width tiles instead of the per-pass choice
+        check(L.gplum_b200_set_tile_cap(boundary_cap))
         F.walks_upload(wb, with_j=False)
+        check(L.gplum_b200_set_tile_cap(0))
         vp = lambda t: C.c_void_p(t.data_ptr())
         if halo:
             # local j-array = [own | halo]: own particles are packed in place, the halo region is the
@@ -51,13 +62,26 @@ class MultiGpuPass:
             self.d_send_idx = torch.from_numpy(np.ascontiguousarray(sh.send_idx)).cuda()
             check(L.gplum_b200_walks_set_packed_dev(vp(self.jbuf), n_own + n_halo, None, 0))
             self.exchange_bytes = (n_send + n_halo) * EB
+        elif peer:
+            h = (C.c_char * 128)()
+            check(L.gplum_b200_peer_setup(world, rank, sh.shift, h))
+            mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).cuda()
+            every = torch.zeros(world * 128, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine)
+            self._handles = every.cpu().numpy().tobytes()
+            check(L.gplum_b200_peer_open(self._handles))
+            self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            self.exchange_bytes = 4
+            dist.barrier()
         else:
             # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
             self.jbuf = torch.zeros(world * sh.epj_cap * EB, dtype=torch.uint8, device="cuda")
             self.my_slab = self.jbuf[rank * sh.epj_cap * EB:(rank + 1) * sh.epj_cap * EB]
             check(L.gplum_b200_walks_set_packed_dev(vp(self.jbuf), world * sh.epj_cap, None, 0))
             self.exchange_bytes = int(self.jbuf.numel())
-        self.side = torch.cuda.Stream()    # boundary walks: start when the exchange lands, co-run with the interior tail
+        # boundary walks: start when the exchange lands; HIGH priority so that their CTAs are scheduled
+        # ahead of the interior kernel's not-yet-resident CTAs and the two kernels really co-run
+        self.side = torch.cuda.Stream(priority=-1)
         self.ev_side, self.ev_pack = torch.cuda.Event(), torch.cuda.Event()
 
     def _use(self, st):
@@ -66,6 +90,9 @@ class MultiGpuPass:
     def exchange(self):
         """Pack own EPJ, start the NCCL exchange; returns the async work handle."""
         L, vp = self.L, (lambda t: C.c_void_p(t.data_ptr()))
+        if self.exchange_kind == "peer":
+            check(L.gplum_b200_peer_pack(vp(self.d_epj_raw), len(self.lw.epj_all)))
+            return dist.all_reduce(self.flag, async_op=True)       # barrier: every slab is packed
         check(L.gplum_b200_pack_epj_dev(vp(self.d_epj_raw), len(self.lw.epj_all), vp(self.my_slab)))
         if self.exchange_kind == "halo":
             check(L.gplum_b200_gather_epj_packed_dev(vp(self.my_slab), vp(self.d_send_idx), len(self.sh.send_idx),
@@ -74,22 +101,42 @@ class MultiGpuPass:
                                           async_op=True)
         return dist.all_gather_into_tensor(self.jbuf, self.my_slab, async_op=True)
 
-    def step(self):
+    def step(self, trace=None):
+        """One force pass of this rank.  trace: optional dict that receives timing events."""
         stream, side = self.stream, self.side
+        if trace is not None:
+            ev = {k: torch.cuda.Event(enable_timing=True) for k in ("start", "packed", "int_end", "side_ready", "bnd_end")}
+            ev["start"].record(stream)
         work = self.exchange()
         check(self.L.gplum_b200_walks_pack())      # SPJ pack (every rank holds the cells itself)
         self.ev_pack.record(stream)
+        if trace is not None:
+            ev["packed"].record(stream)
         F.walks_select(0)
         F.walks_run(repack=False)          # interior walks: overlap the exchange
+        if trace is not None:
+            ev["int_end"].record(stream)
         with torch.cuda.stream(side):
             work.wait()                    # the side stream waits for NCCL ...
             side.wait_event(self.ev_pack)  # ... and for the packed SPJ
+            if trace is not None:
+                ev["side_ready"].record(side)
             self._use(side)
             F.walks_select(1)
             F.walks_run(repack=False)      # boundary walks read the other ranks' particles
             self.ev_side.record(side)
+            if trace is not None:
+                ev["bnd_end"].record(side)
         self._use(stream)
         stream.wait_event(self.ev_side)
+        if trace is not None:
+            trace["events"] = ev
+
+    @staticmethod
+    def trace_ms(trace):
+        torch.cuda.synchronize()
+        ev = trace["events"]
+        return {k: round(ev["start"].elapsed_time(ev[k]), 4) for k in ("packed", "int_end", "side_ready", "bnd_end")}
 
     def forces(self):
         """This rank's forces (host, ForceGrav[ len(local.epi) ]) after step()."""
@@ -108,5 +155,11 @@ class MultiGpuPass:
         return out
 
     def close(self):
+        torch.cuda.synchronize()
+        if self.exchange_kind == "peer":
+            dist.barrier()                         # nobody reads a peer slab any more
+            check(self.L.gplum_b200_peer_close())
+            dist.barrier()                         # every mapping is closed before a slab is freed
+            check(self.L.gplum_b200_peer_free())
         check(self.L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
         F.walks_select(0)

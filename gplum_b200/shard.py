@@ -31,11 +31,20 @@ def split_walks(w, world):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
+def trim_spj(w, s0, s1):
+    """A rank holds only the superparticles its own walks reference (in the reference each rank's
+    spj_sorted_ is its own LET's, FDPS/src/tree_for_force_impl_exlet.hpp): returns the remapped
+    index list, the compact SPJ array and the global indices it was taken from."""
+    adr = w.adr_spj[s0:s1]
+    used = np.unique(adr)
+    return np.searchsorted(used, adr).astype(np.int32), w.spj_all[used], used
+
+
 class Shard:
     """Everything rank `rank` needs: its walks (re-indexed to the padded gather layout), the
     range of j-particles / cells it packs, and the padded slab sizes."""
 
-    def __init__(self, w, world, rank):
+    def __init__(self, w, world, rank, pow2_cap=False):
         self.world, self.rank = world, rank
         ranges = split_walks(w, world)
         # particle (EPJ) ownership = Morton range of the rank's i-particles
@@ -44,6 +53,9 @@ class Shard:
         p_hi = p_lo[1:] + [len(w.epj_all)]
         self.epj_ranges = list(zip(p_lo, p_hi))
         self.epj_cap = max(b - a for a, b in self.epj_ranges)
+        if pow2_cap:            # peer mode: index = (owner << shift) | local
+            self.shift = max(1, int(self.epj_cap - 1).bit_length())
+            self.epj_cap = 1 << self.shift
         self.walk_range = ranges[rank]
         w0, w1 = ranges[rank]
         e0 = int(w.epi_off[w0]) if w0 < w.n_walk else len(w.epi)
@@ -55,10 +67,11 @@ class Shard:
         s1 = int(w.spj_disp[w1 - 1] + w.n_spj[w1 - 1]) if w1 > w0 else 0
         self.adr_epj_range, self.adr_spj_range = (a0, a1), (s0, s1)
         adr_e = self.remap(w.adr_epj[a0:a1], self.epj_ranges, self.epj_cap)
+        adr_s, spj_loc, self.spj_used = trim_spj(w, s0, s1)
         self.local = Walks(w.epi[e0:e1], w.epi_off[w0:w1] - e0, w.ni[w0:w1],
                            adr_e, w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
-                           w.adr_spj[s0:s1], w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
-                           w.epj_all[self.epj_ranges[rank][0]:self.epj_ranges[rank][1]], w.spj_all)
+                           adr_s, w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
+                           w.epj_all[self.epj_ranges[rank][0]:self.epj_ranges[rank][1]], spj_loc)
         # interior walks: every EP index inside this rank's own slab of the gather buffer
         lo, hi = rank * self.epj_cap, rank * self.epj_cap + (self.epj_ranges[rank][1] - self.epj_ranges[rank][0])
         lw = self.local
@@ -146,10 +159,11 @@ class HaloShard:
         own = (adr >= p0) & (adr < p1)
         adr_l = np.where(own, adr - p0, self.n_own + np.searchsorted(need, adr)).astype(np.int32)
         self.need = need
+        adr_s, spj_loc, self.spj_used = trim_spj(w, s0, s1)
         self.local = Walks(w.epi[e0:e1], w.epi_off[w0:w1] - e0, w.ni[w0:w1],
                            adr_l, w.epj_disp[w0:w1] - a0, w.n_epj[w0:w1],
-                           w.adr_spj[s0:s1], w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
-                           w.epj_all[p0:p1], w.spj_all)
+                           adr_s, w.spj_disp[w0:w1] - s0, w.n_spj[w0:w1],
+                           w.epj_all[p0:p1], spj_loc)
         lw = self.local
         c = np.concatenate([[0], np.cumsum(own.astype(np.int64))])
         d0 = lw.epj_disp

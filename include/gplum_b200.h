@@ -99,6 +99,10 @@ int gplum_b200_calc_walks(int n_walk, const void *epi_all, const int *epi_off, c
  * _download and _time act on the selected one.  walks_upload with epj_all == spj_all == NULL
  * keeps the current j-set. */
 int gplum_b200_walks_select(int slot);
+/* i-particles per work item for the walk sets uploaded / dispatched next: 64 (two per lane, the most
+ * efficient), 32, or 16 / 8 / 4 (j-lists split over lane groups); 0 = chosen per pass: 64 unless the
+ * pass has too few items to occupy a quarter of the GPU's warp slots (latency-bound small passes). */
+int gplum_b200_set_tile_cap(int cap);
 int gplum_b200_walks_upload(int n_walk, const void *epi_all, const int *epi_off, const int *ni,
                             const int *adr_epj, const long long *epj_disp, const int *n_epj,
                             const int *adr_spj, const long long *spj_disp, const int *n_spj,
@@ -119,6 +123,21 @@ int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev
  * boundary walks need (the trimmed LET exchange) before an all-to-all. */
 int gplum_b200_gather_epj_packed_dev(const void *src_packed_dev, const int *idx_dev, int n, void *dst_packed_dev);
 void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes);
+
+/* ---- multi-GPU peer mode: boundary walks read the other ranks' packed EPJ straight over NVLink ----
+ * Every rank owns two slabs (double buffer) of 2^shift packed records; EP list indices are
+ * (owner_rank << shift) | index_in_owner_slab.  peer_setup allocates the slabs and writes this
+ * rank's two CUDA IPC handles (2 x 64 bytes) to handles_out; the caller all-gathers the handles
+ * (rank-major) and passes them to peer_open.  peer_pack flips the buffer and packs n AoS records
+ * (device pointer) into this rank's slab on the library stream; the caller then runs ONE barrier
+ * collective per step before launching walks that read other ranks' slabs.  Replaces the EPJ part
+ * of FDPS's LET exchange (FDPS/src/tree_for_force_impl_exlet.hpp:343-403) without moving data
+ * ahead of time.  peer_close unmaps, peer_free (after a barrier) releases the slabs. */
+int gplum_b200_peer_setup(int world, int rank, int shift, void *handles_out);
+int gplum_b200_peer_open(const void *all_handles);
+int gplum_b200_peer_pack(const void *epj_aos_dev, int n);
+int gplum_b200_peer_close(void);
+int gplum_b200_peer_free(void);
 
 /* Use an existing CUDA stream (cudaStream_t as void*) for the batched / device-resident
  * forms, so that a caller's events on that stream bracket the kernels.  NULL = own stream. */

@@ -57,7 +57,7 @@ def _worker(rank, world, port, out_dir, exchange):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("exchange", ["halo", "allgather"])
+@pytest.mark.parametrize("exchange", ["peer", "halo", "allgather"])
 def test_two_ranks_match_single_rank_oracle(exchange, tmp_path):
     import torch.multiprocessing as mp
     import oracle_api as O

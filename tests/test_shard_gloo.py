@@ -52,7 +52,7 @@ def _worker(rank, world, port, out_dir):
     f = S.cleared_force(len(lw.epi)); n_int = 0
     for part, jarr in ((sh.walks_interior, own), (sh.walks_boundary, epj_g)):
         pw = O.Walks(part.epi, part.epi_off, part.ni, part.adr_epj, part.epj_disp, part.n_epj, part.adr_spj,
-                     part.spj_disp, part.n_spj, jarr, w.spj_all)
+                     part.spj_disp, part.n_spj, jarr, lw.spj_all)
         f, n = O.calc_walks(pw, 0.0, force=f)
         n_int += n
     assert sh.interior.sum() + (~sh.interior).sum() == lw.n_walk and (world == 1 or (~sh.interior).any())
@@ -82,7 +82,7 @@ def _worker_halo(rank, world, port, out_dir):
     f = S.cleared_force(len(lw.epi)); n_int = 0
     for part, jarr in ((sh.walks_interior, own_only), (sh.walks_boundary, jl)):
         pw = O.Walks(part.epi, part.epi_off, part.ni, part.adr_epj, part.epj_disp, part.n_epj, part.adr_spj,
-                     part.spj_disp, part.n_spj, jarr, w.spj_all)
+                     part.spj_disp, part.n_spj, jarr, lw.spj_all)
         f, n = O.calc_walks(pw, 0.0, force=f)
         n_int += n
     np.save(os.path.join(out_dir, "f%d.npy" % rank), f)
