@@ -31,3 +31,25 @@ def cleared_force(n):
     f["id_max"] = ID_MAX_CLEAR
     f["id_min"] = ID_MIN_CLEAR
     return f
+
+# ---- changeover correction (correctForceLong, src/gravity_soft.h:245-372): results per i-particle ----
+# CORR      acc/phi are the FP64 corrections to ADD to the (widened) tree force; `number` neighbours
+#           start at ngb[ngb_off]; id_local is the pp index FDPS's write-back would target
+# CORR_INIT the extra sums of correctForceLongInitial (:375-528)
+# NGB       NeighborId (src/neighbor.h:205-245)
+CORR = np.dtype([("acc", "<f8", (3,)), ("phi", "<f8"), ("acc0", "<f8"), ("id_cluster", "<i8"),
+                 ("number", "<i4"), ("id_local", "<i4"), ("ngb_off", "<i4"), ("in_domain", "<i4")], align=True)
+CORR_INIT = np.dtype([("acc_d", "<f8", (3,)), ("jerk_d", "<f8", (3,)), ("phi_d", "<f8"), ("pad", "<f8")], align=True)
+NGB = np.dtype([("id", "<i8"), ("rank", "<i4"), ("id_local", "<i4")], align=True)
+CORR_PARAMS = np.dtype([("eps2", "<f8"), ("dt_tree", "<f8"), ("gamma", "<f8"), ("R_search2", "<f8"),
+                        ("R_search3", "<f8"), ("re_search", "<i4"), ("initial", "<i4")], align=True)
+assert CORR.itemsize == 64 and CORR_INIT.itemsize == 64 and NGB.itemsize == 16 and CORR_PARAMS.itemsize == 48
+
+
+def corr_params(eps2=0.0, dt_tree=2.0 ** -6, gamma=0.5, R_search2=1.0, R_search3=4.0, re_search=True, initial=False):
+    """Defaults: sample/parameter.dat (dt_tree, gamma) and src/particle.h:927-928 (R_search2/3);
+    re_search mirrors `#define USE_RE_SEARCH_NEIGHBOR` (src/main_p3t.cpp:15)."""
+    p = np.zeros(1, dtype=CORR_PARAMS)
+    p["eps2"], p["dt_tree"], p["gamma"], p["R_search2"], p["R_search3"] = eps2, dt_tree, gamma, R_search2, R_search3
+    p["re_search"], p["initial"] = int(re_search), int(initial)
+    return p

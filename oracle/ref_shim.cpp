@@ -252,6 +252,86 @@ void ref_tree_copy(void *epi, int *epi_off, int *ni, int *adr_epj, long long *ep
     if (force) std::memcpy(force, g_rec.force.data(), g_rec.force.size() * sizeof(Force_t));
 }
 
+// ---- the changeover correction: the reference's own correctForceLong / correctForceLongInitial ----
+// Runs what src/main_p3t.cpp:582-593 (or :351-361 with initial != 0) runs on one rank: id_local /
+// myrank assignment (src/func.h:135-147), the tree force through the multi-walk-index interface
+// (so the interaction lists of exactly this tree are recorded for ref_tree_copy), then
+// correctForceLong (src/gravity_soft.h:245-372) or correctForceLongInitial (:375-528) with the
+// reference's NeighborList.  Per particle (original order) out_f64[i*16 ..] =
+// {acc xyz, phi, acc0, acc_d xyz, phi_d, jerk_d xyz, acc_before xyz (F32 tree force widened)},
+// out_i64[i*4 ..] = {id_cluster, neighbor.number, inDomain, offset into ngb}; ngb holds
+// {id, rank, id_local} triples (3 x int64 per neighbour).  Returns the total neighbour count, or
+// -1 when ngb_cap is too small.
+long long ref_correct_long(int n, const double *pos, const double *vel, const double *acc_d, const double *mass,
+                           const double *r_out, const double *r_search, const long long *id,
+                           double theta, int n_leaf_limit, int n_group_limit, int n_walk_limit,
+                           double eps2, double dt_tree, double gamma, double R_search2, double R_search3,
+                           int initial, double *out_f64, long long *out_i64, long long *ngb, long long ngb_cap)
+{
+    if (!g_ps_initialized) {
+        int argc = 1;
+        char arg0[] = "ref_shim";
+        char *argv_[] = {arg0, nullptr};
+        char **argv = argv_;
+        PS::Initialize(argc, argv);
+        g_ps_initialized = true;
+    }
+    g_rec.clear();
+    FP_t::eps2 = eps2;
+    FP_t::dt_tree = dt_tree;
+    FP_t::R_search2 = R_search2;
+    FP_t::R_search3 = R_search3;
+    FP_t::setGamma(gamma);
+    PS::ParticleSystem<FP_t> psys;
+    psys.initialize();
+    psys.setNumberOfParticleLocal(n);
+    for (int i = 0; i < n; i++) {
+        psys[i].id = id ? id[i] : i;
+        psys[i].pos = PS::F64vec(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        psys[i].vel = PS::F64vec(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        psys[i].acc_d = PS::F64vec(acc_d[3 * i], acc_d[3 * i + 1], acc_d[3 * i + 2]);
+        psys[i].mass = mass[i];
+        psys[i].r_out = r_out[i];
+        psys[i].r_out_inv = 1. / r_out[i];          // src/particle.h:728
+        psys[i].r_search = r_search[i];
+    }
+    NeighborList NList;
+    setIDLocalAndMyrank(psys, NList);
+    PS::DomainInfo dinfo;
+    dinfo.initialize(0.3);
+    dinfo.setNumberOfDomainMultiDimension(1, 1, 1);
+    dinfo.setBoundaryCondition(PS::BOUNDARY_CONDITION_OPEN);
+    dinfo.collectSampleParticle(psys, true);
+    dinfo.decomposeDomain();
+    Tree_t tree;
+    tree.initialize(n, theta, n_leaf_limit, n_group_limit);
+    tree.calcForceAllAndWriteBackMultiWalkIndex(RecDispatch, RecRetrieve, 1, psys, dinfo, n_walk_limit, true);
+    std::vector<PS::F64vec> before(n);
+    for (int i = 0; i < n; i++) before[i] = psys[i].acc;
+    PS::S32 n_ngb_tot = 0, n_with_ngb = 0;
+    if (initial) correctForceLongInitial(psys, tree, NList, n_ngb_tot, n_with_ngb);
+    else correctForceLong(psys, tree, NList, n_ngb_tot, n_with_ngb);
+    long long off = 0;
+    for (int i = 0; i < n; i++) {
+        double *o = out_f64 + 16 * (size_t)i;
+        o[0] = psys[i].acc.x; o[1] = psys[i].acc.y; o[2] = psys[i].acc.z; o[3] = psys[i].phi; o[4] = psys[i].acc0;
+        o[5] = psys[i].acc_d.x; o[6] = psys[i].acc_d.y; o[7] = psys[i].acc_d.z; o[8] = psys[i].phi_d;
+        o[9] = psys[i].jerk_d.x; o[10] = psys[i].jerk_d.y; o[11] = psys[i].jerk_d.z;
+        o[12] = before[i].x; o[13] = before[i].y; o[14] = before[i].z; o[15] = 0.0;
+        long long *q = out_i64 + 4 * (size_t)i;
+        q[0] = psys[i].id_cluster; q[1] = psys[i].neighbor.number; q[2] = psys[i].inDomain ? 1 : 0; q[3] = off;
+        const std::vector<NeighborId> &l = NList.n_list[i];
+        if ((long long)l.size() != psys[i].neighbor.number) return -2;
+        for (size_t k = 0; k < l.size(); k++) {
+            if (off >= ngb_cap) return -1;
+            ngb[3 * off] = l[k].id; ngb[3 * off + 1] = l[k].rank; ngb[3 * off + 2] = l[k].id_local;
+            off++;
+        }
+    }
+    if (off != n_ngb_tot) return -3;
+    return off;
+}
+
 // The reference program, unmodified (src/main_p3t.cpp:83).  Runs in the current directory.
 int ref_main(int argc, char **argv) { return gplum_reference_main(argc, argv); }
 

@@ -9,6 +9,10 @@ i.e. gravity_kernel.hpp's non-PIKG branch incl. its `tr = xx+yy+xx`):
                      from the reference's FDPS tree (theta=0.5, n_leaf_limit=8, n_group_limit=64,
                      sample/parameter.dat), force = reference functors on every walk.
   disk2k_g256.npz    2000-particle annulus, n_group_limit=256 (GPU-sized groups).
+  corr_long.npz      changeover correction: a crowded 1500-particle annulus (most particles have
+                     > 2 candidates), lists + tree force from the reference's tree, and the results
+                     of the reference's correctForceLong AND correctForceLongInitial
+                     (src/gravity_soft.h:245-528) per particle in original order + neighbour lists.
   groups.npz         single functor calls incl. edge cases (ni=1, nj=0, multi-rank, eps2>0,
                      pre-loaded force for accumulate semantics).
 """
@@ -41,6 +45,29 @@ def walks_fixture(path, pos, vel, mass, n_group_limit, eps2=0.0):
           "with candidates", int((f_ref["number"] > 0).sum()), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
+def corr_fixture(path, n=1500, seed=2):
+    d = disk.make_disk(n, a_in=0.995, a_out=1.005, seed=seed)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    ro, rs = ro * 5.0, rs * 6.0
+    rng = np.random.default_rng(seed + 100)
+    acc_d = rng.normal(size=(n, 3)) * 1e-3
+    ids = rng.permutation(n).astype(np.int64) * 3 + 11
+    z = {}
+    for initial in (0, 1):
+        prm = S.corr_params(initial=bool(initial))
+        w, f_tree, ref, lists = O.ref_correct_long(d["pos"], d["vel"], acc_d, d["mass"], ro, rs, ids, prm, n_group_limit=32)
+        tag = "init_" if initial else "long_"
+        for k, v in ref.items():
+            z[tag + k] = v
+        z[tag + "ngb"] = np.concatenate(lists) if len(lists) else np.zeros((0, 3), np.int64)
+        z[tag + "prm"] = prm
+    for k in ("epi", "epi_off", "ni", "adr_epj", "epj_disp", "n_epj", "adr_spj", "spj_disp", "n_spj", "epj_all", "spj_all"):
+        z[k] = getattr(w, k)
+    np.savez_compressed(path, force_ref=f_tree, **z)
+    print(path, "walks", w.n_walk, "neighbours", int(ref["number"].sum()), "with >2 candidates",
+          int((f_tree["number"] > 2).sum()), "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
 def main():
     assert O.have_ref("scalar"), "build oracle/_ref first: make -C oracle ref"
     d = np.loadtxt(REF_SAMPLE, skiprows=1)
@@ -48,6 +75,8 @@ def main():
     walks_fixture(os.path.join(HERE, "init3000_g64.npz"), d[:, 4:7].copy(), d[:, 7:10].copy(), d[:, 1].copy(), 64)
     dk = disk.make_disk(2000, a_in=0.98, a_out=1.02, seed=7)
     walks_fixture(os.path.join(HERE, "disk2k_g256.npz"), dk["pos"], dk["vel"], dk["mass"], 256)
+
+    corr_fixture(os.path.join(HERE, "corr_long.npz"))
 
     cases = {}
     specs = [(1, 1, 1, 0, 0.0, 1), (24, 157, 166, 1, 0.0, 1), (64, 301, 200, 2, 0.0, 2),

@@ -144,3 +144,64 @@ def ref_tree_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_grou
                       _ptr(adr_spj), _ptr(spj_disp), _ptr(n_spj), _ptr(epj_all), _ptr(spj_all), _ptr(force))
     w = Walks(epi, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, epj_all, spj_all)
     return (w, force) if with_force else w
+
+
+# ------------------------------------------------------------------ changeover correction
+def correct_long(w, prm, force=None):
+    """oracle/soft_corr_oracle.c on the walks `w`: (corr[n_epi], init[n_epi] or None, ngb[n])."""
+    lib = oracle()
+    lib.oracle_correct_long.restype = C.c_longlong
+    lib.oracle_correct_long.argtypes = [_i] + [_vp] * 12 + [C.c_longlong]
+    n = len(w.epi)
+    out = np.zeros(n, dtype=S.CORR)
+    init = np.zeros(n, dtype=S.CORR_INIT) if int(prm["initial"][0]) else None
+    cap = max(1024, 64 * n)
+    ngb = np.zeros(cap, dtype=S.NGB)
+    r = lib.oracle_correct_long(w.n_walk, _ptr(w.epi), _ptr(w.epi_off), _ptr(w.ni), _ptr(w.adr_epj),
+                                _ptr(w.epj_disp), _ptr(w.n_epj), _ptr(w.epj_all),
+                                None if force is None else _ptr(force), _ptr(prm), _ptr(out),
+                                None if init is None else _ptr(init), _ptr(ngb), cap)
+    assert r >= 0, "oracle_correct_long failed: %d" % r
+    return out, init, ngb[:r]
+
+
+def ref_correct_long(pos, vel, acc_d, mass, r_out, r_search, ids, prm, theta=0.5, n_leaf_limit=8,
+                     n_group_limit=64, n_walk_limit=200, kind="scalar"):
+    """The reference's own tree force + correctForceLong{,Initial} on one rank (oracle/ref_shim.cpp).
+    Returns (walks recorded from that tree, tree force in walk order, dict of per-particle results
+    in ORIGINAL order, list of neighbour arrays)."""
+    lib = ref(kind)
+    lib.ref_correct_long.restype = C.c_longlong
+    lib.ref_correct_long.argtypes = [_i] + [_vp] * 7 + [C.c_double, _i, _i, _i] + [C.c_double] * 5 + [_i, _vp, _vp, _vp, C.c_longlong]
+    n = len(pos)
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pos, vel, acc_d, mass, r_out, r_search = map(f64, (pos, vel, acc_d, mass, r_out, r_search))
+    ids = np.ascontiguousarray(ids, dtype=np.int64)
+    of = np.zeros((n, 16)); oi = np.zeros((n, 4), dtype=np.int64)
+    cap = max(1024, 64 * n)
+    ngb = np.zeros((cap, 3), dtype=np.int64)
+    p = prm[0]
+    r = lib.ref_correct_long(n, _ptr(pos), _ptr(vel), _ptr(acc_d), _ptr(mass), _ptr(r_out), _ptr(r_search),
+                             _ptr(ids), theta, n_leaf_limit, n_group_limit, n_walk_limit, float(p["eps2"]),
+                             float(p["dt_tree"]), float(p["gamma"]), float(p["R_search2"]), float(p["R_search3"]),
+                             int(p["initial"]), _ptr(of), _ptr(oi), _ptr(ngb), cap)
+    assert r >= 0, "ref_correct_long failed: %d" % r
+    sz = np.zeros(8, dtype=np.int64)
+    lib.ref_tree_sizes(_ptr(sz))
+    nw = int(sz[0])
+    epi = np.zeros(sz[1], dtype=S.EPI)
+    epi_off = np.zeros(nw, dtype=np.int32); ni = np.zeros(nw, dtype=np.int32)
+    adr_epj = np.zeros(sz[2], dtype=np.int32); epj_disp = np.zeros(nw, dtype=np.int64)
+    n_epj = np.zeros(nw, dtype=np.int32)
+    adr_spj = np.zeros(sz[3], dtype=np.int32); spj_disp = np.zeros(nw, dtype=np.int64)
+    n_spj = np.zeros(nw, dtype=np.int32)
+    epj_all = np.zeros(sz[4], dtype=S.EPJ); spj_all = np.zeros(sz[5], dtype=S.SPJ_QUAD)
+    force = np.zeros(sz[1], dtype=S.FORCE)
+    lib.ref_tree_copy(_ptr(epi), _ptr(epi_off), _ptr(ni), _ptr(adr_epj), _ptr(epj_disp), _ptr(n_epj),
+                      _ptr(adr_spj), _ptr(spj_disp), _ptr(n_spj), _ptr(epj_all), _ptr(spj_all), _ptr(force))
+    w = Walks(epi, epi_off, ni, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, epj_all, spj_all)
+    res = {"acc": of[:, 0:3], "phi": of[:, 3], "acc0": of[:, 4], "acc_d": of[:, 5:8], "phi_d": of[:, 8],
+           "jerk_d": of[:, 9:12], "acc_before": of[:, 12:15], "id_cluster": oi[:, 0], "number": oi[:, 1],
+           "in_domain": oi[:, 2]}
+    lists = [ngb[oi[i, 3]:oi[i, 3] + oi[i, 1]] for i in range(n)]
+    return w, force, res, lists
