@@ -47,6 +47,10 @@ SYMBOLS = {
     "gplum_b200_tree_copy": (_i, [_vp] * 11 + [_i, _i, _vp]),
     "gplum_b200_tree_free": (None, []),
     "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
+    "gplum_b200_soft_corr_enable": (_i, [_i, _ll]),
+    "gplum_b200_correct_long_run": (_i, [_i, _vp, _i]),
+    "gplum_b200_correct_long_download": (_i, [_i, _vp, _vp, _vp, _ll, C.POINTER(_ll), C.POINTER(_ll)]),
+    "gplum_b200_correct_long_time": (_i, [_i, _vp, _i, _i, C.POINTER(_f)]),
 }
 
 _lib = None

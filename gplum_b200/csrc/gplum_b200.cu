@@ -18,6 +18,7 @@
 
 #include "../../include/gplum_b200.h"
 #include "kernels.cuh"
+#include "soft_corr.h"
 
 namespace {
 
@@ -85,10 +86,15 @@ struct WalkSet {
     std::vector<long long> epi_off_host;
     bool pending = false;
     cudaEvent_t done = nullptr;                  // recorded after the D2H of a dispatch: retrieve(tag) waits on it only
+    // changeover correction (soft_corr.cu): candidate capture of the last pass + work/result buffers
+    DevBuf self_adr, pairs, corr_meta, cnt, off, cursor, csr, corr_out, corr_init, ngb, scan_temp;
+    unsigned int pair_cap = 0;
+    bool captured = false, corrected = false, corrected_initial = false;
     void release()
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
-        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force})
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force,
+                          &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp})
             b->release();
         h_force.release(); h_stage.release();
     }
@@ -134,6 +140,8 @@ struct Ctx {
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
+    bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
+    long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
 };
 Ctx g;
 
@@ -211,6 +219,23 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
     p.items = (const WorkItem *)ws.items.p;
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
+    p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
+    ws.captured = false; ws.corrected = false;
+    if (g.corr_on) {
+        const long long cap = g.corr_cap > 0 ? g.corr_cap : 4 * ws.n_epi + (1 << 20);
+        if (cap > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "pair capacity %lld exceeds 2^31", cap);
+        if (int r = ws.self_adr.reserve((size_t)ws.n_epi * 4)) return r;
+        if (int r = ws.pairs.reserve((size_t)cap * sizeof(int2))) return r;
+        if (int r = ws.corr_meta.reserve(16)) return r;
+        ws.pair_cap = (unsigned int)cap;
+        CU(cudaMemsetAsync(ws.self_adr.p, 0xff, (size_t)ws.n_epi * 4, st));
+        CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
+        p.self_adr = (int *)ws.self_adr.p;
+        p.pairs = (int2 *)ws.pairs.p;
+        p.pair_count = (unsigned int *)ws.corr_meta.p;
+        p.pair_cap = ws.pair_cap;
+        ws.captured = true;
+    }
     if (g.rmax <= 2) force_pass_kernel<2><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
     else force_pass_kernel<4><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
     CU(cudaGetLastError());
@@ -387,6 +412,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.items = (const WorkItem *)(dm + sizeof(Meta));
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
+    p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
     if (g.rmax <= 2) force_pass_kernel<2><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else force_pass_kernel<4><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     CU(cudaGetLastError());
@@ -820,6 +846,111 @@ int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev
                                                           (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2);
     CU(cudaGetLastError());
     g.launches++;
+    return 0;
+}
+
+// ---- changeover correction (soft_corr.cu) ----
+int gplum_b200_soft_corr_enable(int on, long long pair_cap)
+{
+    if (pair_cap < 0) return fail(GPLUM_B200_ERR_ARG, "pair_cap < 0");
+    g.corr_on = on != 0;
+    g.corr_cap = pair_cap;
+    return 0;
+}
+
+int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int initial)
+{
+    if (int r = ensure_init()) return r;
+    if (slot < 0 || slot >= N_TAG || !prm) return fail(GPLUM_B200_ERR_ARG, "correct_long_run(slot=%d)", slot);
+    WalkSet &ws = g.slots[slot];
+    if (!ws.captured) return fail(GPLUM_B200_ERR_STATE, "no captured pass in slot %d: call soft_corr_enable(1, cap) before the pass", slot);
+    if (g.jset.ext_epj || g.peer.on || !g.jset.epj_aos.p)
+        return fail(GPLUM_B200_ERR_STATE, "the correction needs the raw EPJGrav array of the pass on this device");
+    CU(cudaSetDevice(g.device));
+    const int n = (int)ws.n_epi;
+    if (n == 0) { ws.corrected = true; return 0; }
+    if (int r = ws.cnt.reserve((size_t)(n + 1) * 4)) return r;
+    if (int r = ws.off.reserve((size_t)(n + 1) * 4)) return r;
+    if (int r = ws.cursor.reserve((size_t)(n + 1) * 4)) return r;
+    if (int r = ws.csr.reserve((size_t)ws.pair_cap * 4)) return r;
+    if (int r = ws.corr_out.reserve((size_t)n * sizeof(SoftCorr))) return r;
+    if (initial) if (int r = ws.corr_init.reserve((size_t)n * sizeof(SoftCorrInit))) return r;
+    if (int r = ws.ngb.reserve((size_t)ws.pair_cap * sizeof(SoftNgb))) return r;
+    const size_t tb = soft_corr_scan_temp_bytes(n);
+    if (int r = ws.scan_temp.reserve(tb)) return r;
+    SoftCorrArgs a;
+    a.n_epi = n; a.epi = ws.epi.p; a.force = ws.force.p; a.epj_aos = g.jset.epj_aos.p;
+    a.self_adr = (const int *)ws.self_adr.p;
+    a.pairs = (const int2 *)ws.pairs.p; a.pair_count = (const unsigned int *)ws.corr_meta.p; a.pair_cap = ws.pair_cap;
+    a.cnt = (int *)ws.cnt.p; a.off = (int *)ws.off.p; a.cursor = (int *)ws.cursor.p; a.csr = (int *)ws.csr.p;
+    a.out = (SoftCorr *)ws.corr_out.p; a.init_out = initial ? (SoftCorrInit *)ws.corr_init.p : nullptr;
+    a.ngb = (SoftNgb *)ws.ngb.p;
+    a.status = (unsigned int *)ws.corr_meta.p + 1;
+    a.prm.eps2 = prm->eps2; a.prm.dt_tree = prm->dt_tree; a.prm.gamma = prm->gamma;
+    a.prm.R_search2 = prm->R_search2; a.prm.R_search3 = prm->R_search3;
+    a.prm.re_search = prm->re_search; a.prm.initial = initial ? 1 : 0;
+    CU(cudaMemsetAsync((unsigned int *)ws.corr_meta.p + 1, 0, 12, g.stream));
+    int launched = 0;
+    const int e = soft_corr_launch(a, ws.scan_temp.p, ws.scan_temp.cap, g.stream, &launched);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "soft_corr_launch -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches += launched;
+    ws.corrected = true; ws.corrected_initial = initial != 0;
+    return 0;
+}
+
+int gplum_b200_correct_long_download(int slot, void *corr_out, void *init_out, void *ngb_out,
+                                     long long ngb_cap, long long *n_ngb_slots, long long *n_pairs)
+{
+    if (int r = ensure_init()) return r;
+    if (slot < 0 || slot >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "slot %d out of range", slot);
+    WalkSet &ws = g.slots[slot];
+    if (!ws.corrected) return fail(GPLUM_B200_ERR_STATE, "correct_long_download before correct_long_run");
+    if (init_out && !ws.corrected_initial) return fail(GPLUM_B200_ERR_STATE, "init_out requested but the run was not `initial`");
+    CU(cudaSetDevice(g.device));
+    const int n = (int)ws.n_epi;
+    if (n_ngb_slots) *n_ngb_slots = 0;
+    if (n_pairs) *n_pairs = 0;
+    if (n == 0) return 0;
+    unsigned int meta[4] = {0, 0, 0, 0};
+    int total = 0;
+    CU(cudaMemcpyAsync(meta, ws.corr_meta.p, 16, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaMemcpyAsync(&total, (const int *)ws.off.p + n, 4, cudaMemcpyDeviceToHost, g.stream));
+    if (corr_out) CU(cudaMemcpyAsync(corr_out, ws.corr_out.p, (size_t)n * sizeof(SoftCorr), cudaMemcpyDeviceToHost, g.stream));
+    if (init_out) CU(cudaMemcpyAsync(init_out, ws.corr_init.p, (size_t)n * sizeof(SoftCorrInit), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    if (n_pairs) *n_pairs = meta[0];
+    if (meta[1] > 0)
+        return fail(GPLUM_B200_ERR_OVERFLOW, "%u candidate pairs dropped: pair buffer holds %u, pass produced %u", meta[1], ws.pair_cap, meta[0]);
+    if (meta[2] > 0)
+        return fail(GPLUM_B200_ERR_STATE, "%u i-particles are not in their own EP list (not an FDPS interaction list)", meta[2]);
+    if ((long long)total != (long long)meta[0])
+        return fail(GPLUM_B200_ERR_STATE, "candidate counts (%d) and captured pairs (%u) disagree", total, meta[0]);
+    if (n_ngb_slots) *n_ngb_slots = total;
+    if (ngb_out && total > 0) {
+        if (total > ngb_cap) return fail(GPLUM_B200_ERR_ARG, "ngb_out holds %lld entries, %d needed", ngb_cap, total);
+        CU(cudaMemcpy(ngb_out, ws.ngb.p, (size_t)total * sizeof(SoftNgb), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int gplum_b200_correct_long_time(int slot, const gplum_b200_corr_params *prm, int initial, int iters, float *ms_out)
+{
+    if (int r = ensure_init()) return r;
+    if (iters <= 0) return fail(GPLUM_B200_ERR_ARG, "iters <= 0");
+    CU(cudaSetDevice(g.device));
+    if (int r = gplum_b200_correct_long_run(slot, prm, initial)) return r;     // sizes the buffers
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaStreamSynchronize(g.stream));
+    CU(cudaEventRecord(e0, g.stream));
+    for (int i = 0; i < iters; i++)
+        if (int r = gplum_b200_correct_long_run(slot, prm, initial)) return r;
+    CU(cudaEventRecord(e1, g.stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms / iters;
     return 0;
 }
 

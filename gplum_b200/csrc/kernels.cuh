@@ -71,6 +71,12 @@ struct PassParams {
     const WorkItem *items;
     float eps2;
     int rank_squared;
+    // candidate capture for the changeover correction (soft_corr.cu; src/gravity_soft.h:245-372): every
+    // (i, j) that passes the exact candidate test is appended to `pairs` (i = index into epi/force,
+    // j = EP index as listed), and the j that IS i (same id_local and rank) is noted in self_adr[i].
+    // All three are nullptr unless capture is enabled.
+    int *self_adr;
+    int2 *pairs; unsigned int *pair_count; unsigned int pair_cap;
 };
 
 __device__ __forceinline__ float rsqrt_approx(float x)
@@ -198,7 +204,7 @@ struct WarpSmem {
     float4 raw[JW * 4];        // cp.async landing zone: 64 B per j (EP records use 48)
     float4 j4[JW];             // dx,dy,dz,m
     union {
-        struct { float rout2[JW]; float rs2[JW]; int id[JW]; int rank[JW]; } ep;
+        struct { float rout2[JW]; float rs2[JW]; int id[JW]; int rank[JW]; int adr[JW]; } ep;
         struct { float4 q0[JW]; float4 q1[JW]; } sp;   // Qxx,Qyy,Qzz,Qxy | Qyz,Qzx,mtr,-
     };
     float i_rs2[IW];
@@ -259,7 +265,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         const float4 *src = &s.raw[sl * 4];
         if (idx < 0) {                        // padding: massless, far away, never a candidate
             s.j4[sl] = make_float4(1.0e10f, 1.0e10f, 1.0e10f, 0.0f);
-            if (t < nt_ep) { s.ep.rout2[sl] = 0.0f; s.ep.rs2[sl] = 0.0f; s.ep.id[sl] = -1; s.ep.rank[sl] = 0; }
+            if (t < nt_ep) { s.ep.rout2[sl] = 0.0f; s.ep.rs2[sl] = 0.0f; s.ep.id[sl] = -1; s.ep.rank[sl] = 0; s.ep.adr[sl] = -1; }
             else { s.sp.q0[sl] = make_float4(0.f, 0.f, 0.f, 0.f); s.sp.q1[sl] = make_float4(0.f, 0.f, 0.f, 0.f); }
             return 0.0f;
         }
@@ -271,6 +277,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         if (t < nt_ep) {
             s.ep.rout2[sl] = bq.w; s.ep.rs2[sl] = c.x;
             s.ep.id[sl] = __float_as_int(c.y); s.ep.rank[sl] = __float_as_int(c.z);
+            s.ep.adr[sl] = idx;
             return c.x;
         }
         const float4 d = src[3];
@@ -381,12 +388,19 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
                             if (rs2i[r] >= 0.0f && r2e < rs2) {
                                 const int idj = s.ep.id[j], rkj = s.ep.rank[j];
                                 const int idi = s.i_id[il], rki = s.i_rank[il];
+                                const int gi = ibase + ((G == 1) ? il : lane % W);
                                 if (idi != idj || rki != rkj) {     // only this lane touches entry il
                                     const int dr = rki - rkj;
                                     s.nb_number[il] += 1;
                                     s.nb_rank[il] += p.rank_squared ? dr * dr : abs(dr);
                                     s.nb_idmax[il] = max(s.nb_idmax[il], idj);
                                     s.nb_idmin[il] = min(s.nb_idmin[il], idj);
+                                    if (p.pairs) {
+                                        const unsigned int k = atomicAdd(p.pair_count, 1u);
+                                        if (k < p.pair_cap) p.pairs[k] = make_int2(gi, s.ep.adr[j]);
+                                    }
+                                } else if (p.self_adr) {
+                                    p.self_adr[gi] = s.ep.adr[j];
                                 }
                             }
                         }

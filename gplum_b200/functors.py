@@ -6,6 +6,8 @@
   dispatch / retrieve : FDPS multi-walk-index accelerator functors
       (FDPS/src/tree_for_force_impl_force.hpp:78-83,232-242).
   calc_walks : one whole calcForce pass over flat arrays (impl_force.hpp:1404-1564).
+  correctForceLong : the changeover correction + final neighbour lists on the walks of the last
+      pass (src/gravity_soft.h:245-372; `initial=True` = correctForceLongInitial, :375-528).
 
 Arrays are numpy structured arrays with the reference layouts (gplum_b200.structs).
 """
@@ -131,3 +133,47 @@ def counters(reset=False):
     a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
     lib().gplum_b200_counters(C.byref(a), C.byref(b), C.byref(c), int(reset))
     return a.value, b.value, c.value
+
+
+# ------------------------------------------------------------------ changeover correction
+def soft_corr_enable(on=True, pair_cap=0):
+    """Make the following force passes record their neighbour-candidate pairs."""
+    check(lib().gplum_b200_soft_corr_enable(int(bool(on)), int(pair_cap)))
+
+
+def correct_long_run(prm, initial=False, slot=0):
+    assert prm.dtype == S.CORR_PARAMS
+    check(lib().gplum_b200_correct_long_run(int(slot), _p(prm), int(bool(initial))))
+
+
+def correct_long_download(n_epi, initial=False, slot=0, ngb_cap=None):
+    """(corr[n_epi], init[n_epi] or None, ngb) -- particle k's neighbours are
+    ngb[corr[k].ngb_off : corr[k].ngb_off + corr[k].number]."""
+    corr = np.zeros(n_epi, dtype=S.CORR)
+    init = np.zeros(n_epi, dtype=S.CORR_INIT) if initial else None
+    cap = int(ngb_cap) if ngb_cap is not None else 4 * n_epi + (1 << 20)
+    ngb = np.zeros(cap, dtype=S.NGB)
+    n_slots, n_pairs = C.c_longlong(0), C.c_longlong(0)
+    check(lib().gplum_b200_correct_long_download(int(slot), _p(corr), None if init is None else _p(init), _p(ngb),
+                                                 cap, C.byref(n_slots), C.byref(n_pairs)))
+    return corr, init, ngb[:n_slots.value]
+
+
+def correctForceLong(w, prm, initial=False):
+    """Tree force + changeover correction of the walks `w` through host buffers: returns
+    (force, corr, init, ngb).  The reference: calcForceAllAndWriteBack followed by
+    correctForceLong{,Initial} (src/main_p3t.cpp:583-593, 351-361)."""
+    soft_corr_enable(True)
+    try:
+        f = calc_walks(w)
+        correct_long_run(prm, initial)
+        corr, init, ngb = correct_long_download(len(w.epi), initial)
+    finally:
+        soft_corr_enable(False)
+    return f, corr, init, ngb
+
+
+def correct_long_time(prm, iters, initial=False, slot=0):
+    ms = C.c_float(0)
+    check(lib().gplum_b200_correct_long_time(int(slot), _p(prm), int(bool(initial)), int(iters), C.byref(ms)))
+    return ms.value

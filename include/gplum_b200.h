@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GPLUM_B200_ABI_VERSION 1
+#define GPLUM_B200_ABI_VERSION 2
 
 /* mode flags (gplum_b200_set_params) */
 #define GPLUM_B200_TRACE_AS_SHIPPED 1 /* tr = qxx+qyy+qxx, the non-PIKG branch's arithmetic
@@ -138,6 +138,40 @@ int gplum_b200_peer_open(const void *all_handles);
 int gplum_b200_peer_pack(const void *epj_aos_dev, int n);
 int gplum_b200_peer_close(void);
 int gplum_b200_peer_free(void);
+
+/* ---- changeover correction + final neighbour lists (next row of the path: SURVEY 8f-2) ----
+ * Replaces correctForceLong / correctForceLongInitial (src/gravity_soft.h:245-372,375-528), i.e.
+ * correctForceBetween2Particles{,Initial} (:76-153,155-242) with cutoff_W/K/dKdt (src/cutfunc.h),
+ * for the i-particles of a resident walk set.  The reference re-searches the tree for every
+ * particle with candidates (getNeighborListOneParticle, :295-297); here the force pass records
+ * the candidate pairs itself while it runs, so the correction is three small kernels after it.
+ *   1. gplum_b200_soft_corr_enable(1, cap) BEFORE the pass is launched (cap = pair-buffer capacity,
+ *      0 = 4 x n_epi + 2^20); capture costs nothing in the pair loop, only the rare path writes.
+ *   2. run the pass (walks_run / calc_walks / dispatch).
+ *   3. gplum_b200_correct_long_run(slot, prm, initial) launches the correction on the library
+ *      stream; gplum_b200_correct_long_download copies the results to host buffers.
+ * Results are per i-particle in the walk-concatenated order of epi/force:
+ *   gplum_b200_corr.acc/phi are the FP64 sums `acci`, `phii` the reference ADDS to the widened tree
+ *   force (:366-367); acc0, number, id_cluster, in_domain as src/gravity_soft.h:368 and
+ *   NeighborList::addNeighbor (src/neighbor.h:635-664); the particle's neighbours are
+ *   ngb[ngb_off .. ngb_off+number) = NeighborId{id, rank, id_local} (src/neighbor.h:205-245), in
+ *   ascending EP-index order; id_local is the pp index FDPS's write-back targets.
+ * Needs the raw EPJGrav array of the pass on the device (every form that takes epj_all keeps it). */
+typedef struct { double eps2, dt_tree, gamma, R_search2, R_search3; int re_search, reserved; } gplum_b200_corr_params;
+typedef struct { double acc[3]; double phi; double acc0; long long id_cluster;
+                 int number, id_local, ngb_off, in_domain; } gplum_b200_corr;              /* 64 B */
+typedef struct { double acc_d[3]; double jerk_d[3]; double phi_d; double pad; } gplum_b200_corr_init; /* 64 B */
+typedef struct { long long id; int rank, id_local; } gplum_b200_ngb;                      /* 16 B */
+#define GPLUM_B200_ERR_OVERFLOW 5  /* pair buffer too small: enlarge (soft_corr_enable) and redo the pass */
+int gplum_b200_soft_corr_enable(int on, long long pair_cap);
+int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int initial);
+/* n_ngb_slots: entries of ngb to copy = ngb_off + number of the last particle with candidates (the
+ * list is segmented by candidate counts); n_ngb_total: neighbours actually present.  init_out may be
+ * NULL.  ngb_cap = capacity of ngb_out in entries. */
+int gplum_b200_correct_long_download(int slot, void *corr_out, void *init_out, void *ngb_out,
+                                     long long ngb_cap, long long *n_ngb_slots, long long *n_pairs);
+/* mean milliseconds of `iters` correction launches (CUDA events on the library stream) */
+int gplum_b200_correct_long_time(int slot, const gplum_b200_corr_params *prm, int initial, int iters, float *ms);
 
 /* Use an existing CUDA stream (cudaStream_t as void*) for the batched / device-resident
  * forms, so that a caller's events on that stream bracket the kernels.  NULL = own stream. */
