@@ -48,7 +48,12 @@ def make_workload(n, group, seed=0, a_in=0.9, a_out=1.1):
     # fields the force kernels never read but the changeover correction does (EPJGrav::vel, id)
     w.epj_all["vel"] = d["vel"][order]
     w.epj_all["id"] = order
-    return w, time.time() - t0
+    t_build = time.time() - t0
+    w.raw = {"pos": d["pos"], "mass": d["mass"], "r_out": r_out, "r_search": r_search}     # the particles themselves
+    t0 = time.time()
+    tree.build_walks(d["pos"], d["mass"], r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=group)
+    w.t_host_lists = time.time() - t0            # host builder alone (all host threads), lists copied out
+    return w, t_build
 
 
 class ClockSampler(threading.Thread):
@@ -145,6 +150,73 @@ def pinned_like(a):
     b = t.numpy().view(a.dtype).reshape(a.shape)
     b[...] = a
     return b, t
+
+
+def soft_step_leg(args, w, F, S, L, check):
+    """Next rows of the path (SURVEY 8f-1 + 8f-2): one whole soft-force evaluation without host-side
+    lists.  Per step, inside the timed region: raw particles (pinned host SoA, 48 B each) -> device,
+    tree + i-groups + interaction lists built on the GPU (dev_tree.cu), force pass with candidate
+    capture, changeover correction, forces + corrections + neighbour lists back to pinned host memory.
+    The reference: setParticleLocalTree .. calcForceAllAndWriteBack + correctForceLong
+    (src/main_p3t.cpp:583-593)."""
+    import ctypes as C
+    import torch
+    from gplum_b200 import tree
+    n = args.n
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    raw = {k: pin(np.ascontiguousarray(v, dtype=np.float64)) for k, v in w.raw.items()}
+    p_force = pin(np.zeros(n, dtype=S.FORCE))
+    p_corr = pin(np.zeros(n, dtype=S.CORR))
+    ngb_cap = 4 * n + (1 << 20)
+    p_ngb = pin(np.zeros(ngb_cap, dtype=S.NGB))
+    prm = S.corr_params()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_slots, n_pairs = C.c_longlong(0), C.c_longlong(0)
+    sizes = [None]
+
+    def one():
+        sizes[0] = tree.build_walks_gpu(raw["pos"], raw["mass"], raw["r_out"], raw["r_search"], theta=0.5,
+                                        n_leaf_limit=8, n_group_limit=args.group)
+        F.walks_run(repack=False)
+        F.correct_long_run(prm)
+        check(L.gplum_b200_walks_download(vp(p_force)))
+        check(L.gplum_b200_correct_long_download(0, vp(p_corr), None, vp(p_ngb), ngb_cap, C.byref(n_slots), C.byref(n_pairs)))
+
+    F.soft_corr_enable(True)
+    try:
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize()
+        reps = max(3, args.steps // 2)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        phases = tree.gpu_build_times()
+        # the list build alone (device time of its kernels; two host syncs inside)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            tree.build_walks_gpu(raw["pos"], raw["mass"], raw["r_out"], raw["r_search"], theta=0.5, n_leaf_limit=8,
+                                 n_group_limit=args.group)
+        torch.cuda.synchronize()
+        dt_build = (time.perf_counter() - t0) / reps
+        k_ms = F.walks_time(max(3, args.steps), repack=False)
+    finally:
+        F.soft_corr_enable(False)
+    sz = sizes[0]
+    n_int = int(sz[6] + sz[7])
+    assert (int(sz[6]), int(sz[7])) == w.n_interactions(), "GPU-built lists differ from the host builder's"
+    return {"ms_per_step": dt * 1e3, "interactions_per_s": n_int / dt,
+            "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int((32 + 64) * n + 16 * n_slots.value),
+            "list_build_ms_wall": dt_build * 1e3, "list_build_gpu_phases_ms": {k: round(v, 4) for k, v in phases.items()},
+            "list_build_ms_host_builder": w.t_host_lists * 1e3,
+            "force_pass_ms_on_gpu_lists": k_ms, "n_walks": int(sz[0]), "n_cells": int(sz[5]),
+            "neighbour_pairs": int(n_pairs.value),
+            "api": "gplum_b200_tree_build_gpu + walks_run + correct_long_run + walks_download + correct_long_download, "
+                   "pinned host buffers"}
 
 
 def main():
@@ -278,6 +350,10 @@ def main():
         soft_corr = {"force_pass_with_capture_ms": k_cap_ms, "correction_ms": c_ms,
                      "candidate_pairs": int(len(ngb)), "neighbours": int(corr["number"].sum()),
                      "particles_with_neighbours": int((corr["number"] > 0).sum())}
+    soft_step = None
+    if world == 1:
+        soft_step = soft_step_leg(args, w, F, S, L, check)
+        F.walks_upload(w)                        # back to the host-built set for the legs below
     peak_tf, _ = F.fp32_peak(10)
     my_ee, my_es = (ee, es) if world == 1 else sh.local.n_interactions()
     flop = FLOP_EPEP * my_ee + FLOP_EPSP * my_es
@@ -367,6 +443,8 @@ def main():
            "list_build_s_host": t_build}
     if soft_corr is not None:
         out["soft_corr"] = soft_corr
+    if soft_step is not None:
+        out["soft_step"] = soft_step
     if world > 1:
         out["phases_rank0"] = phases
         out["phases_all"] = all_phases

@@ -1,0 +1,798 @@
+// dev_tree.cu -- interaction-list construction on the GPU: what FDPS does between
+// setParticleLocalTree and calcForce, single rank, open boundary, SEARCH_MODE_LONG_SYMMETRY.
+//
+//   Morton keys + sort      FDPS/src/tree_for_force_impl.hpp:280-330 (setParticleLocalTree, mortonSortLocalTreeOnly)
+//   cells (n_leaf_limit)    FDPS/src/tree_for_force_utils.hpp:289 (LinkCell)
+//   moments, in/out boxes   FDPS/src/tree_for_force_utils_moment.hpp:6,189; tree.hpp:576-641,1186-1205
+//   i-groups (n_group_limit) tree_for_force_utils.hpp:619-650 (MakeIPGroup)
+//   per-group walk          FDPS/src/tree_walk.hpp:545-583,706-785 (symmetric search: a cell is opened if the
+//                           group's inner box overlaps its outer box, or the group's outer box overlaps its
+//                           inner box, or dist^2(group inner box, cell com) <= (size/theta)^2)
+//
+// Same semantics, same cell numbering and bit-identical FP64 results as the host builder
+// (let_tree.cpp): this file is compiled with -fmad=false and every FP64 expression keeps the
+// host's evaluation order, so the lists the two produce are equal as sets and the SPJ records are
+// equal bit for bit (tests/test_tree_gpu.py).  Within a list the order differs (the host walks
+// depth-first with a scalar stack, a warp here expands four cells = 32 children per step).
+//
+// Layout in HBM: cells are SoA-of-records -- int4 {first, n, child, level}, moments as
+// MySPJQuadrupole-shaped 80 B records {mass, com[3], quad[6]} (so the SPJ array of the force pass is
+// a plain copy), boxes as 12 doubles {in.lo, in.hi, out.lo, out.hi}.  Children of a cell are 8
+// consecutive records; cells of one level are contiguous (breadth-first numbering), which is what
+// makes the level-by-level build and the bottom-up moment sweep coalesced.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <stdint.h>
+
+#include <algorithm>
+#include <utility>
+
+#include "dev_tree.h"
+#include "items.h"
+#include "records.h"
+
+namespace gbt {
+
+using gb::EpiAos;
+using gb::EpjAos;
+using gb::SpjMonoAos;
+using gb::SpjQuadAos;
+using gb::WorkItem;
+
+namespace {
+
+constexpr int MAX_LEVEL = 21;
+constexpr int N_LVL = MAX_LEVEL + 2;       // lvl_start[l] .. lvl_start[l+1] = cells of level l, l = 0..21
+constexpr int NB = 592;                    // blocks of the level kernels (4 per SM), <= 1024 (split_scan_kernel)
+constexpr int TPB = 256;
+constexpr int WALK_WPB = 8;                // warps per block of the walk kernels
+constexpr int STK = 1024;                  // per-warp stack of open cells (depth-first in steps of 4: <= ~28 x levels)
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// device-side scalars of a build
+struct Meta {
+    double org[3], inv, len;               // root cube: origin corner, 2^21 / len, edge length
+    int lvl_start[N_LVL + 1];
+    int fcount[N_LVL];                     // cells of level l that split
+    int overflow;
+    int n_walk;
+    int cap, n_items;
+    long long n_adr_epj, n_adr_spj, n_int_epep, n_int_epsp;
+};
+
+struct State {
+    Buf keys_a, keys_b, idx_a, idx_b, cub_temp;
+    Buf bbox_part, meta, blk_cnt, blk_off;
+    Buf c_meta, c_mom, c_box, fr_a, fr_b, grp_at, walk_cell;
+    Buf w_epi_off, w_ni, w_ne, w_ns, w_ed, w_sd, w_nitems, w_ioff;
+    Buf item_key_a, item_key_b, item_a;
+    Meta *h_meta = nullptr;                // pinned
+    int cell_cap = 0, n = 0, n_walk = 0, n_cells = 0, n_levels = 0, lvl_start[N_LVL + 1] = {};
+    cudaEvent_t ev[7] = {};
+    bool ev_ok = false, timed = false;
+} S;
+
+#define CK(call)                                  \
+    do {                                          \
+        cudaError_t e_ = (call);                  \
+        if (e_ != cudaSuccess) return (int)e_;    \
+    } while (0)
+
+struct KP {                                // pointers every tree kernel sees
+    int n, n_leaf, n_group, cell_cap;
+    double theta;
+    const EpjAos *epj;                     // sorted
+    const uint64_t *key;                   // sorted
+    int4 *c_meta; double *c_mom; double *c_box;
+    int *grp_at;
+    Meta *meta;
+};
+
+__device__ __forceinline__ uint64_t spread3(uint64_t x)
+{
+    x &= 0x1fffff;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+// ---- root cube: bbox of pos +- 1.1*r_search (FDPS/src/tree_for_force_impl.hpp:846-866) ----
+__global__ void __launch_bounds__(TPB) bbox_kernel(const EpjAos *__restrict__ p, int n, double *__restrict__ part)
+{
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+        const double r = 1.1 * p[i].r_search * 1.000001;
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fmin(lo[k], p[i].pos[k] - r);
+            hi[k] = fmax(hi[k], p[i].pos[k] + r);
+        }
+    }
+    __shared__ double sm[TPB / 32][6];
+    for (int k = 0; k < 3; k++)
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], d));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], d));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 3; k++) { sm[threadIdx.x >> 5][k] = lo[k]; sm[threadIdx.x >> 5][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[0][threadIdx.x];
+        for (int w = 1; w < TPB / 32; w++) v = threadIdx.x < 3 ? fmin(v, sm[w][threadIdx.x]) : fmax(v, sm[w][threadIdx.x]);
+        part[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void bbox_final_kernel(const double *__restrict__ part, int n_part, KP P)
+{
+    __shared__ double sm[6];
+    if (threadIdx.x < 6) {
+        double v = part[threadIdx.x];
+        for (int b = 1; b < n_part; b++) v = threadIdx.x < 3 ? fmin(v, part[b * 6 + threadIdx.x]) : fmax(v, part[b * 6 + threadIdx.x]);
+        sm[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *lo = sm, *hi = sm + 3;
+        double full = 0, cen[3];
+        for (int k = 0; k < 3; k++) { cen[k] = 0.5 * (lo[k] + hi[k]); full = fmax(full, hi[k] - lo[k]); }
+        // a dimension much thinner than the cube (a disk's z) is pushed wholly into one half
+        for (int k = 0; k < 3; k++) if (hi[k] - lo[k] < 0.1 * full) cen[k] -= (hi[k] - lo[k]) * 0.51;
+        double half = 0.5 * full * 1.000001;
+        if (half <= 0) half = 1.0;
+        const double len = 2.0 * half;
+        Meta *m = P.meta;
+        for (int k = 0; k < 3; k++) m->org[k] = cen[k] - half;
+        m->len = len;
+        m->inv = (double)(1u << MAX_LEVEL) / len;
+        // the root cell and the level table
+        for (int l = 0; l <= N_LVL; l++) m->lvl_start[l] = l == 0 ? 0 : 1;
+        for (int l = 0; l < N_LVL; l++) m->fcount[l] = 0;
+        const bool root_splits = P.n > P.n_leaf;
+        m->fcount[0] = root_splits ? 1 : 0;
+        m->overflow = 0;
+        P.c_meta[0] = make_int4(0, P.n, -1, 0);
+        if (P.n <= P.n_group || !root_splits) P.grp_at[0] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) key_kernel(const EpjAos *__restrict__ p, int n, const Meta *__restrict__ m,
+                                                  uint64_t *__restrict__ key, int *__restrict__ idx)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c[3];
+    for (int k = 0; k < 3; k++) {
+        double f = (p[i].pos[k] - m->org[k]) * m->inv;
+        f = fmin(fmax(f, 0.0), (double)((1u << MAX_LEVEL) - 1));
+        c[k] = (uint64_t)f;
+    }
+    key[i] = spread3(c[0]) << 2 | spread3(c[1]) << 1 | spread3(c[2]);
+    idx[i] = i;
+}
+
+// sorted EPJ (112 B records moved as 7 x 16 B) and the EPI of the same particle
+__global__ void __launch_bounds__(TPB) gather_kernel(const uint4 *__restrict__ in, const int *__restrict__ idx, int n,
+                                                     uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
+{
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    const int i = t >> 3, q = t & 7;              // 8 lanes per record, 7 of them move 16 B
+    if (i >= n) return;
+    const int src = idx[i];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q < 7) {
+        v = __ldg(in + (size_t)src * 7 + q);
+        epj[(size_t)i * 7 + q] = v;
+    }
+    // EPIGrav = the first 48 B of EPJGrav (src/particle.h:93-109,149-156)
+    if (q < 3) reinterpret_cast<uint4 *>(epi)[(size_t)i * 3 + q] = v;
+}
+
+__global__ void __launch_bounds__(TPB) soa_to_epj_kernel(int n, const double *__restrict__ pos, const double *__restrict__ mass,
+                                                         const double *__restrict__ r_out, const double *__restrict__ r_search,
+                                                         int rank, EpjAos *__restrict__ out)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    EpjAos j;
+    j.id_local = i; j.myrank = rank; j.id = i;
+    for (int k = 0; k < 3; k++) { j.pos[k] = pos[3 * (size_t)i + k]; j.vel[k] = 0.0; j.acc_d[k] = 0.0; }
+    j.r_out = r_out[i]; j.r_search = r_search[i]; j.mass = mass[i];
+    out[i] = j;
+}
+
+// ---- cells, one level per launch triple ----
+// The frontier of level L = its cells that split (n > n_leaf), in breadth-first order; the children of
+// frontier entry f are the 8 cells lvl_start[L+1] + 8 f + o.  8 lanes work on one cell: lane o finds
+// the end of octant o by binary search on the key digit of that level.
+__device__ __forceinline__ void child_range(const KP &P, const int *__restrict__ fr, int f, int f1, int o, int L,
+                                            int &cell, int &pn, int &lb, int &ub)
+{
+    int first = 0, n = 0;
+    cell = -1;
+    if (f < f1) { cell = fr[f]; const int4 m = P.c_meta[cell]; first = m.x; n = m.y; }
+    pn = n;
+    const int end = first + n;
+    ub = end;
+    if (o < 7 && n > 0) {
+        const int shift = 3 * (MAX_LEVEL - 1 - L);
+        int lo = first, hi = end;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)((P.key[mid] >> shift) & 7) <= o) lo = mid + 1; else hi = mid;
+        }
+        ub = lo;
+    }
+    lb = __shfl_up_sync(FULL, ub, 1, 8);
+    if (o == 0) lb = first;
+}
+
+__device__ __forceinline__ void chunk_of(int F, int &f0, int &f1)
+{
+    const int chunk = ((F + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
+    f0 = min(F, (int)blockIdx.x * chunk);
+    f1 = min(F, f0 + chunk);
+}
+
+__global__ void __launch_bounds__(TPB) split_count_kernel(KP P, const int *__restrict__ fr, int L, int *__restrict__ blk_cnt)
+{
+    const int F = P.meta->fcount[L];
+    int f0, f1;
+    chunk_of(F, f0, f1);
+    int cnt = 0;
+    for (int base = f0; base < f1; base += TPB / 8) {
+        int cell, pn, lb, ub;
+        child_range(P, fr, base + (threadIdx.x >> 3), f1, threadIdx.x & 7, L, cell, pn, lb, ub);
+        cnt += (ub - lb > P.n_leaf && L + 1 < MAX_LEVEL) ? 1 : 0;
+    }
+    __shared__ int sm[TPB / 32];
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < TPB / 32; w++) s += sm[w];
+        blk_cnt[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024) split_scan_kernel(KP P, int L, int nb, const int *__restrict__ blk_cnt, int *__restrict__ blk_off)
+{
+    __shared__ int wsum[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int v = t < nb ? blk_cnt[t] : 0;
+    int inc = v;
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = wsum[lane];
+        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, s, d); if (lane >= d) s += u; }
+        wsum[lane] = s;                            // inclusive over warps
+    }
+    __syncthreads();
+    const int woff = w > 0 ? wsum[w - 1] : 0;
+    if (t < nb) blk_off[t] = woff + inc - v;
+    if (t == 0) {
+        Meta *m = P.meta;
+        int total = wsum[31];                      // cells of level L+1 that split
+        const int F = m->fcount[L];
+        const int next_start = m->lvl_start[L + 1] + 8 * F;      // first cell of level L+2
+        // this level's children were checked one level up; make sure the next level's children fit
+        if ((long long)next_start + 8LL * total > (long long)P.cell_cap) { m->overflow = 1; total = 0; }
+        for (int l = L + 2; l <= N_LVL; l++) m->lvl_start[l] = next_start;
+        m->fcount[L + 1] = total;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) split_write_kernel(KP P, const int *__restrict__ fr, int *__restrict__ fr_next, int L,
+                                                          const int *__restrict__ blk_off)
+{
+    const int F = P.meta->fcount[L];
+    if (F == 0) return;
+    const int cbase = P.meta->lvl_start[L + 1];
+    int f0, f1;
+    chunk_of(F, f0, f1);
+    __shared__ int wcnt[TPB / 32];
+    int running = blk_off[blockIdx.x];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, o = threadIdx.x & 7;
+    for (int base = f0; base < f1; base += TPB / 8) {
+        const int f = base + (threadIdx.x >> 3);
+        int cell, pn, lb, ub;
+        child_range(P, fr, f, f1, o, L, cell, pn, lb, ub);
+        const int cn = ub - lb;
+        const bool will = cell >= 0 && cn > P.n_leaf && L + 1 < MAX_LEVEL;
+        const unsigned bal = __ballot_sync(FULL, will);
+        if (lane == 0) wcnt[w] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int k = 0; k < TPB / 32; k++) { const int c = wcnt[k]; if (k < w) before += c; total += c; }
+        __syncthreads();
+        if (cell >= 0) {
+            const int cidx = cbase + 8 * f + o;
+            P.c_meta[cidx] = make_int4(lb, cn, -1, L + 1);
+            if (o == 0) reinterpret_cast<int *>(&P.c_meta[cell])[2] = cbase + 8 * f;
+            // i-groups: the shallowest cells with <= n_group particles (or leaves)
+            if (pn > P.n_group && cn > 0 && (cn <= P.n_group || !will)) P.grp_at[lb] = cidx;
+            if (will) fr_next[running + before + __popc(bal & ((1u << lane) - 1))] = cidx;
+        }
+        running += total;
+    }
+}
+
+// ---- moments and boxes, bottom-up, one level per launch (children are complete before parents) ----
+__global__ void __launch_bounds__(TPB) moment_kernel(KP P, int c0, int c1)
+{
+    const int c = c0 + blockIdx.x * TPB + threadIdx.x;
+    if (c >= c1) return;
+    const int4 m = P.c_meta[c];
+    double mass = 0, com[3] = {0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0};
+    double ilo[3] = {1e300, 1e300, 1e300}, ihi[3] = {-1e300, -1e300, -1e300};
+    double olo[3] = {1e300, 1e300, 1e300}, ohi[3] = {-1e300, -1e300, -1e300};
+    if (m.y > 0) {
+        if (m.z < 0) {
+            for (int i = m.x; i < m.x + m.y; i++) {
+                const EpjAos &p = P.epj[i];
+                const double mi = p.mass, rs = 1.1 * p.r_search;
+                mass += mi;
+                for (int k = 0; k < 3; k++) {
+                    const double x = p.pos[k];
+                    com[k] += mi * x;
+                    ilo[k] = fmin(ilo[k], x - 0.0); ihi[k] = fmax(ihi[k], x + 0.0);
+                    olo[k] = fmin(olo[k], x - rs); ohi[k] = fmax(ohi[k], x + rs);
+                }
+            }
+            for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
+            for (int i = m.x; i < m.x + m.y; i++) {
+                const EpjAos &p = P.epj[i];
+                const double mi = p.mass;
+                const double d0 = p.pos[0] - com[0], d1 = p.pos[1] - com[1], d2 = p.pos[2] - com[2];
+                q[0] += mi * d0 * d0; q[1] += mi * d1 * d1; q[2] += mi * d2 * d2;
+                q[3] += mi * d0 * d1; q[4] += mi * d0 * d2; q[5] += mi * d1 * d2;
+            }
+        } else {
+            for (int o = 0; o < 8; o++) {
+                const int ch = m.z + o;
+                if (P.c_meta[ch].y == 0) continue;
+                const double *cm = P.c_mom + (size_t)ch * 10, *cb = P.c_box + (size_t)ch * 12;
+                const double cmass = cm[0];
+                mass += cmass;
+                for (int k = 0; k < 3; k++) {
+                    com[k] += cmass * cm[1 + k];
+                    ilo[k] = fmin(ilo[k], cb[k]); ihi[k] = fmax(ihi[k], cb[3 + k]);
+                    olo[k] = fmin(olo[k], cb[6 + k]); ohi[k] = fmax(ohi[k], cb[9 + k]);
+                }
+            }
+            for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
+            for (int o = 0; o < 8; o++) {
+                const int ch = m.z + o;
+                if (P.c_meta[ch].y == 0) continue;
+                const double *cm = P.c_mom + (size_t)ch * 10;
+                const double mi = cm[0];
+                const double d0 = cm[1] - com[0], d1 = cm[2] - com[1], d2 = cm[3] - com[2];
+                q[0] += mi * d0 * d0 + cm[4]; q[1] += mi * d1 * d1 + cm[5]; q[2] += mi * d2 * d2 + cm[6];
+                q[3] += mi * d0 * d1 + cm[7]; q[4] += mi * d0 * d2 + cm[8]; q[5] += mi * d1 * d2 + cm[9];
+            }
+        }
+    }
+    double *om = P.c_mom + (size_t)c * 10, *ob = P.c_box + (size_t)c * 12;
+    om[0] = mass;
+    for (int k = 0; k < 3; k++) { om[1 + k] = com[k]; ob[k] = ilo[k]; ob[3 + k] = ihi[k]; ob[6 + k] = olo[k]; ob[9 + k] = ohi[k]; }
+    for (int k = 0; k < 6; k++) om[4 + k] = q[k];
+}
+
+// ---- per-group walk: one warp per group, depth-first in steps of 4 cells x 8 children ----
+struct WalkP {
+    KP P;
+    const int *walk_cell; int n_walk;
+    int *epi_off, *ni, *n_epj, *n_spj;                     // per walk
+    const long long *epj_disp, *spj_disp;                  // FILL
+    int *adr_epj, *adr_spj;                                // FILL
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(WALK_WPB * 32) walk_kernel(WalkP A)
+{
+    __shared__ int stk_all[WALK_WPB][STK];
+    const KP &P = A.P;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int *stk = stk_all[wib];
+    const double inv_theta2 = 1.0 / (P.theta * P.theta);
+    const double len = P.meta->len;
+    const unsigned lt = (1u << lane) - 1;
+    for (int g = blockIdx.x * WALK_WPB + wib; g < A.n_walk; g += gridDim.x * WALK_WPB) {
+        const int gc = A.walk_cell[g];
+        const int4 gm = P.c_meta[gc];
+        // group boxes: lanes 0..11 load one double each, everybody gets all 12
+        double bv = lane < 12 ? P.c_box[(size_t)gc * 12 + lane] : 0.0;
+        double gb[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) gb[k] = __shfl_sync(FULL, bv, k);
+        long long ed = 0, sd = 0;
+        if (FILL) { ed = A.epj_disp[g]; sd = A.spj_disp[g]; }
+        int ne = 0, ns = 0, top = 0;
+        const int4 root = P.c_meta[0];
+        if (root.z < 0) {                                   // the root is a leaf: every particle
+            if (FILL) for (int k = lane; k < root.y; k += 32) A.adr_epj[ed + k] = root.x + k;
+            ne = root.y;
+        } else {
+            if (lane == 0) stk[0] = 0;
+            top = 1;
+        }
+        __syncwarp();
+        while (top > 0) {
+            const int take = min(top, 4);
+            top -= take;
+            const int sub = lane >> 3, o = lane & 7;
+            int ci = -1;
+            int4 cm = make_int4(0, 0, -1, 0);
+            if (sub < take) { ci = P.c_meta[stk[top + sub]].z + o; cm = P.c_meta[ci]; }
+            __syncwarp();                                   // stack entries read before they are overwritten
+            const bool valid = cm.y > 0;
+            bool open = false;
+            if (valid) {
+                const double *mo = P.c_mom + (size_t)ci * 10;
+                const double cx[3] = {mo[1], mo[2], mo[3]};
+                const double size = ldexp(len, -cm.w);
+                double d2 = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double d = fmax(0.0, fmax(gb[k] - cx[k], cx[k] - gb[3 + k])); d2 += d * d; }
+                open = d2 <= size * size * inv_theta2;
+                if (!open) {
+                    const double *cb = P.c_box + (size_t)ci * 12;
+                    bool a = true, b = true;              // a: group.in overlaps cell.out; b: group.out overlaps cell.in
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const double cilo = cb[k], cihi = cb[3 + k], colo = cb[6 + k], cohi = cb[9 + k];
+                        if (gb[3 + k] < colo || cohi < gb[k]) a = false;
+                        if (gb[9 + k] < cilo || cihi < gb[6 + k]) b = false;
+                    }
+                    open = a || b;
+                }
+            }
+            const bool leaf = cm.z < 0;
+            const bool is_sp = valid && !open, is_push = valid && open && !leaf, is_ep = valid && open && leaf;
+            const unsigned m_sp = __ballot_sync(FULL, is_sp), m_push = __ballot_sync(FULL, is_push);
+            if (FILL && is_sp) A.adr_spj[sd + ns + __popc(m_sp & lt)] = ci;
+            ns += __popc(m_sp);
+            const int n_push = __popc(m_push);
+            if (top + n_push > STK) {                       // cannot happen for sane trees; flagged, never silent
+                if (lane == 0) P.meta->overflow = 2;
+                top = 0;
+                break;
+            }
+            if (is_push) stk[top + __popc(m_push & lt)] = ci;
+            top += n_push;
+            const int cnt = is_ep ? cm.y : 0;
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
+            if (FILL && is_ep) {
+                int *dst = A.adr_epj + ed + ne + (inc - cnt);
+                for (int k = 0; k < cnt; k++) dst[k] = cm.x + k;
+            }
+            ne += __shfl_sync(FULL, inc, 31);
+            __syncwarp();
+        }
+        if (!FILL && lane == 0) {
+            A.epi_off[g] = gm.x; A.ni[g] = gm.y; A.n_epj[g] = ne; A.n_spj[g] = ns;
+        }
+    }
+}
+
+// ---- totals, tile capacity, per-walk item counts ----
+struct AsLL { __host__ __device__ long long operator()(const int &v) const { return (long long)v; } };
+struct NonNeg { __host__ __device__ bool operator()(const int &v) const { return v >= 0; } };
+
+__global__ void __launch_bounds__(1024) totals_kernel(int n_walk, const int *__restrict__ ni, const int *__restrict__ ne,
+                                                      const int *__restrict__ ns, Meta *m, long long warp_slots,
+                                                      int tile_cap, int jsplit, int rmax)
+{
+    long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // adr_epj, adr_spj, int_ee, int_es, items at cap 64..4
+    for (int w = threadIdx.x; w < n_walk; w += 1024) {
+        const long long i = ni[w], e = ne[w], s = ns[w];
+        v[0] += e; v[1] += s; v[2] += i * e; v[3] += i * s;
+        for (int k = 0; k < 5; k++) v[4 + k] += (i + (64 >> k) - 1) / (64 >> k);
+    }
+    __shared__ long long sm[32][9];
+    for (int k = 0; k < 9; k++)
+        for (int d = 16; d > 0; d >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], d);
+    if ((threadIdx.x & 31) == 0) for (int k = 0; k < 9; k++) sm[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t[9];
+        for (int k = 0; k < 9; k++) { t[k] = 0; for (int w = 0; w < 32; w++) t[k] += sm[w][k]; }
+        m->n_adr_epj = t[0]; m->n_adr_spj = t[1]; m->n_int_epep = t[2]; m->n_int_epsp = t[3];
+        m->cap = gb::tile_cap_choose(t + 4, warp_slots, tile_cap, jsplit != 0, rmax);
+        m->n_walk = n_walk;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) item_count_kernel(int n_walk, const int *__restrict__ ni, const Meta *__restrict__ m,
+                                                         int jsplit, int *__restrict__ n_items)
+{
+    const int w = blockIdx.x * TPB + threadIdx.x;
+    if (w >= n_walk) return;
+    const int cap = m->cap;
+    int rem = ni[w], cnt = 0;
+    while (rem > 0) { int n, shape; gb::tile_next(rem, cap, jsplit != 0, n, shape); rem -= n; cnt++; }
+    n_items[w] = cnt;
+}
+
+__global__ void item_total_kernel(int n_walk, const int *__restrict__ n_items, const int *__restrict__ ioff, Meta *m)
+{
+    m->n_items = n_walk > 0 ? ioff[n_walk - 1] + n_items[n_walk - 1] : 0;
+}
+
+__device__ __forceinline__ uint64_t cost_key(double c) { return (uint64_t)__double_as_longlong(c); }   // c > 0
+
+__global__ void __launch_bounds__(TPB) item_emit_kernel(int n_walk, const int *__restrict__ ni, const int *__restrict__ ne,
+                                                        const int *__restrict__ ns, const int *__restrict__ ioff,
+                                                        const Meta *__restrict__ m, int jsplit,
+                                                        WorkItem *__restrict__ items, uint64_t *__restrict__ keys)
+{
+    const int w = blockIdx.x * TPB + threadIdx.x;
+    if (w >= n_walk) return;
+    const int cap = m->cap;
+    int rem = ni[w], i0 = 0, k = ioff[w];
+    while (rem > 0) {
+        int n, shape;
+        gb::tile_next(rem, cap, jsplit != 0, n, shape);
+        items[k] = WorkItem{w, i0, n, gb::tile_cfg_of(shape)};
+        keys[k] = cost_key(gb::tile_cost(ne[w], ns[w], shape));
+        rem -= n; i0 += n; k++;
+    }
+}
+
+// ---- SPJ records of the force pass: the cells' moments ----
+__global__ void __launch_bounds__(TPB) spj_mono_kernel(int n_cells, const double *__restrict__ mom, SpjMonoAos *__restrict__ out)
+{
+    const int c = blockIdx.x * TPB + threadIdx.x;
+    if (c >= n_cells) return;
+    SpjMonoAos s;
+    s.mass = mom[(size_t)c * 10];
+    for (int k = 0; k < 3; k++) s.pos[k] = mom[(size_t)c * 10 + 1 + k];
+    out[c] = s;
+}
+
+inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
+
+}  // namespace
+
+const int *tree_sorted_to_original() { return (const int *)S.idx_b.p; }
+const int *tree_walk_ni() { return (const int *)S.w_ni.p; }
+
+void tree_phase_ms(float ms[6])
+{
+    for (int k = 0; k < 6; k++) {
+        ms[k] = 0.f;
+        if (S.timed) cudaEventElapsedTime(&ms[k], S.ev[k], S.ev[k + 1]);
+    }
+}
+
+void tree_release()
+{
+    for (Buf *b : {&S.keys_a, &S.keys_b, &S.idx_a, &S.idx_b, &S.cub_temp, &S.bbox_part, &S.meta, &S.blk_cnt, &S.blk_off,
+                   &S.c_meta, &S.c_mom, &S.c_box, &S.fr_a, &S.fr_b, &S.grp_at, &S.walk_cell, &S.w_epi_off, &S.w_ni, &S.w_ne,
+                   &S.w_ns, &S.w_ed, &S.w_sd, &S.w_nitems, &S.w_ioff, &S.item_key_a, &S.item_key_b, &S.item_a})
+        b->release();
+    if (S.h_meta) { cudaFreeHost(S.h_meta); S.h_meta = nullptr; }
+    if (S.ev_ok) { for (auto &e : S.ev) cudaEventDestroy(e); S.ev_ok = false; }
+    S.timed = false; S.cell_cap = 0; S.n = 0;
+}
+
+int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *r_out, const double *r_search,
+                    int rank, void *epj_out, cudaStream_t st, int *launches)
+{
+    if (n <= 0) return 0;
+    soa_to_epj_kernel<<<nblk(n, TPB), TPB, 0, st>>>(n, pos, mass, r_out, r_search, rank, (EpjAos *)epj_out);
+    CK(cudaGetLastError());
+    ++*launches;
+    return 0;
+}
+
+static KP make_kp(const TreeCfg &cfg, const void *epj_sorted)
+{
+    KP P;
+    P.n = cfg.n; P.n_leaf = cfg.n_leaf; P.n_group = cfg.n_group; P.cell_cap = S.cell_cap; P.theta = cfg.theta;
+    P.epj = (const EpjAos *)epj_sorted; P.key = (const uint64_t *)S.keys_b.p;
+    P.c_meta = (int4 *)S.c_meta.p; P.c_mom = (double *)S.c_mom.p; P.c_box = (double *)S.c_box.p;
+    P.grp_at = (int *)S.grp_at.p; P.meta = (Meta *)S.meta.p;
+    return P;
+}
+
+int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, void *epi, TreeCounts *counts,
+                cudaStream_t st, int *launches)
+{
+    const int n = cfg.n;
+    S.timed = false;
+    if (!S.ev_ok) { for (auto &e : S.ev) CK(cudaEventCreate(&e)); S.ev_ok = true; }
+    if (!S.h_meta) CK(cudaMallocHost((void **)&S.h_meta, sizeof(Meta)));
+    // the host builder's tree of the N = 1e6 disk has 0.74 n cells; a rejected capacity doubles and retries
+    if (S.n != n || S.cell_cap == 0) S.cell_cap = 2 * n + 4096;
+    S.n = n;
+    for (int attempt = 0;; attempt++) {
+        const size_t C = (size_t)S.cell_cap;
+        CK(S.keys_a.reserve((size_t)n * 8)); CK(S.keys_b.reserve((size_t)n * 8));
+        CK(S.idx_a.reserve((size_t)n * 4)); CK(S.idx_b.reserve((size_t)n * 4));
+        CK(S.bbox_part.reserve((size_t)NB * 6 * 8)); CK(S.meta.reserve(sizeof(Meta)));
+        CK(S.blk_cnt.reserve(NB * 4)); CK(S.blk_off.reserve(NB * 4));
+        CK(S.c_meta.reserve(C * sizeof(int4))); CK(S.c_mom.reserve(C * 80)); CK(S.c_box.reserve(C * 96));
+        CK(S.fr_a.reserve(C / 8 * 4 + 64)); CK(S.fr_b.reserve(C / 8 * 4 + 64));
+        CK(S.grp_at.reserve((size_t)n * 4)); CK(S.walk_cell.reserve((size_t)n * 4 + 16));
+        KP P = make_kp(cfg, epj_sorted);
+        const EpjAos *raw = (const EpjAos *)epj_unsorted;
+
+        CK(cudaEventRecord(S.ev[0], st));
+        CK(cudaMemsetAsync(S.grp_at.p, 0xff, (size_t)n * 4, st));
+        const int nbb = std::min(NB, nblk(n, TPB));
+        bbox_kernel<<<nbb, TPB, 0, st>>>(raw, n, (double *)S.bbox_part.p);
+        bbox_final_kernel<<<1, 32, 0, st>>>((const double *)S.bbox_part.p, nbb, P);
+        key_kernel<<<nblk(n, TPB), TPB, 0, st>>>(raw, n, P.meta, (uint64_t *)S.keys_a.p, (int *)S.idx_a.p);
+        CK(cudaGetLastError());
+        *launches += 3;
+        size_t tb = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t *)S.keys_a.p, (uint64_t *)S.keys_b.p,
+                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * MAX_LEVEL, st));
+        CK(S.cub_temp.reserve(tb));
+        CK(cub::DeviceRadixSort::SortPairs(S.cub_temp.p, tb, (const uint64_t *)S.keys_a.p, (uint64_t *)S.keys_b.p,
+                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * MAX_LEVEL, st));
+        gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)raw, (const int *)S.idx_b.p, n,
+                                                                   (uint4 *)epj_sorted, (EpiAos *)epi);
+        CK(cudaGetLastError());
+        *launches += 1;
+        CK(cudaEventRecord(S.ev[1], st));
+
+        // cells: frontier arrays ping-pong; level 0's frontier is the root
+        CK(cudaMemsetAsync(S.fr_a.p, 0, 4, st));
+        int *fr = (int *)S.fr_a.p, *fr_next = (int *)S.fr_b.p;
+        for (int L = 0; L < MAX_LEVEL; L++) {
+            split_count_kernel<<<NB, TPB, 0, st>>>(P, fr, L, (int *)S.blk_cnt.p);
+            split_scan_kernel<<<1, 1024, 0, st>>>(P, L, NB, (const int *)S.blk_cnt.p, (int *)S.blk_off.p);
+            split_write_kernel<<<NB, TPB, 0, st>>>(P, fr, fr_next, L, (const int *)S.blk_off.p);
+            std::swap(fr, fr_next);
+            *launches += 3;
+        }
+        CK(cudaGetLastError());
+        // i-groups in Morton order: grp_at[first particle] = cell, compacted
+        int *d_nwalk = &((Meta *)S.meta.p)->n_walk;
+        CK(cub::DeviceSelect::If(nullptr, tb, (const int *)S.grp_at.p, (int *)S.walk_cell.p, d_nwalk, n, NonNeg(), st));
+        CK(S.cub_temp.reserve(tb));
+        CK(cub::DeviceSelect::If(S.cub_temp.p, tb, (const int *)S.grp_at.p, (int *)S.walk_cell.p, d_nwalk, n, NonNeg(), st));
+        CK(cudaMemcpyAsync(S.h_meta, S.meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(S.ev[2], st));
+        CK(cudaStreamSynchronize(st));
+        if (S.h_meta->overflow) {
+            if (attempt >= 4) { counts->overflow = 1; return -1; }
+            S.cell_cap *= 2;
+            continue;
+        }
+        break;
+    }
+    KP P = make_kp(cfg, epj_sorted);
+    for (int l = 0; l <= N_LVL; l++) S.lvl_start[l] = S.h_meta->lvl_start[l];
+    S.n_cells = S.lvl_start[N_LVL];
+    S.n_walk = S.h_meta->n_walk;
+    S.n_levels = 0;
+    for (int l = 0; l < N_LVL; l++) if (S.lvl_start[l + 1] > S.lvl_start[l]) S.n_levels = l + 1;
+    for (int l = S.n_levels - 1; l >= 0; l--) {
+        const int c0 = S.lvl_start[l], c1 = S.lvl_start[l + 1];
+        moment_kernel<<<nblk(c1 - c0, TPB), TPB, 0, st>>>(P, c0, c1);
+        ++*launches;
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(S.ev[3], st));
+
+    const int nw = S.n_walk;
+    for (Buf *b : {&S.w_epi_off, &S.w_ni, &S.w_ne, &S.w_ns, &S.w_nitems, &S.w_ioff}) CK(b->reserve((size_t)nw * 4 + 16));
+    CK(S.w_ed.reserve((size_t)nw * 8 + 16)); CK(S.w_sd.reserve((size_t)nw * 8 + 16));
+    WalkP A;
+    A.P = P; A.walk_cell = (const int *)S.walk_cell.p; A.n_walk = nw;
+    A.epi_off = (int *)S.w_epi_off.p; A.ni = (int *)S.w_ni.p; A.n_epj = (int *)S.w_ne.p; A.n_spj = (int *)S.w_ns.p;
+    A.epj_disp = nullptr; A.spj_disp = nullptr; A.adr_epj = nullptr; A.adr_spj = nullptr;
+    if (nw > 0) {
+        walk_kernel<false><<<std::min(nblk(nw, WALK_WPB), 148 * 8), WALK_WPB * 32, 0, st>>>(A);
+        CK(cudaGetLastError());
+        ++*launches;
+        size_t tb = 0, tb2 = 0;
+        cub::TransformInputIterator<long long, AsLL, const int *> ne_ll((const int *)S.w_ne.p, AsLL()), ns_ll((const int *)S.w_ns.p, AsLL());
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ne_ll, (long long *)S.w_ed.p, nw, st));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, (const int *)S.w_nitems.p, (int *)S.w_ioff.p, nw, st));
+        CK(S.cub_temp.reserve(std::max(tb, tb2)));
+        CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb, ne_ll, (long long *)S.w_ed.p, nw, st));
+        CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb, ns_ll, (long long *)S.w_sd.p, nw, st));
+        totals_kernel<<<1, 1024, 0, st>>>(nw, (const int *)S.w_ni.p, (const int *)S.w_ne.p, (const int *)S.w_ns.p, P.meta,
+                                          cfg.warp_slots, cfg.tile_cap, cfg.jsplit, cfg.rmax);
+        item_count_kernel<<<nblk(nw, TPB), TPB, 0, st>>>(nw, (const int *)S.w_ni.p, P.meta, cfg.jsplit, (int *)S.w_nitems.p);
+        CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb2, (const int *)S.w_nitems.p, (int *)S.w_ioff.p, nw, st));
+        item_total_kernel<<<1, 1, 0, st>>>(nw, (const int *)S.w_nitems.p, (const int *)S.w_ioff.p, P.meta);
+        CK(cudaGetLastError());
+        *launches += 3;
+    }
+    CK(cudaMemcpyAsync(S.h_meta, S.meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(S.ev[4], st));
+    CK(cudaStreamSynchronize(st));
+    counts->n_cells = S.n_cells; counts->n_walk = nw; counts->n_levels = S.n_levels;
+    counts->overflow = S.h_meta->overflow;
+    counts->n_items = nw > 0 ? S.h_meta->n_items : 0; counts->cap = nw > 0 ? S.h_meta->cap : 0;
+    counts->n_adr_epj = nw > 0 ? S.h_meta->n_adr_epj : 0; counts->n_adr_spj = nw > 0 ? S.h_meta->n_adr_spj : 0;
+    counts->n_int_epep = nw > 0 ? S.h_meta->n_int_epep : 0; counts->n_int_epsp = nw > 0 ? S.h_meta->n_int_epsp : 0;
+    return counts->overflow ? -1 : 0;
+}
+
+int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *launches)
+{
+    const int nw = S.n_walk;
+    const cudaMemcpyKind D2D = cudaMemcpyDeviceToDevice;
+    if (nw > 0) {
+        WalkP A;
+        A.P = make_kp(cfg, nullptr); A.walk_cell = (const int *)S.walk_cell.p; A.n_walk = nw;
+        A.epi_off = nullptr; A.ni = nullptr; A.n_epj = nullptr; A.n_spj = nullptr;
+        A.epj_disp = (const long long *)S.w_ed.p; A.spj_disp = (const long long *)S.w_sd.p;
+        A.adr_epj = out.adr_epj; A.adr_spj = out.adr_spj;
+        walk_kernel<true><<<std::min(nblk(nw, WALK_WPB), 148 * 8), WALK_WPB * 32, 0, st>>>(A);
+        CK(cudaGetLastError());
+        ++*launches;
+    }
+    CK(cudaEventRecord(S.ev[5], st));
+    if (nw > 0) {
+        CK(cudaMemcpyAsync(out.epi_off, S.w_epi_off.p, (size_t)nw * 4, D2D, st));
+        if (out.ni) CK(cudaMemcpyAsync(out.ni, S.w_ni.p, (size_t)nw * 4, D2D, st));
+        CK(cudaMemcpyAsync(out.n_epj, S.w_ne.p, (size_t)nw * 4, D2D, st));
+        CK(cudaMemcpyAsync(out.n_spj, S.w_ns.p, (size_t)nw * 4, D2D, st));
+        CK(cudaMemcpyAsync(out.epj_disp, S.w_ed.p, (size_t)nw * 8, D2D, st));
+        CK(cudaMemcpyAsync(out.spj_disp, S.w_sd.p, (size_t)nw * 8, D2D, st));
+        // work items, longest first (stable: equal costs keep walk order, as the host list does)
+        const int nit = S.h_meta->n_items;
+        CK(S.item_key_a.reserve((size_t)nit * 8 + 16)); CK(S.item_key_b.reserve((size_t)nit * 8 + 16));
+        CK(S.item_a.reserve((size_t)nit * sizeof(WorkItem) + 16));
+        item_emit_kernel<<<nblk(nw, TPB), TPB, 0, st>>>(nw, (const int *)S.w_ni.p, (const int *)S.w_ne.p, (const int *)S.w_ns.p,
+                                                        (const int *)S.w_ioff.p, (const Meta *)S.meta.p, cfg.jsplit,
+                                                        (WorkItem *)S.item_a.p, (uint64_t *)S.item_key_a.p);
+        CK(cudaGetLastError());
+        ++*launches;
+        if (nit > 0) {
+            size_t tb = 0;
+            CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const uint64_t *)S.item_key_a.p, (uint64_t *)S.item_key_b.p,
+                                                         (const int4 *)S.item_a.p, (int4 *)out.items, nit, 0, 64, st));
+            CK(S.cub_temp.reserve(tb));
+            CK(cub::DeviceRadixSort::SortPairsDescending(S.cub_temp.p, tb, (const uint64_t *)S.item_key_a.p, (uint64_t *)S.item_key_b.p,
+                                                         (const int4 *)S.item_a.p, (int4 *)out.items, nit, 0, 64, st));
+        }
+    }
+    if (S.n_cells > 0) {
+        if (cfg.quad) CK(cudaMemcpyAsync(out.spj_aos, S.c_mom.p, (size_t)S.n_cells * 80, D2D, st));
+        else {
+            spj_mono_kernel<<<nblk(S.n_cells, TPB), TPB, 0, st>>>(S.n_cells, (const double *)S.c_mom.p, (SpjMonoAos *)out.spj_aos);
+            CK(cudaGetLastError());
+            ++*launches;
+        }
+    }
+    CK(cudaEventRecord(S.ev[6], st));
+    S.timed = true;
+    return 0;
+}
+
+}  // namespace gbt

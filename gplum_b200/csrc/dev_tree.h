@@ -1,0 +1,52 @@
+// dev_tree.h -- launch interface of dev_tree.cu: the interaction-list builder on the GPU
+// (SURVEY 8 f1).  Device pointers only; gplum_b200.cu owns the walk-set / j-set buffers and
+// reserves them between the two phases.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace gbt {
+
+struct TreeCfg {
+    int n;                       // particles
+    double theta;
+    int n_leaf, n_group;
+    int quad;                    // SPJ layout: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B)
+    // work-list policy (items.h)
+    long long warp_slots; int tile_cap, jsplit, rmax;
+};
+
+// totals of a build, valid on the host after phase1 returned
+struct TreeCounts {
+    int n_cells, n_walk, n_items, cap;
+    long long n_adr_epj, n_adr_spj, n_int_epep, n_int_epsp;
+    int n_levels, overflow;      // overflow: 1 = cell capacity, 2 = walk stack
+};
+
+struct TreeOut {                 // destination buffers of phase 2 (sizes from TreeCounts)
+    int *epi_off, *ni, *n_epj, *n_spj;           // n_walk (ni may be NULL)
+    long long *epj_disp, *spj_disp;              // n_walk
+    int *adr_epj, *adr_spj;                      // n_adr_epj, n_adr_spj
+    void *items;                                 // n_items x WorkItem (16 B)
+    void *spj_aos;                               // n_cells x (80 | 32) B
+};
+
+// Phase 1: Morton keys, radix sort, gather (writes epj_sorted = EPJGrav[n] and epi = EPIGrav[n] in tree
+// order), cells, moments, i-groups, counting walk, scans.  Synchronises the stream twice (cell / group
+// counts, list totals).  epj_unsorted: EPJGrav[n] on the device, any order.  Returns cudaError_t (0 = ok)
+// or -1 with counts->overflow set.
+int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, void *epi,
+                TreeCounts *counts, cudaStream_t st, int *launches);
+// Phase 2: filling walk, work items (sorted longest first), SPJ records.
+int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *launches);
+// EPJGrav[n] from SoA inputs (device pointers; pos is [n][3]): id_local = id = index, vel = acc_d = 0
+int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *r_out, const double *r_search,
+                    int rank, void *epj_out, cudaStream_t st, int *launches);
+const int *tree_sorted_to_original();            // device pointer, n entries, valid after phase 1
+const int *tree_walk_ni();                       // device pointer, n_walk entries: i-particles per walk
+// milliseconds between the phase marks of the last build: [0] keys+sort+gather, [1] cells+groups,
+// [2] moments, [3] counting walk + scans, [4] filling walk, [5] items + SPJ
+void tree_phase_ms(float ms[6]);
+void tree_release();
+
+}  // namespace gbt

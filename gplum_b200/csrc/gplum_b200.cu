@@ -18,7 +18,9 @@
 
 #include "../../include/gplum_b200.h"
 #include "kernels.cuh"
+#include "items.h"
 #include "soft_corr.h"
+#include "dev_tree.h"
 
 namespace {
 
@@ -142,6 +144,9 @@ struct Ctx {
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
     long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
+    DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
+    PinBuf tree_pin;            // pinned staging of pageable SoA inputs
+    bool tree_built = false;    // the selected slot + j-set hold a GPU-built tree
 };
 Ctx g;
 
@@ -152,51 +157,31 @@ int ensure_init()
     return gplum_b200_init(env ? atoi(env) : 0, 0, 0);
 }
 
-// ---- work list: split every walk into i-tiles, choose a tile shape, longest first ----
+// ---- work list: split every walk into i-tiles, choose a tile shape, longest first (items.h) ----
 void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items)
 {
     items.clear();
     std::vector<std::pair<double, WorkItem>> tmp;
     tmp.reserve((size_t)n_walk * 2);
-    // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
     const bool split = g.jsplit != 0;
-    // Tile capacity: 64 i-particles per warp is the most efficient shape (staging is amortised over
-    // the most pairs), and measured on 1/4- and 1/8-size shards it stays the fastest even at 0.6 waves.
-    // Only a pass that cannot give every fourth warp slot an item (per-call functor form, a small
-    // boundary set) is latency-bound on one item's serial chain: there use 32, or j-split tiles.
-    int cap = g.rmax >= 2 ? 64 : 32;
-    if (g.tile_cap > 0) cap = std::min(cap, g.tile_cap);
-    else if (split && g.rmax <= 2) {
-        const long long target = g.warp_slots / 4;
-        for (; cap > 4; cap >>= 1) {
-            long long n_it = 0;
-            for (int w = 0; w < n_walk; w++) n_it += (ni[w] + cap - 1) / cap;
-            if (n_it >= target) break;
-        }
-    }
-    auto cfg_of = [](int c) { return c == 64 ? 1 : c == 32 ? 0 : c == 16 ? 9 : c == 8 ? 10 : 11; };
+    long long n_items_at[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < n_walk; w++)
+        for (int k = 0; k < 5; k++) n_items_at[k] += (ni[w] + (64 >> k) - 1) / (64 >> k);
+    const int cap = tile_cap_choose(n_items_at, g.warp_slots, g.tile_cap, split, g.rmax);
     for (int w = 0; w < n_walk; w++) {
         int rem = ni[w], i0 = 0;
-        const double cost_j = 18.5 * n_epj[w] + 37.0 * n_spj[w];
-        const double cost_tiles = 90.0 * ((n_epj[w] + 63) / 64 + (n_spj[w] + 63) / 64) + 200.0;
-        auto push = [&](int n, int cfg, double cost) {
-            tmp.push_back({cost, WorkItem{w, i0, n, cfg}});
-            rem -= n; i0 += n;
-        };
-        auto push_shape = [&](int n, int c) { push(n, cfg_of(c), cost_j * c / 32.0 + cost_tiles); };
-        // Finer decompositions of a remainder (e.g. 20 -> 16 + 4) were measured slower at
-        // n_group_limit = 64: every extra item pays its own staging.
         while (rem > 0) {
             if (g.rmax >= 3 && rem > 64) {                   // RMAX = 4 build: up to 128 i-particles per warp
                 const int n = std::min(rem, 128);
                 const int cfg = (n + 31) / 32 - 1;
-                push(n, cfg, cost_j * (cfg + 1) + cost_tiles);
+                tmp.push_back({tile_cost(n_epj[w], n_spj[w], 32 * (cfg + 1)), WorkItem{w, i0, n, cfg}});
+                rem -= n; i0 += n;
                 continue;
             }
-            if (rem >= cap) { push_shape(cap, cap); continue; }
-            if (!split) { push_shape(rem, rem > 32 ? 64 : 32); continue; }
-            if (rem > 32 && rem <= 48) { push_shape(32, 32); continue; }     // 32 + a j-split tail beats a half-empty 64
-            push_shape(rem, rem > 32 ? 64 : rem > 16 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4);
+            int n, shape;
+            tile_next(rem, cap, split, n, shape);
+            tmp.push_back({tile_cost(n_epj[w], n_spj[w], shape), WorkItem{w, i0, n, tile_cfg_of(shape)}});
+            rem -= n; i0 += n;
         }
     }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
@@ -292,6 +277,7 @@ int upload_walks(WalkSet &ws, int n_walk, const void *epi_all, const int *epi_of
     }
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es;
+    g.tree_built = false;
     std::vector<WorkItem> items;
     build_items(n_walk, ni, n_epj, n_spj, items);
     ws.n_items = (int)items.size();
@@ -478,6 +464,9 @@ int gplum_b200_finalize(void)
     gplum_b200_peer_close();
     gplum_b200_peer_free();
     g.jset.release();
+    g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release();
+    gbt::tree_release();
+    g.tree_built = false;
     for (auto &s : g.slots) s.release();
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
     g.own_stream = g.stream = nullptr;
@@ -978,6 +967,148 @@ int gplum_b200_fp32_peak(int iters, float *tflops, float *ms_out)
     const double flop = 2.0 * 16.0 * inner * 256.0 * blocks * iters;
     if (tflops) *tflops = (float)(flop / (ms * 1e-3) / 1e12);
     if (ms_out) *ms_out = ms / iters;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- interaction lists built on the GPU (dev_tree.cu) ----
+namespace {
+int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_leaf_limit, int n_group_limit, long long *sizes)
+{
+    if (g.rmax > 2) return fail(GPLUM_B200_ERR_STATE, "the GPU list builder needs the RMAX <= 2 kernel");
+    cudaStream_t st = g.stream;
+    WalkSet &ws = g.slots[g.cur];
+    JSet &j = g.jset;
+    g.tree_built = false;
+    if (int r = ws.epi.reserve((size_t)n * sizeof(EpiAos))) return r;
+    if (int r = ws.force.reserve((size_t)n * sizeof(ForceAos))) return r;
+    if (int r = j.epj_aos.reserve((size_t)n * sizeof(EpjAos))) return r;
+    if (int r = j.epj_packed.reserve((size_t)n * sizeof(EpjPacked))) return r;
+    gbt::TreeCfg cfg;
+    cfg.n = n; cfg.theta = theta; cfg.n_leaf = n_leaf_limit; cfg.n_group = n_group_limit; cfg.quad = g.quad;
+    cfg.warp_slots = g.warp_slots; cfg.tile_cap = g.tile_cap; cfg.jsplit = g.jsplit; cfg.rmax = g.rmax;
+    gbt::TreeCounts c;
+    memset(&c, 0, sizeof(c));
+    int launches = 0;
+    int e = gbt::tree_phase1(cfg, epj_unsorted_dev, j.epj_aos.p, ws.epi.p, &c, st, &launches);
+    g.launches += launches;
+    if (e > 0) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 1: %s", cudaGetErrorString((cudaError_t)e));
+    if (e < 0) return fail(GPLUM_B200_ERR_OVERFLOW, "GPU list builder: %s overflow", c.overflow == 1 ? "cell capacity" : "walk stack");
+    const size_t ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
+    const size_t nw = (size_t)c.n_walk;
+    if (int r = ws.epi_off.reserve(nw * 4)) return r;
+    if (int r = ws.n_epj.reserve(nw * 4)) return r;
+    if (int r = ws.n_spj.reserve(nw * 4)) return r;
+    if (int r = ws.epj_disp.reserve(nw * 8)) return r;
+    if (int r = ws.spj_disp.reserve(nw * 8)) return r;
+    if (int r = ws.adr_epj.reserve((size_t)c.n_adr_epj * 4)) return r;
+    if (int r = ws.adr_spj.reserve((size_t)c.n_adr_spj * 4)) return r;
+    if (int r = ws.items.reserve((size_t)c.n_items * sizeof(WorkItem))) return r;
+    if (int r = j.spj_aos.reserve((size_t)c.n_cells * ssz)) return r;
+    if (int r = j.spj_packed.reserve((size_t)c.n_cells * sizeof(SpjPacked))) return r;
+    gbt::TreeOut o;
+    o.epi_off = (int *)ws.epi_off.p; o.ni = nullptr; o.n_epj = (int *)ws.n_epj.p; o.n_spj = (int *)ws.n_spj.p;
+    o.epj_disp = (long long *)ws.epj_disp.p; o.spj_disp = (long long *)ws.spj_disp.p;
+    o.adr_epj = (int *)ws.adr_epj.p; o.adr_spj = (int *)ws.adr_spj.p;
+    o.items = ws.items.p; o.spj_aos = j.spj_aos.p;
+    launches = 0;
+    e = gbt::tree_phase2(cfg, o, st, &launches);
+    g.launches += launches;
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 2: %s", cudaGetErrorString((cudaError_t)e));
+    ws.n_walk = c.n_walk; ws.n_items = c.n_items; ws.n_epi = n;
+    ws.n_adr_epj = c.n_adr_epj; ws.n_adr_spj = c.n_adr_spj;
+    ws.n_int_epep = c.n_int_epep; ws.n_int_epsp = c.n_int_epsp;
+    ws.ni_host.clear(); ws.epi_off_host.clear();
+    ws.pending = false; ws.captured = false; ws.corrected = false;
+    j.ext_epj = j.ext_spj = nullptr;
+    j.n_epj = n; j.n_spj = c.n_cells;
+    if (int r = pack_j(st, g.eps2)) return r;
+    g.tree_built = true;
+    if (sizes) {
+        sizes[0] = c.n_walk; sizes[1] = n; sizes[2] = c.n_adr_epj; sizes[3] = c.n_adr_spj; sizes[4] = n;
+        sizes[5] = c.n_cells; sizes[6] = c.n_int_epep; sizes[7] = c.n_int_epsp;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, const double *r_out,
+                              const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
+                              int rank, long long *sizes)
+{
+    if (n <= 0 || !pos || !mass || !r_out || !r_search || theta <= 0.0) return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    const size_t N = (size_t)n;
+    if (int r = g.tree_in.reserve(N * 48)) return r;
+    if (int r = g.tree_raw.reserve(N * sizeof(EpjAos))) return r;
+    double *d = (double *)g.tree_in.p;
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(d, pos, N * 24, H2D, st));
+    CU(cudaMemcpyAsync(d + 3 * N, mass, N * 8, H2D, st));
+    CU(cudaMemcpyAsync(d + 4 * N, r_out, N * 8, H2D, st));
+    CU(cudaMemcpyAsync(d + 5 * N, r_search, N * 8, H2D, st));
+    int launches = 0;
+    if (int e = gbt::tree_soa_to_epj(n, d, d + 3 * N, d + 4 * N, d + 5 * N, rank, g.tree_raw.p, st, &launches))
+        return fail(GPLUM_B200_ERR_CUDA, "soa_to_epj: %s", cudaGetErrorString((cudaError_t)e));
+    g.launches += launches;
+    return tree_build_common(n, g.tree_raw.p, theta, n_leaf_limit, n_group_limit, sizes);
+}
+
+int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double theta, int n_leaf_limit,
+                                  int n_group_limit, long long *sizes)
+{
+    if (n <= 0 || !epj || theta <= 0.0) return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu_epj: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    const void *src = epj;
+    if (!on_device) {
+        if (int r = g.tree_raw.reserve((size_t)n * sizeof(EpjAos))) return r;
+        CU(cudaMemcpyAsync(g.tree_raw.p, epj, (size_t)n * sizeof(EpjAos), cudaMemcpyHostToDevice, g.stream));
+        src = g.tree_raw.p;
+    }
+    return tree_build_common(n, src, theta, n_leaf_limit, n_group_limit, sizes);
+}
+
+int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,
+                             int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
+                             int *sorted_to_original)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_copy_gpu: no GPU-built tree in the selected slot");
+    CU(cudaSetDevice(g.device));
+    WalkSet &ws = g.slots[g.cur];
+    JSet &j = g.jset;
+    CU(cudaStreamSynchronize(g.stream));
+    const cudaMemcpyKind D2H = cudaMemcpyDeviceToHost;
+    const size_t nw = (size_t)ws.n_walk, ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
+    if (epi) CU(cudaMemcpy(epi, ws.epi.p, (size_t)ws.n_epi * sizeof(EpiAos), D2H));
+    if (epj_all) CU(cudaMemcpy(epj_all, j.epj_aos.p, (size_t)j.n_epj * sizeof(EpjAos), D2H));
+    if (spj_all && j.n_spj) CU(cudaMemcpy(spj_all, j.spj_aos.p, (size_t)j.n_spj * ssz, D2H));
+    if (sorted_to_original) CU(cudaMemcpy(sorted_to_original, gbt::tree_sorted_to_original(), (size_t)ws.n_epi * 4, D2H));
+    if (nw) {
+        if (epi_off) CU(cudaMemcpy(epi_off, ws.epi_off.p, nw * 4, D2H));
+        if (ni) CU(cudaMemcpy(ni, gbt::tree_walk_ni(), nw * 4, D2H));
+        if (n_epj) CU(cudaMemcpy(n_epj, ws.n_epj.p, nw * 4, D2H));
+        if (n_spj) CU(cudaMemcpy(n_spj, ws.n_spj.p, nw * 4, D2H));
+        if (epj_disp) CU(cudaMemcpy(epj_disp, ws.epj_disp.p, nw * 8, D2H));
+        if (spj_disp) CU(cudaMemcpy(spj_disp, ws.spj_disp.p, nw * 8, D2H));
+    }
+    if (adr_epj && ws.n_adr_epj) CU(cudaMemcpy(adr_epj, ws.adr_epj.p, (size_t)ws.n_adr_epj * 4, D2H));
+    if (adr_spj && ws.n_adr_spj) CU(cudaMemcpy(adr_spj, ws.adr_spj.p, (size_t)ws.n_adr_spj * 4, D2H));
+    return 0;
+}
+
+int gplum_b200_tree_gpu_times(float *ms6)
+{
+    if (!ms6) return fail(GPLUM_B200_ERR_ARG, "tree_gpu_times: NULL");
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_gpu_times: no GPU-built tree");
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamSynchronize(g.stream));
+    gbt::tree_phase_ms(ms6);
     return 0;
 }
 

@@ -39,3 +39,51 @@ def build_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_l
     w = Walks(epi, epi_off, ni, adr_e, ed, ne, adr_s, sd, ns, epj, spj)
     assert w.n_interactions() == (int(sz[6]), int(sz[7]))
     return w, order
+
+
+# ------------------------------------------------------------------ on the GPU (csrc/dev_tree.cu)
+def build_walks_gpu(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=64, rank=0):
+    """Builds tree, i-groups and lists on the device from SoA host arrays; the result becomes the
+    selected resident walk set + j-set (nothing is copied back).  Returns sizes[8] like the host
+    builder: n_walk, n_epi, n_adr_epj, n_adr_spj, n_epj_all, n_spj_all, n_int_epep, n_int_epsp."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    n = len(pos)
+    mass = np.ascontiguousarray(np.broadcast_to(mass, (n,)), dtype=np.float64)
+    r_out = np.ascontiguousarray(np.broadcast_to(r_out, (n,)), dtype=np.float64)
+    r_search = np.ascontiguousarray(np.broadcast_to(r_search, (n,)), dtype=np.float64)
+    sz = np.zeros(8, dtype=np.int64)
+    check(lib().gplum_b200_tree_build_gpu(n, _p(pos), _p(mass), _p(r_out), _p(r_search), float(theta),
+                                          int(n_leaf_limit), int(n_group_limit), int(rank), _p(sz)))
+    return sz
+
+
+def build_walks_gpu_epj(epj, theta=0.5, n_leaf_limit=8, n_group_limit=64):
+    """Same from EPJGrav records in any order (FDPS's epj_org_), host memory."""
+    epj = np.ascontiguousarray(epj, dtype=S.EPJ)
+    sz = np.zeros(8, dtype=np.int64)
+    check(lib().gplum_b200_tree_build_gpu_epj(len(epj), _p(epj), 0, float(theta), int(n_leaf_limit),
+                                              int(n_group_limit), _p(sz)))
+    return sz
+
+
+def copy_walks_gpu(sz, quad=True):
+    """(Walks, sorted_to_original) of the last GPU build, copied to the host (tests)."""
+    nw, n = int(sz[0]), int(sz[1])
+    epi = np.zeros(n, dtype=S.EPI)
+    epj = np.zeros(int(sz[4]), dtype=S.EPJ)
+    spj = np.zeros(int(sz[5]), dtype=S.SPJ_QUAD if quad else S.SPJ_MONO)
+    epi_off = np.zeros(nw, np.int32); ni = np.zeros(nw, np.int32)
+    adr_e = np.zeros(int(sz[2]), np.int32); adr_s = np.zeros(int(sz[3]), np.int32)
+    ed = np.zeros(nw, np.int64); sd = np.zeros(nw, np.int64)
+    ne = np.zeros(nw, np.int32); ns = np.zeros(nw, np.int32)
+    order = np.zeros(n, np.int32)
+    check(lib().gplum_b200_tree_copy_gpu(_p(epi), _p(epi_off), _p(ni), _p(adr_e), _p(ed), _p(ne), _p(adr_s),
+                                         _p(sd), _p(ns), _p(epj), _p(spj), _p(order)))
+    return Walks(epi, epi_off, ni, adr_e, ed, ne, adr_s, sd, ns, epj, spj), order
+
+
+def gpu_build_times():
+    """Device milliseconds of the last GPU build, by phase."""
+    ms = (C.c_float * 6)()
+    check(lib().gplum_b200_tree_gpu_times(ms))
+    return dict(zip(("sort_gather", "cells_groups", "moments", "count_walk", "fill_walk", "items_spj"), [float(x) for x in ms]))

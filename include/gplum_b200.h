@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GPLUM_B200_ABI_VERSION 2
+#define GPLUM_B200_ABI_VERSION 3
 
 /* mode flags (gplum_b200_set_params) */
 #define GPLUM_B200_TRACE_AS_SHIPPED 1 /* tr = qxx+qyy+qxx, the non-PIKG branch's arithmetic
@@ -195,6 +195,31 @@ int gplum_b200_tree_copy(void *epi, int *epi_off, int *ni, int *adr_epj, long lo
                          int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
                          int quad, int rank, int *sorted_to_original);
 void gplum_b200_tree_free(void);
+
+/* ---- interaction-list builder on the GPU (gplum_b200/csrc/dev_tree.cu) ----
+ * Same semantics, cell numbering and FP64 results as gplum_b200_tree_build, but every stage runs on the
+ * device: Morton keys, radix sort, cells level by level (FDPS LinkCell, tree_for_force_utils.hpp:289),
+ * moments + in/out boxes bottom-up (utils_moment.hpp:6,189), i-groups (MakeIPGroup, utils.hpp:619-650),
+ * one warp per group for the symmetric-search walk (tree_walk.hpp:545-583,706-785), work items.  The
+ * result is not copied anywhere: it becomes the selected resident walk set and the current j-set (EPJ in
+ * tree order, SPJ = cell moments, both packed), ready for gplum_b200_walks_run / _download and the
+ * changeover correction.  Lists equal the host builder's as sets; within a list the order differs.
+ *   tree_build_gpu      SoA host inputs (pos is [n][3]), 48 B per particle over PCIe; EPJ records get
+ *                       id_local = id = input index, myrank = rank, vel = acc_d = 0.
+ *   tree_build_gpu_epj  EPJGrav[n] in any order (FDPS's epj_org_), host or device memory (16 B aligned);
+ *                       records are carried whole, so the correction sees vel / acc_d / id.
+ *   tree_copy_gpu       copies lists / particles back to host arrays (tests; any pointer may be NULL).
+ *   tree_gpu_times      device milliseconds of the last build: keys+sort+gather, cells+groups, moments,
+ *                       counting walk+scans, filling walk, items+SPJ. */
+int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, const double *r_out,
+                              const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
+                              int rank, long long *sizes);
+int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double theta, int n_leaf_limit,
+                                  int n_group_limit, long long *sizes);
+int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,
+                             int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
+                             int *sorted_to_original);
+int gplum_b200_tree_gpu_times(float *ms6);
 
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */

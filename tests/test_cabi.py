@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     h = C.CDLL(_lib.LIB_PATH)
     for name in _declared():
         assert hasattr(h, name), name
-    assert _lib.lib().gplum_b200_abi_version() == 2
+    assert _lib.lib().gplum_b200_abi_version() == 3
     e, s = C.c_int(0), C.c_int(0)
     _lib.lib().gplum_b200_packed_sizes(C.byref(e), C.byref(s))
     assert (e.value, s.value) == (48, 64)
