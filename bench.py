@@ -254,6 +254,9 @@ def main():
     import ctypes as C
 
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: one JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w, t_build = make_workload(args.n, args.group)
@@ -361,7 +364,12 @@ def main():
     alg_bytes = (48 + 32) * (len(w.epi) if world == 1 else len(sh.local.epi)) + \
         4 * ((len(w.adr_epj) + len(w.adr_spj)) if world == 1 else (len(sh.local.adr_epj) + len(sh.local.adr_spj)))
     roofline = {"bound": "fp32", "kernel": "force_pass_kernel", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
+                # (profiles/r1_force_pass_v5_ncu_summary.txt: 235.96 MB read + 32.71 MB written); other
+                # workloads have no capture
+                "traffic": 268674560 if (world == 1 and args.n == 1000000 and args.group == 512) else None,
+                "traffic_unit": "bytes/launch",
                 "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no CUDA-core figure); "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "kernel_ms": k_ms, "flop_per_launch": flop,

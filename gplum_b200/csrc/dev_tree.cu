@@ -21,6 +21,7 @@
 // consecutive records; cells of one level are contiguous (breadth-first numbering), which is what
 // makes the level-by-level build and the bottom-up moment sweep coalesced.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -46,7 +47,7 @@ namespace {
 
 constexpr int MAX_LEVEL = 21;
 constexpr int N_LVL = MAX_LEVEL + 2;       // lvl_start[l] .. lvl_start[l+1] = cells of level l, l = 0..21
-constexpr int NB = 592;                    // blocks of the level kernels (4 per SM), <= 1024 (split_scan_kernel)
+constexpr int NB = 444;                    // blocks of the cooperative tree kernel (3 per SM on 148 SMs)
 constexpr int TPB = 256;
 constexpr int WALK_WPB = 8;                // warps per block of the walk kernels
 constexpr int STK = 1024;                  // per-warp stack of open cells (depth-first in steps of 4: <= ~28 x levels)
@@ -81,12 +82,12 @@ struct Meta {
 
 struct State {
     Buf keys_a, keys_b, idx_a, idx_b, cub_temp;
-    Buf bbox_part, meta, blk_cnt, blk_off;
+    Buf bbox_part, meta, blk_cnt;
     Buf c_meta, c_mom, c_box, fr_a, fr_b, grp_at, walk_cell;
     Buf w_epi_off, w_ni, w_ne, w_ns, w_ed, w_sd, w_nitems, w_ioff;
     Buf item_key_a, item_key_b, item_a;
     Meta *h_meta = nullptr;                // pinned
-    int cell_cap = 0, n = 0, n_walk = 0, n_cells = 0, n_levels = 0, lvl_start[N_LVL + 1] = {};
+    int coop_blocks = 0, cell_cap = 0, n = 0, n_walk = 0, n_cells = 0, n_levels = 0, lvl_start[N_LVL + 1] = {};
     cudaEvent_t ev[7] = {};
     bool ev_ok = false, timed = false;
 } S;
@@ -227,12 +228,14 @@ __global__ void __launch_bounds__(TPB) soa_to_epj_kernel(int n, const double *__
 // The frontier of level L = its cells that split (n > n_leaf), in breadth-first order; the children of
 // frontier entry f are the 8 cells lvl_start[L+1] + 8 f + o.  8 lanes work on one cell: lane o finds
 // the end of octant o by binary search on the key digit of that level.
-__device__ __forceinline__ void child_range(const KP &P, const int *__restrict__ fr, int f, int f1, int o, int L,
+// (Cells and frontier entries are written by other blocks of the same launch one grid barrier earlier:
+// they are read with ld.global.cg, never through L1 or the read-only path.)
+__device__ __forceinline__ void child_range(const KP &P, const int *fr, int f, int f1, int o, int L,
                                             int &cell, int &pn, int &lb, int &ub)
 {
     int first = 0, n = 0;
     cell = -1;
-    if (f < f1) { cell = fr[f]; const int4 m = P.c_meta[cell]; first = m.x; n = m.y; }
+    if (f < f1) { cell = __ldcg(fr + f); const int4 m = __ldcg(P.c_meta + cell); first = m.x; n = m.y; }
     pn = n;
     const int end = first + n;
     ub = end;
@@ -256,144 +259,82 @@ __device__ __forceinline__ void chunk_of(int F, int &f0, int &f1)
     f1 = min(F, f0 + chunk);
 }
 
-__global__ void __launch_bounds__(TPB) split_count_kernel(KP P, const int *__restrict__ fr, int L, int *__restrict__ blk_cnt)
+// One thread per cell.  A cell's latency is what a level costs (every level ends in a grid barrier), so the
+// loads of a cell are issued in batches that do not depend on each other: leaf particles four at a time
+// (index clamped, accumulation predicated -- the order of the sums stays the host's), the 8 children of an
+// inner cell unconditionally (an empty child holds mass = com = quad = 0 and boxes at +-1e300: adding it is
+// exact, so skipping it like the host does and not skipping it give the same bits).
+__device__ __forceinline__ void moment_cell(const KP &P, int c)
 {
-    const int F = P.meta->fcount[L];
-    int f0, f1;
-    chunk_of(F, f0, f1);
-    int cnt = 0;
-    for (int base = f0; base < f1; base += TPB / 8) {
-        int cell, pn, lb, ub;
-        child_range(P, fr, base + (threadIdx.x >> 3), f1, threadIdx.x & 7, L, cell, pn, lb, ub);
-        cnt += (ub - lb > P.n_leaf && L + 1 < MAX_LEVEL) ? 1 : 0;
-    }
-    __shared__ int sm[TPB / 32];
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int w = 0; w < TPB / 32; w++) s += sm[w];
-        blk_cnt[blockIdx.x] = s;
-    }
-}
-
-__global__ void __launch_bounds__(1024) split_scan_kernel(KP P, int L, int nb, const int *__restrict__ blk_cnt, int *__restrict__ blk_off)
-{
-    __shared__ int wsum[32];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int v = t < nb ? blk_cnt[t] : 0;
-    int inc = v;
-    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += u; }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int s = wsum[lane];
-        for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(FULL, s, d); if (lane >= d) s += u; }
-        wsum[lane] = s;                            // inclusive over warps
-    }
-    __syncthreads();
-    const int woff = w > 0 ? wsum[w - 1] : 0;
-    if (t < nb) blk_off[t] = woff + inc - v;
-    if (t == 0) {
-        Meta *m = P.meta;
-        int total = wsum[31];                      // cells of level L+1 that split
-        const int F = m->fcount[L];
-        const int next_start = m->lvl_start[L + 1] + 8 * F;      // first cell of level L+2
-        // this level's children were checked one level up; make sure the next level's children fit
-        if ((long long)next_start + 8LL * total > (long long)P.cell_cap) { m->overflow = 1; total = 0; }
-        for (int l = L + 2; l <= N_LVL; l++) m->lvl_start[l] = next_start;
-        m->fcount[L + 1] = total;
-    }
-}
-
-__global__ void __launch_bounds__(TPB) split_write_kernel(KP P, const int *__restrict__ fr, int *__restrict__ fr_next, int L,
-                                                          const int *__restrict__ blk_off)
-{
-    const int F = P.meta->fcount[L];
-    if (F == 0) return;
-    const int cbase = P.meta->lvl_start[L + 1];
-    int f0, f1;
-    chunk_of(F, f0, f1);
-    __shared__ int wcnt[TPB / 32];
-    int running = blk_off[blockIdx.x];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, o = threadIdx.x & 7;
-    for (int base = f0; base < f1; base += TPB / 8) {
-        const int f = base + (threadIdx.x >> 3);
-        int cell, pn, lb, ub;
-        child_range(P, fr, f, f1, o, L, cell, pn, lb, ub);
-        const int cn = ub - lb;
-        const bool will = cell >= 0 && cn > P.n_leaf && L + 1 < MAX_LEVEL;
-        const unsigned bal = __ballot_sync(FULL, will);
-        if (lane == 0) wcnt[w] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int k = 0; k < TPB / 32; k++) { const int c = wcnt[k]; if (k < w) before += c; total += c; }
-        __syncthreads();
-        if (cell >= 0) {
-            const int cidx = cbase + 8 * f + o;
-            P.c_meta[cidx] = make_int4(lb, cn, -1, L + 1);
-            if (o == 0) reinterpret_cast<int *>(&P.c_meta[cell])[2] = cbase + 8 * f;
-            // i-groups: the shallowest cells with <= n_group particles (or leaves)
-            if (pn > P.n_group && cn > 0 && (cn <= P.n_group || !will)) P.grp_at[lb] = cidx;
-            if (will) fr_next[running + before + __popc(bal & ((1u << lane) - 1))] = cidx;
-        }
-        running += total;
-    }
-}
-
-// ---- moments and boxes, bottom-up, one level per launch (children are complete before parents) ----
-__global__ void __launch_bounds__(TPB) moment_kernel(KP P, int c0, int c1)
-{
-    const int c = c0 + blockIdx.x * TPB + threadIdx.x;
-    if (c >= c1) return;
-    const int4 m = P.c_meta[c];
+    const int4 m = __ldcg(P.c_meta + c);
     double mass = 0, com[3] = {0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0};
     double ilo[3] = {1e300, 1e300, 1e300}, ihi[3] = {-1e300, -1e300, -1e300};
     double olo[3] = {1e300, 1e300, 1e300}, ohi[3] = {-1e300, -1e300, -1e300};
     if (m.y > 0) {
         if (m.z < 0) {
-            for (int i = m.x; i < m.x + m.y; i++) {
-                const EpjAos &p = P.epj[i];
-                const double mi = p.mass, rs = 1.1 * p.r_search;
-                mass += mi;
-                for (int k = 0; k < 3; k++) {
-                    const double x = p.pos[k];
-                    com[k] += mi * x;
-                    ilo[k] = fmin(ilo[k], x - 0.0); ihi[k] = fmax(ihi[k], x + 0.0);
-                    olo[k] = fmin(olo[k], x - rs); ohi[k] = fmax(ohi[k], x + rs);
+            const int end = m.x + m.y;
+            for (int i0 = m.x; i0 < end; i0 += 4) {
+                double mi[4], rs[4], x[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const EpjAos &p = P.epj[min(i0 + u, end - 1)];
+                    mi[u] = p.mass; rs[u] = p.r_search;
+                    x[u][0] = p.pos[0]; x[u][1] = p.pos[1]; x[u][2] = p.pos[2];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + u < end) {
+                        const double r = 1.1 * rs[u];
+                        mass += mi[u];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            com[k] += mi[u] * x[u][k];
+                            ilo[k] = fmin(ilo[k], x[u][k] - 0.0); ihi[k] = fmax(ihi[k], x[u][k] + 0.0);
+                            olo[k] = fmin(olo[k], x[u][k] - r); ohi[k] = fmax(ohi[k], x[u][k] + r);
+                        }
+                    }
                 }
             }
             for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
-            for (int i = m.x; i < m.x + m.y; i++) {
-                const EpjAos &p = P.epj[i];
-                const double mi = p.mass;
-                const double d0 = p.pos[0] - com[0], d1 = p.pos[1] - com[1], d2 = p.pos[2] - com[2];
-                q[0] += mi * d0 * d0; q[1] += mi * d1 * d1; q[2] += mi * d2 * d2;
-                q[3] += mi * d0 * d1; q[4] += mi * d0 * d2; q[5] += mi * d1 * d2;
+            for (int i0 = m.x; i0 < end; i0 += 4) {
+                double mi[4], x[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const EpjAos &p = P.epj[min(i0 + u, end - 1)];
+                    mi[u] = p.mass;
+                    x[u][0] = p.pos[0]; x[u][1] = p.pos[1]; x[u][2] = p.pos[2];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + u < end) {
+                        const double d0 = x[u][0] - com[0], d1 = x[u][1] - com[1], d2 = x[u][2] - com[2];
+                        q[0] += mi[u] * d0 * d0; q[1] += mi[u] * d1 * d1; q[2] += mi[u] * d2 * d2;
+                        q[3] += mi[u] * d0 * d1; q[4] += mi[u] * d0 * d2; q[5] += mi[u] * d1 * d2;
+                    }
+                }
             }
         } else {
+            const double *cm0 = P.c_mom + (size_t)m.z * 10, *cb0 = P.c_box + (size_t)m.z * 12;
+#pragma unroll
             for (int o = 0; o < 8; o++) {
-                const int ch = m.z + o;
-                if (P.c_meta[ch].y == 0) continue;
-                const double *cm = P.c_mom + (size_t)ch * 10, *cb = P.c_box + (size_t)ch * 12;
-                const double cmass = cm[0];
+                const double *cm = cm0 + o * 10, *cb = cb0 + o * 12;
+                const double cmass = __ldcg(cm);
                 mass += cmass;
+#pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    com[k] += cmass * cm[1 + k];
-                    ilo[k] = fmin(ilo[k], cb[k]); ihi[k] = fmax(ihi[k], cb[3 + k]);
-                    olo[k] = fmin(olo[k], cb[6 + k]); ohi[k] = fmax(ohi[k], cb[9 + k]);
+                    com[k] += cmass * __ldcg(cm + 1 + k);
+                    ilo[k] = fmin(ilo[k], __ldcg(cb + k)); ihi[k] = fmax(ihi[k], __ldcg(cb + 3 + k));
+                    olo[k] = fmin(olo[k], __ldcg(cb + 6 + k)); ohi[k] = fmax(ohi[k], __ldcg(cb + 9 + k));
                 }
             }
             for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
+#pragma unroll
             for (int o = 0; o < 8; o++) {
-                const int ch = m.z + o;
-                if (P.c_meta[ch].y == 0) continue;
-                const double *cm = P.c_mom + (size_t)ch * 10;
-                const double mi = cm[0];
-                const double d0 = cm[1] - com[0], d1 = cm[2] - com[1], d2 = cm[3] - com[2];
-                q[0] += mi * d0 * d0 + cm[4]; q[1] += mi * d1 * d1 + cm[5]; q[2] += mi * d2 * d2 + cm[6];
-                q[3] += mi * d0 * d1 + cm[7]; q[4] += mi * d0 * d2 + cm[8]; q[5] += mi * d1 * d2 + cm[9];
+                const double *cm = cm0 + o * 10;
+                const double mi = __ldcg(cm);
+                const double d0 = __ldcg(cm + 1) - com[0], d1 = __ldcg(cm + 2) - com[1], d2 = __ldcg(cm + 3) - com[2];
+                q[0] += mi * d0 * d0 + __ldcg(cm + 4); q[1] += mi * d1 * d1 + __ldcg(cm + 5); q[2] += mi * d2 * d2 + __ldcg(cm + 6);
+                q[3] += mi * d0 * d1 + __ldcg(cm + 7); q[4] += mi * d0 * d2 + __ldcg(cm + 8); q[5] += mi * d1 * d2 + __ldcg(cm + 9);
             }
         }
     }
@@ -401,6 +342,94 @@ __global__ void __launch_bounds__(TPB) moment_kernel(KP P, int c0, int c1)
     om[0] = mass;
     for (int k = 0; k < 3; k++) { om[1 + k] = com[k]; ob[k] = ilo[k]; ob[3 + k] = ihi[k]; ob[6 + k] = olo[k]; ob[9 + k] = ohi[k]; }
     for (int k = 0; k < 6; k++) om[4 + k] = q[k];
+}
+
+// ---- cells (top-down, one level per pair of grid barriers) and moments + boxes (bottom-up, one level per
+// barrier) in ONE cooperative launch: the level loops are latency chains of tiny kernels otherwise (a 1e6
+// disk has 12 levels; 3 launches per level and 21 possible levels cost more than the work) ----
+__global__ void __launch_bounds__(TPB, 3) tree_coop_kernel(KP P, int *fr_a, int *fr_b, int *blk_cnt)
+{
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ int wcnt[TPB / 32];
+    __shared__ int s_red[2][TPB / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, o = threadIdx.x & 7;
+    const int nb = gridDim.x, b = blockIdx.x;
+    Meta *meta = P.meta;
+    int *fr = fr_a, *fr_next = fr_b;
+    int L = 0;
+    for (; L < MAX_LEVEL; L++) {
+        const int F = __ldcg(&meta->fcount[L]);
+        if (F == 0) break;                                   // same value in every block
+        int f0, f1;
+        chunk_of(F, f0, f1);
+        // phase A: how many children of my chunk of the frontier split again
+        int cnt = 0;
+        int cell0 = -1, pn0 = 0, lb0 = 0, ub0 = 0;           // first round's searches, reused in phase B
+        for (int base = f0; base < f1; base += TPB / 8) {
+            int cell, pn, lb, ub;
+            child_range(P, fr, base + (threadIdx.x >> 3), f1, o, L, cell, pn, lb, ub);
+            if (base == f0) { cell0 = cell; pn0 = pn; lb0 = lb; ub0 = ub; }
+            cnt += (ub - lb > P.n_leaf && L + 1 < MAX_LEVEL) ? 1 : 0;
+        }
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+        if (lane == 0) wcnt[w] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int k = 0; k < TPB / 32; k++) s += wcnt[k];
+            blk_cnt[b] = s;
+        }
+        grid.sync();
+        // phase B: my offset into the next frontier = counts of the blocks before me
+        int before_me = 0, total = 0;
+        for (int k = threadIdx.x; k < nb; k += TPB) { const int v = __ldcg(blk_cnt + k); total += v; if (k < b) before_me += v; }
+        for (int d = 16; d > 0; d >>= 1) { before_me += __shfl_xor_sync(FULL, before_me, d); total += __shfl_xor_sync(FULL, total, d); }
+        if (lane == 0) { s_red[0][w] = before_me; s_red[1][w] = total; }
+        __syncthreads();
+        before_me = 0; total = 0;
+        for (int k = 0; k < TPB / 32; k++) { before_me += s_red[0][k]; total += s_red[1][k]; }
+        const int cbase = __ldcg(&meta->lvl_start[L + 1]);
+        if (b == 0 && threadIdx.x == 0) {
+            const int next_start = cbase + 8 * F;            // first cell of level L+2
+            int t = total;
+            // this level's children were checked one level up; make sure the next level's children fit
+            if ((long long)next_start + 8LL * t > (long long)P.cell_cap) { meta->overflow = 1; t = 0; }
+            for (int l = L + 2; l <= N_LVL; l++) meta->lvl_start[l] = next_start;
+            meta->fcount[L + 1] = t;
+        }
+        int running = before_me;
+        for (int base = f0; base < f1; base += TPB / 8) {
+            const int f = base + (threadIdx.x >> 3);
+            int cell = cell0, pn = pn0, lb = lb0, ub = ub0;
+            if (base != f0) child_range(P, fr, f, f1, o, L, cell, pn, lb, ub);      // block-uniform branch
+            const int cn = ub - lb;
+            const bool will = cell >= 0 && cn > P.n_leaf && L + 1 < MAX_LEVEL;
+            const unsigned bal = __ballot_sync(FULL, will);
+            __syncthreads();                                 // wcnt of the previous round has been read
+            if (lane == 0) wcnt[w] = __popc(bal);
+            __syncthreads();
+            int before = 0, tot = 0;
+            for (int k = 0; k < TPB / 32; k++) { const int c = wcnt[k]; if (k < w) before += c; tot += c; }
+            if (cell >= 0) {
+                const int cidx = cbase + 8 * f + o;
+                P.c_meta[cidx] = make_int4(lb, cn, -1, L + 1);
+                if (o == 0) reinterpret_cast<int *>(&P.c_meta[cell])[2] = cbase + 8 * f;
+                // i-groups: the shallowest cells with <= n_group particles (or leaves)
+                if (pn > P.n_group && cn > 0 && (cn <= P.n_group || !will)) P.grp_at[lb] = cidx;
+                if (will) fr_next[running + before + __popc(bal & ((1u << lane) - 1))] = cidx;
+            }
+            running += tot;
+        }
+        grid.sync();
+        int *t = fr; fr = fr_next; fr_next = t;
+    }
+    // cells exist on levels 0..L; the barrier that ended the last level also published its cells
+    const int gtid = b * TPB + threadIdx.x, gthreads = nb * TPB;
+    for (int l = L; l >= 0; l--) {
+        const int c0 = __ldcg(&meta->lvl_start[l]), c1 = __ldcg(&meta->lvl_start[l + 1]);
+        for (int c = c0 + gtid; c < c1; c += gthreads) moment_cell(P, c);
+        if (l > 0) grid.sync();
+    }
 }
 
 // ---- per-group walk: one warp per group, depth-first in steps of 4 cells x 8 children ----
@@ -594,13 +623,13 @@ void tree_phase_ms(float ms[6])
 
 void tree_release()
 {
-    for (Buf *b : {&S.keys_a, &S.keys_b, &S.idx_a, &S.idx_b, &S.cub_temp, &S.bbox_part, &S.meta, &S.blk_cnt, &S.blk_off,
+    for (Buf *b : {&S.keys_a, &S.keys_b, &S.idx_a, &S.idx_b, &S.cub_temp, &S.bbox_part, &S.meta, &S.blk_cnt,
                    &S.c_meta, &S.c_mom, &S.c_box, &S.fr_a, &S.fr_b, &S.grp_at, &S.walk_cell, &S.w_epi_off, &S.w_ni, &S.w_ne,
                    &S.w_ns, &S.w_ed, &S.w_sd, &S.w_nitems, &S.w_ioff, &S.item_key_a, &S.item_key_b, &S.item_a})
         b->release();
     if (S.h_meta) { cudaFreeHost(S.h_meta); S.h_meta = nullptr; }
     if (S.ev_ok) { for (auto &e : S.ev) cudaEventDestroy(e); S.ev_ok = false; }
-    S.timed = false; S.cell_cap = 0; S.n = 0;
+    S.timed = false; S.cell_cap = 0; S.n = 0; S.coop_blocks = 0;
 }
 
 int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *r_out, const double *r_search,
@@ -630,6 +659,15 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
     S.timed = false;
     if (!S.ev_ok) { for (auto &e : S.ev) CK(cudaEventCreate(&e)); S.ev_ok = true; }
     if (!S.h_meta) CK(cudaMallocHost((void **)&S.h_meta, sizeof(Meta)));
+    if (S.coop_blocks == 0) {
+        int dev = 0, sms = 0, occ = 0, coop = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tree_coop_kernel, TPB, 0));
+        if (!coop || occ < 1) return (int)cudaErrorCooperativeLaunchTooLarge;
+        S.coop_blocks = std::min(NB, occ * sms);          // every block must be resident: grid barriers
+    }
     // the host builder's tree of the N = 1e6 disk has 0.74 n cells; a rejected capacity doubles and retries
     if (S.n != n || S.cell_cap == 0) S.cell_cap = 2 * n + 4096;
     S.n = n;
@@ -638,9 +676,9 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         CK(S.keys_a.reserve((size_t)n * 8)); CK(S.keys_b.reserve((size_t)n * 8));
         CK(S.idx_a.reserve((size_t)n * 4)); CK(S.idx_b.reserve((size_t)n * 4));
         CK(S.bbox_part.reserve((size_t)NB * 6 * 8)); CK(S.meta.reserve(sizeof(Meta)));
-        CK(S.blk_cnt.reserve(NB * 4)); CK(S.blk_off.reserve(NB * 4));
+        CK(S.blk_cnt.reserve(NB * 4));
         CK(S.c_meta.reserve(C * sizeof(int4))); CK(S.c_mom.reserve(C * 80)); CK(S.c_box.reserve(C * 96));
-        CK(S.fr_a.reserve(C / 8 * 4 + 64)); CK(S.fr_b.reserve(C / 8 * 4 + 64));
+        CK(S.fr_a.reserve(C * 4 + 64)); CK(S.fr_b.reserve(C * 4 + 64));     // a frontier <= the cells of its level
         CK(S.grp_at.reserve((size_t)n * 4)); CK(S.walk_cell.reserve((size_t)n * 4 + 16));
         KP P = make_kp(cfg, epj_sorted);
         const EpjAos *raw = (const EpjAos *)epj_unsorted;
@@ -665,24 +703,22 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         *launches += 1;
         CK(cudaEventRecord(S.ev[1], st));
 
-        // cells: frontier arrays ping-pong; level 0's frontier is the root
+        // cells + moments: one cooperative launch; frontier arrays ping-pong, level 0's frontier is the root
         CK(cudaMemsetAsync(S.fr_a.p, 0, 4, st));
-        int *fr = (int *)S.fr_a.p, *fr_next = (int *)S.fr_b.p;
-        for (int L = 0; L < MAX_LEVEL; L++) {
-            split_count_kernel<<<NB, TPB, 0, st>>>(P, fr, L, (int *)S.blk_cnt.p);
-            split_scan_kernel<<<1, 1024, 0, st>>>(P, L, NB, (const int *)S.blk_cnt.p, (int *)S.blk_off.p);
-            split_write_kernel<<<NB, TPB, 0, st>>>(P, fr, fr_next, L, (const int *)S.blk_off.p);
-            std::swap(fr, fr_next);
-            *launches += 3;
+        {
+            int *fr_a = (int *)S.fr_a.p, *fr_b = (int *)S.fr_b.p, *bc = (int *)S.blk_cnt.p;
+            void *args[] = {&P, &fr_a, &fr_b, &bc};
+            CK(cudaLaunchCooperativeKernel((const void *)tree_coop_kernel, dim3(S.coop_blocks), dim3(TPB), args, 0, st));
+            *launches += 1;
         }
-        CK(cudaGetLastError());
+        CK(cudaEventRecord(S.ev[2], st));
         // i-groups in Morton order: grp_at[first particle] = cell, compacted
         int *d_nwalk = &((Meta *)S.meta.p)->n_walk;
         CK(cub::DeviceSelect::If(nullptr, tb, (const int *)S.grp_at.p, (int *)S.walk_cell.p, d_nwalk, n, NonNeg(), st));
         CK(S.cub_temp.reserve(tb));
         CK(cub::DeviceSelect::If(S.cub_temp.p, tb, (const int *)S.grp_at.p, (int *)S.walk_cell.p, d_nwalk, n, NonNeg(), st));
         CK(cudaMemcpyAsync(S.h_meta, S.meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(S.ev[2], st));
+        CK(cudaEventRecord(S.ev[3], st));
         CK(cudaStreamSynchronize(st));
         if (S.h_meta->overflow) {
             if (attempt >= 4) { counts->overflow = 1; return -1; }
@@ -697,14 +733,6 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
     S.n_walk = S.h_meta->n_walk;
     S.n_levels = 0;
     for (int l = 0; l < N_LVL; l++) if (S.lvl_start[l + 1] > S.lvl_start[l]) S.n_levels = l + 1;
-    for (int l = S.n_levels - 1; l >= 0; l--) {
-        const int c0 = S.lvl_start[l], c1 = S.lvl_start[l + 1];
-        moment_kernel<<<nblk(c1 - c0, TPB), TPB, 0, st>>>(P, c0, c1);
-        ++*launches;
-    }
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(S.ev[3], st));
-
     const int nw = S.n_walk;
     for (Buf *b : {&S.w_epi_off, &S.w_ni, &S.w_ne, &S.w_ns, &S.w_nitems, &S.w_ioff}) CK(b->reserve((size_t)nw * 4 + 16));
     CK(S.w_ed.reserve((size_t)nw * 8 + 16)); CK(S.w_sd.reserve((size_t)nw * 8 + 16));

@@ -44,8 +44,9 @@ int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *
                     int rank, void *epj_out, cudaStream_t st, int *launches);
 const int *tree_sorted_to_original();            // device pointer, n entries, valid after phase 1
 const int *tree_walk_ni();                       // device pointer, n_walk entries: i-particles per walk
-// milliseconds between the phase marks of the last build: [0] keys+sort+gather, [1] cells+groups,
-// [2] moments, [3] counting walk + scans, [4] filling walk, [5] items + SPJ
+// milliseconds between the phase marks of the last build: [0] keys+sort+gather, [1] cells+moments (one
+// cooperative kernel), [2] i-group compaction + first host sync, [3] counting walk + scans + second sync,
+// [4] filling walk, [5] items + SPJ
 void tree_phase_ms(float ms[6]);
 void tree_release();
 

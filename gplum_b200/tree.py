@@ -86,4 +86,4 @@ def gpu_build_times():
     """Device milliseconds of the last GPU build, by phase."""
     ms = (C.c_float * 6)()
     check(lib().gplum_b200_tree_gpu_times(ms))
-    return dict(zip(("sort_gather", "cells_groups", "moments", "count_walk", "fill_walk", "items_spj"), [float(x) for x in ms]))
+    return dict(zip(("sort_gather", "cells_moments", "groups_sync", "count_walk", "fill_walk", "items_spj"), [float(x) for x in ms]))

@@ -209,8 +209,8 @@ void gplum_b200_tree_free(void);
  *   tree_build_gpu_epj  EPJGrav[n] in any order (FDPS's epj_org_), host or device memory (16 B aligned);
  *                       records are carried whole, so the correction sees vel / acc_d / id.
  *   tree_copy_gpu       copies lists / particles back to host arrays (tests; any pointer may be NULL).
- *   tree_gpu_times      device milliseconds of the last build: keys+sort+gather, cells+groups, moments,
- *                       counting walk+scans, filling walk, items+SPJ. */
+ *   tree_gpu_times      device milliseconds of the last build: keys+sort+gather, cells+moments, i-group
+ *                       compaction, counting walk+scans, filling walk, items+SPJ. */
 int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, const double *r_out,
                               const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
                               int rank, long long *sizes);

@@ -111,7 +111,7 @@ def test_force_from_gpu_lists_matches_oracle(n, group, rs_scale):
     got = F.walks_download(n)
     synth.assert_force_close(got, want, 1e-4, "GPU lists")
     launches, n_ee, n_es = F.counters()
-    assert n_ee + n_es == n_int and launches > 60
+    assert n_ee + n_es == n_int and launches >= 10
     t = tree.gpu_build_times()
     assert all(v >= 0 for v in t.values()) and sum(t.values()) > 0
     # a second pass over the resident set gives the same bits (deterministic list order)
