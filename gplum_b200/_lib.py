@@ -50,6 +50,7 @@ SYMBOLS = {
     "gplum_b200_tree_build_gpu_epj": (_i, [_i, _vp, _i, C.c_double, _i, _i, _vp]),
     "gplum_b200_tree_copy_gpu": (_i, [_vp] * 12),
     "gplum_b200_tree_gpu_times": (_i, [C.POINTER(_f)]),
+    "gplum_b200_tree_gpu_stamps": (_i, [_vp, _i]),
     "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
     "gplum_b200_soft_corr_enable": (_i, [_i, _ll]),
     "gplum_b200_correct_long_run": (_i, [_i, _vp, _i]),

@@ -78,6 +78,8 @@ struct Meta {
     int n_walk;
     int cap, n_items;
     long long n_adr_epj, n_adr_spj, n_int_epep, n_int_epsp;
+    unsigned long long stamp[96];          // globaltimer at the phase boundaries of tree_coop_kernel (block 0)
+    int n_stamp;
 };
 
 struct State {
@@ -87,6 +89,7 @@ struct State {
     Buf w_epi_off, w_ni, w_ne, w_ns, w_ed, w_sd, w_nitems, w_ioff;
     Buf item_key_a, item_key_b, item_a;
     Meta *h_meta = nullptr;                // pinned
+    Meta *h_meta_stamps = nullptr;         // = h_meta once a build has completed
     int coop_blocks = 0, cell_cap = 0, n = 0, n_walk = 0, n_cells = 0, n_levels = 0, lvl_start[N_LVL + 1] = {};
     cudaEvent_t ev[7] = {};
     bool ev_ok = false, timed = false;
@@ -264,6 +267,14 @@ __device__ __forceinline__ void chunk_of(int F, int &f0, int &f1)
 // (index clamped, accumulation predicated -- the order of the sums stays the host's), the 8 children of an
 // inner cell unconditionally (an empty child holds mass = com = quad = 0 and boxes at +-1e300: adding it is
 // exact, so skipping it like the host does and not skipping it give the same bits).
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define STAMP() do { if (b == 0 && threadIdx.x == 0 && ns < 96) meta->stamp[ns++] = gtimer(); } while (0)
+
 __device__ __forceinline__ void moment_cell(const KP &P, int c)
 {
     const int4 m = __ldcg(P.c_meta + c);
@@ -314,34 +325,39 @@ __device__ __forceinline__ void moment_cell(const KP &P, int c)
                 }
             }
         } else {
-            const double *cm0 = P.c_mom + (size_t)m.z * 10, *cb0 = P.c_box + (size_t)m.z * 12;
+            // children are 8 consecutive 80 B moment records and 8 consecutive 96 B boxes: 16 B loads
+            const double2 *cm0 = reinterpret_cast<const double2 *>(P.c_mom + (size_t)m.z * 10);
+            const double2 *cb0 = reinterpret_cast<const double2 *>(P.c_box + (size_t)m.z * 12);
 #pragma unroll
             for (int o = 0; o < 8; o++) {
-                const double *cm = cm0 + o * 10, *cb = cb0 + o * 12;
-                const double cmass = __ldcg(cm);
+                const double2 a = __ldcg(cm0 + o * 5), b2 = __ldcg(cm0 + o * 5 + 1);       // mass, cx | cy, cz
+                const double2 b0 = __ldcg(cb0 + o * 6), b1 = __ldcg(cb0 + o * 6 + 1), b2_ = __ldcg(cb0 + o * 6 + 2),
+                              b3 = __ldcg(cb0 + o * 6 + 3), b4 = __ldcg(cb0 + o * 6 + 4), b5 = __ldcg(cb0 + o * 6 + 5);
+                const double cmass = a.x;
                 mass += cmass;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    com[k] += cmass * __ldcg(cm + 1 + k);
-                    ilo[k] = fmin(ilo[k], __ldcg(cb + k)); ihi[k] = fmax(ihi[k], __ldcg(cb + 3 + k));
-                    olo[k] = fmin(olo[k], __ldcg(cb + 6 + k)); ohi[k] = fmax(ohi[k], __ldcg(cb + 9 + k));
-                }
+                com[0] += cmass * a.y; com[1] += cmass * b2.x; com[2] += cmass * b2.y;
+                ilo[0] = fmin(ilo[0], b0.x); ilo[1] = fmin(ilo[1], b0.y); ilo[2] = fmin(ilo[2], b1.x);
+                ihi[0] = fmax(ihi[0], b1.y); ihi[1] = fmax(ihi[1], b2_.x); ihi[2] = fmax(ihi[2], b2_.y);
+                olo[0] = fmin(olo[0], b3.x); olo[1] = fmin(olo[1], b3.y); olo[2] = fmin(olo[2], b4.x);
+                ohi[0] = fmax(ohi[0], b4.y); ohi[1] = fmax(ohi[1], b5.x); ohi[2] = fmax(ohi[2], b5.y);
             }
             for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
 #pragma unroll
             for (int o = 0; o < 8; o++) {
-                const double *cm = cm0 + o * 10;
-                const double mi = __ldcg(cm);
-                const double d0 = __ldcg(cm + 1) - com[0], d1 = __ldcg(cm + 2) - com[1], d2 = __ldcg(cm + 3) - com[2];
-                q[0] += mi * d0 * d0 + __ldcg(cm + 4); q[1] += mi * d1 * d1 + __ldcg(cm + 5); q[2] += mi * d2 * d2 + __ldcg(cm + 6);
-                q[3] += mi * d0 * d1 + __ldcg(cm + 7); q[4] += mi * d0 * d2 + __ldcg(cm + 8); q[5] += mi * d1 * d2 + __ldcg(cm + 9);
+                const double2 a = __ldcg(cm0 + o * 5), b2 = __ldcg(cm0 + o * 5 + 1), q01 = __ldcg(cm0 + o * 5 + 2),
+                              q23 = __ldcg(cm0 + o * 5 + 3), q45 = __ldcg(cm0 + o * 5 + 4);
+                const double mi = a.x;
+                const double d0 = a.y - com[0], d1 = b2.x - com[1], d2 = b2.y - com[2];
+                q[0] += mi * d0 * d0 + q01.x; q[1] += mi * d1 * d1 + q01.y; q[2] += mi * d2 * d2 + q23.x;
+                q[3] += mi * d0 * d1 + q23.y; q[4] += mi * d0 * d2 + q45.x; q[5] += mi * d1 * d2 + q45.y;
             }
         }
     }
-    double *om = P.c_mom + (size_t)c * 10, *ob = P.c_box + (size_t)c * 12;
-    om[0] = mass;
-    for (int k = 0; k < 3; k++) { om[1 + k] = com[k]; ob[k] = ilo[k]; ob[3 + k] = ihi[k]; ob[6 + k] = olo[k]; ob[9 + k] = ohi[k]; }
-    for (int k = 0; k < 6; k++) om[4 + k] = q[k];
+    double2 *om = reinterpret_cast<double2 *>(P.c_mom + (size_t)c * 10), *ob = reinterpret_cast<double2 *>(P.c_box + (size_t)c * 12);
+    om[0] = make_double2(mass, com[0]); om[1] = make_double2(com[1], com[2]);
+    om[2] = make_double2(q[0], q[1]); om[3] = make_double2(q[2], q[3]); om[4] = make_double2(q[4], q[5]);
+    ob[0] = make_double2(ilo[0], ilo[1]); ob[1] = make_double2(ilo[2], ihi[0]); ob[2] = make_double2(ihi[1], ihi[2]);
+    ob[3] = make_double2(olo[0], olo[1]); ob[4] = make_double2(olo[2], ohi[0]); ob[5] = make_double2(ohi[1], ohi[2]);
 }
 
 // ---- cells (top-down, one level per pair of grid barriers) and moments + boxes (bottom-up, one level per
@@ -356,7 +372,8 @@ __global__ void __launch_bounds__(TPB, 3) tree_coop_kernel(KP P, int *fr_a, int 
     const int nb = gridDim.x, b = blockIdx.x;
     Meta *meta = P.meta;
     int *fr = fr_a, *fr_next = fr_b;
-    int L = 0;
+    int L = 0, ns = 0;
+    STAMP();
     for (; L < MAX_LEVEL; L++) {
         const int F = __ldcg(&meta->fcount[L]);
         if (F == 0) break;                                   // same value in every block
@@ -380,6 +397,7 @@ __global__ void __launch_bounds__(TPB, 3) tree_coop_kernel(KP P, int *fr_a, int 
             blk_cnt[b] = s;
         }
         grid.sync();
+        STAMP();
         // phase B: my offset into the next frontier = counts of the blocks before me
         int before_me = 0, total = 0;
         for (int k = threadIdx.x; k < nb; k += TPB) { const int v = __ldcg(blk_cnt + k); total += v; if (k < b) before_me += v; }
@@ -421,15 +439,22 @@ __global__ void __launch_bounds__(TPB, 3) tree_coop_kernel(KP P, int *fr_a, int 
             running += tot;
         }
         grid.sync();
+        STAMP();
         int *t = fr; fr = fr_next; fr_next = t;
     }
     // cells exist on levels 0..L; the barrier that ended the last level also published its cells
-    const int gtid = b * TPB + threadIdx.x, gthreads = nb * TPB;
+    // warps, not threads, are dealt round-robin over the blocks: a small level still uses every SM's
+    // load pipe (uncoalesced record loads cost one L1 tag cycle per sector), and a warp's 32 cells stay
+    // consecutive (children of consecutive cells are consecutive in memory)
+    const int gthreads = nb * TPB;
+    const int gtid = (w * nb + b) * 32 + lane;
     for (int l = L; l >= 0; l--) {
         const int c0 = __ldcg(&meta->lvl_start[l]), c1 = __ldcg(&meta->lvl_start[l + 1]);
         for (int c = c0 + gtid; c < c1; c += gthreads) moment_cell(P, c);
         if (l > 0) grid.sync();
+        STAMP();
     }
+    if (b == 0 && threadIdx.x == 0) meta->n_stamp = ns;
 }
 
 // ---- per-group walk: one warp per group, depth-first in steps of 4 cells x 8 children ----
@@ -621,13 +646,22 @@ void tree_phase_ms(float ms[6])
     }
 }
 
+int tree_stamps(unsigned long long *out, int cap)
+{
+    if (!S.h_meta_stamps) return 0;
+    const Meta *m = S.h_meta_stamps;
+    int n = std::min(std::min(m->n_stamp, 96), cap);
+    for (int k = 0; k < n; k++) out[k] = m->stamp[k];
+    return n;
+}
+
 void tree_release()
 {
     for (Buf *b : {&S.keys_a, &S.keys_b, &S.idx_a, &S.idx_b, &S.cub_temp, &S.bbox_part, &S.meta, &S.blk_cnt,
                    &S.c_meta, &S.c_mom, &S.c_box, &S.fr_a, &S.fr_b, &S.grp_at, &S.walk_cell, &S.w_epi_off, &S.w_ni, &S.w_ne,
                    &S.w_ns, &S.w_ed, &S.w_sd, &S.w_nitems, &S.w_ioff, &S.item_key_a, &S.item_key_b, &S.item_a})
         b->release();
-    if (S.h_meta) { cudaFreeHost(S.h_meta); S.h_meta = nullptr; }
+    if (S.h_meta) { cudaFreeHost(S.h_meta); S.h_meta = nullptr; S.h_meta_stamps = nullptr; }
     if (S.ev_ok) { for (auto &e : S.ev) cudaEventDestroy(e); S.ev_ok = false; }
     S.timed = false; S.cell_cap = 0; S.n = 0; S.coop_blocks = 0;
 }
@@ -762,6 +796,7 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
     CK(cudaMemcpyAsync(S.h_meta, S.meta.p, sizeof(Meta), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(S.ev[4], st));
     CK(cudaStreamSynchronize(st));
+    S.h_meta_stamps = S.h_meta;
     counts->n_cells = S.n_cells; counts->n_walk = nw; counts->n_levels = S.n_levels;
     counts->overflow = S.h_meta->overflow;
     counts->n_items = nw > 0 ? S.h_meta->n_items : 0; counts->cap = nw > 0 ? S.h_meta->cap : 0;

@@ -48,6 +48,8 @@ const int *tree_walk_ni();                       // device pointer, n_walk entri
 // cooperative kernel), [2] i-group compaction + first host sync, [3] counting walk + scans + second sync,
 // [4] filling walk, [5] items + SPJ
 void tree_phase_ms(float ms[6]);
+// globaltimer (ns) at the level boundaries inside the cooperative cells+moments kernel of the last build
+int tree_stamps(unsigned long long *out, int cap);
 void tree_release();
 
 }  // namespace gbt

@@ -1102,6 +1102,12 @@ int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, lon
     return 0;
 }
 
+int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap)
+{
+    if (!ns_out || cap <= 0 || !g.ready || !g.tree_built) return 0;
+    return gbt::tree_stamps(ns_out, cap);
+}
+
 int gplum_b200_tree_gpu_times(float *ms6)
 {
     if (!ms6) return fail(GPLUM_B200_ERR_ARG, "tree_gpu_times: NULL");

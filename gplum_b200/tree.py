@@ -87,3 +87,10 @@ def gpu_build_times():
     ms = (C.c_float * 6)()
     check(lib().gplum_b200_tree_gpu_times(ms))
     return dict(zip(("sort_gather", "cells_moments", "groups_sync", "count_walk", "fill_walk", "items_spj"), [float(x) for x in ms]))
+
+
+def gpu_build_stamps():
+    """Microseconds between the level boundaries inside the cooperative cells+moments kernel."""
+    a = np.zeros(96, dtype=np.uint64)
+    n = lib().gplum_b200_tree_gpu_stamps(_p(a), 96)
+    return (np.diff(a[:n].astype(np.int64)) / 1e3).round(1).tolist()

@@ -220,6 +220,9 @@ int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, lon
                              int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
                              int *sorted_to_original);
 int gplum_b200_tree_gpu_times(float *ms6);
+/* diagnostics: %globaltimer (ns) at the level boundaries inside the cells+moments kernel of the last build;
+ * returns the number of stamps written (<= cap) */
+int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap);
 
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */
