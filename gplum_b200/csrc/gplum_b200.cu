@@ -88,6 +88,10 @@ struct WalkSet {
     std::vector<long long> epi_off_host;
     bool pending = false;
     cudaEvent_t done = nullptr;                  // recorded after the D2H of a dispatch: retrieve(tag) waits on it only
+    // dispatch() pipeline: the walks of one dispatch are cut into sub-batches; sub-batch b's lists go up on the
+    // copy-in stream while b-1 computes and b-2's forces come down on the copy-out stream
+    std::vector<int> sub_w0;                     // first walk of each sub-batch (+ n_walk at the end)
+    std::vector<cudaEvent_t> ev_in, ev_k, ev_out;
     // changeover correction (soft_corr.cu): candidate capture of the last pass + work/result buffers
     DevBuf self_adr, pairs, corr_meta, cnt, off, cursor, csr, corr_out, corr_init, ngb, scan_temp;
     unsigned int pair_cap = 0;
@@ -95,6 +99,7 @@ struct WalkSet {
     void release()
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
+        for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
         for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force,
                           &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp})
             b->release();
@@ -129,6 +134,8 @@ struct Ctx {
     bool ready = false;
     int device = -1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // dispatch()/retrieve() pipeline: H2D and D2H engines
+    cudaEvent_t ev_compute = nullptr, ev_j[8] = {};        // compute-stream marker; j-set upload chunks
     float eps2 = 0.0f;
     int quad = 1, flags = 0;
     JSet jset;
@@ -158,7 +165,7 @@ int ensure_init()
 }
 
 // ---- work list: split every walk into i-tiles, choose a tile shape, longest first (items.h) ----
-void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items)
+void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items, int walk_base = 0)
 {
     items.clear();
     std::vector<std::pair<double, WorkItem>> tmp;
@@ -186,12 +193,15 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
     items.reserve(tmp.size());
-    for (auto &t : tmp) items.push_back(t.second);
+    for (auto &t : tmp) { t.second.walk += walk_base; items.push_back(t.second); }
 }
 
-int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
+// Launches the force kernel on items [item0, item0 + n_items) of the set (default: all).  `first` resets the
+// candidate capture and counts the pass's interactions; sub-batch launches of one pass pass first = false.
+int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_items = -1, bool first = true)
 {
-    if (ws.n_items == 0) return 0;
+    if (n_items < 0) n_items = ws.n_items;
+    if (n_items == 0) return 0;
     PassParams p;
     p.epi = (const EpiAos *)ws.epi.p;
     p.epi_off = (const int *)ws.epi_off.p;
@@ -201,31 +211,33 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2)
     p.peer_epj = g.peer.on ? (const EpjPacked *const *)g.peer.table[g.peer.parity].p : nullptr;
     p.peer_shift = g.peer.shift;
     p.force = (ForceAos *)ws.force.p;
-    p.items = (const WorkItem *)ws.items.p;
+    p.items = (const WorkItem *)ws.items.p + item0;
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
-    ws.captured = false; ws.corrected = false;
+    if (first) { ws.captured = false; ws.corrected = false; }
     if (g.corr_on) {
-        const long long cap = g.corr_cap > 0 ? g.corr_cap : 4 * ws.n_epi + (1 << 20);
-        if (cap > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "pair capacity %lld exceeds 2^31", cap);
-        if (int r = ws.self_adr.reserve((size_t)ws.n_epi * 4)) return r;
-        if (int r = ws.pairs.reserve((size_t)cap * sizeof(int2))) return r;
-        if (int r = ws.corr_meta.reserve(16)) return r;
-        ws.pair_cap = (unsigned int)cap;
-        CU(cudaMemsetAsync(ws.self_adr.p, 0xff, (size_t)ws.n_epi * 4, st));
-        CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
+        if (first) {
+            const long long cap = g.corr_cap > 0 ? g.corr_cap : 4 * ws.n_epi + (1 << 20);
+            if (cap > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "pair capacity %lld exceeds 2^31", cap);
+            if (int r = ws.self_adr.reserve((size_t)ws.n_epi * 4)) return r;
+            if (int r = ws.pairs.reserve((size_t)cap * sizeof(int2))) return r;
+            if (int r = ws.corr_meta.reserve(16)) return r;
+            ws.pair_cap = (unsigned int)cap;
+            CU(cudaMemsetAsync(ws.self_adr.p, 0xff, (size_t)ws.n_epi * 4, st));
+            CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
+        }
         p.self_adr = (int *)ws.self_adr.p;
         p.pairs = (int2 *)ws.pairs.p;
         p.pair_count = (unsigned int *)ws.corr_meta.p;
         p.pair_cap = ws.pair_cap;
         ws.captured = true;
     }
-    if (g.rmax <= 2) force_pass_kernel<2><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
-    else force_pass_kernel<4><<<(ws.n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, ws.n_items);
+    if (g.rmax <= 2) force_pass_kernel<2><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
+    else force_pass_kernel<4><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
     CU(cudaGetLastError());
     g.launches++;
-    g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp;
+    if (first) { g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp; }
     return 0;
 }
 
@@ -469,6 +481,10 @@ int gplum_b200_finalize(void)
     g.tree_built = false;
     for (auto &s : g.slots) s.release();
     if (g.own_stream) cudaStreamDestroy(g.own_stream);
+    if (g.copy_in) { cudaStreamDestroy(g.copy_in); g.copy_in = nullptr; }
+    if (g.copy_out) { cudaStreamDestroy(g.copy_out); g.copy_out = nullptr; }
+    if (g.ev_compute) { cudaEventDestroy(g.ev_compute); g.ev_compute = nullptr; }
+    for (auto &e : g.ev_j) if (e) { cudaEventDestroy(e); e = nullptr; }
     g.own_stream = g.stream = nullptr;
     g.ready = false;
     g.device = -1;
@@ -502,6 +518,8 @@ int gplum_b200_synchronize(void)
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
     CU(cudaStreamSynchronize(g.stream));
+    if (g.copy_in) CU(cudaStreamSynchronize(g.copy_in));
+    if (g.copy_out) CU(cudaStreamSynchronize(g.copy_out));
     return 0;
 }
 
@@ -566,6 +584,68 @@ int gplum_b200_calc_walks(int n_walk, const void *epi_all, const int *epi_off, c
 }
 
 // ---- FDPS multi-walk-index form ----
+// dispatch()/retrieve() run as a three-stage pipeline over PCIe: j-particles and walk sub-batches go up on a
+// copy-in stream, each sub-batch's force kernel runs on the compute stream as soon as its lists have landed,
+// its forces come down on a copy-out stream, and retrieve() hands sub-batches back as they arrive.
+namespace {
+int ensure_pipe()
+{
+    if (!g.copy_in) CU(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
+    if (!g.copy_out) CU(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
+    if (!g.ev_compute) CU(cudaEventCreateWithFlags(&g.ev_compute, cudaEventDisableTiming));
+    for (auto &e : g.ev_j) if (!e) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
+// "send all": upload the j-particles in chunks on the copy-in stream; each chunk is packed on the compute
+// stream as soon as it has landed.
+int send_all_pipelined(const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_all)
+{
+    if (int r = ensure_pipe()) return r;
+    JSet &j = g.jset;
+    cudaStream_t st = g.stream, ci = g.copy_in;
+    const size_t ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
+    j.ext_epj = j.ext_spj = nullptr;
+    j.n_epj = n_epj_all; j.n_spj = n_spj_all;
+    if (int r = j.epj_aos.reserve((size_t)n_epj_all * sizeof(EpjAos))) return r;
+    if (int r = j.epj_packed.reserve((size_t)n_epj_all * sizeof(EpjPacked))) return r;
+    if (int r = j.spj_aos.reserve((size_t)n_spj_all * ssz)) return r;
+    if (int r = j.spj_packed.reserve((size_t)n_spj_all * sizeof(SpjPacked))) return r;
+    // the j arrays may still be read by kernels already queued on the compute stream
+    CU(cudaEventRecord(g.ev_compute, st));
+    CU(cudaStreamWaitEvent(ci, g.ev_compute, 0));
+    constexpr int NCH = 4;                       // chunks per array: g.ev_j[0..3] EP, [4..7] SP
+    const int trace = (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0;
+    for (int c = 0; c < NCH; c++) {
+        // chunk boundaries on multiples of the pack kernels' block (256 records)
+        const long long per = ((long long)(n_epj_all + NCH - 1) / NCH + PACK_BLOCK - 1) / PACK_BLOCK * PACK_BLOCK;
+        const long long i0 = std::min<long long>(n_epj_all, c * per), i1 = std::min<long long>(n_epj_all, i0 + per);
+        if (i1 <= i0) continue;
+        CU(cudaMemcpyAsync((EpjAos *)j.epj_aos.p + i0, (const EpjAos *)epj_all + i0, (size_t)(i1 - i0) * sizeof(EpjAos), cudaMemcpyHostToDevice, ci));
+        CU(cudaEventRecord(g.ev_j[c], ci));
+        CU(cudaStreamWaitEvent(st, g.ev_j[c], 0));
+        const int n = (int)(i1 - i0);
+        pack_epj_kernel<<<(n + PACK_BLOCK - 1) / PACK_BLOCK, PACK_BLOCK, 0, st>>>((const EpjAos *)j.epj_aos.p + i0, n, (EpjPacked *)j.epj_packed.p + i0);
+        CU(cudaGetLastError());
+        g.launches++;
+    }
+    for (int c = 0; c < NCH; c++) {
+        const long long per = ((long long)(n_spj_all + NCH - 1) / NCH + PACK_BLOCK - 1) / PACK_BLOCK * PACK_BLOCK;
+        const long long i0 = std::min<long long>(n_spj_all, c * per), i1 = std::min<long long>(n_spj_all, i0 + per);
+        if (i1 <= i0) continue;
+        CU(cudaMemcpyAsync((char *)j.spj_aos.p + i0 * ssz, (const char *)spj_all + i0 * ssz, (size_t)(i1 - i0) * ssz, cudaMemcpyHostToDevice, ci));
+        CU(cudaEventRecord(g.ev_j[4 + c], ci));
+        CU(cudaStreamWaitEvent(st, g.ev_j[4 + c], 0));
+        const int n = (int)(i1 - i0);
+        pack_spj_kernel<<<(n + PACK_BLOCK - 1) / PACK_BLOCK, PACK_BLOCK, 0, st>>>((const char *)j.spj_aos.p + i0 * ssz, n, (SpjPacked *)j.spj_packed.p + i0,
+                                                                                  g.quad, trace, g.eps2);
+        CU(cudaGetLastError());
+        g.launches++;
+    }
+    return 0;
+}
+}  // namespace
+
 int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *ni,
                         const int *const *adr_epj, const int *n_epj,
                         const int *const *adr_spj, const int *n_spj,
@@ -574,28 +654,33 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
 {
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
-    cudaStream_t st = g.stream;
-    if (send_all) {
-        if (int r = upload_j(epj_all, n_epj_all, spj_all, n_spj_all, st)) return r;
-        return pack_j(st, g.eps2);
-    }
+    if (send_all) return send_all_pipelined(epj_all, n_epj_all, spj_all, n_spj_all);
+    if (int r = ensure_pipe()) return r;
+    cudaStream_t st = g.stream, ci = g.copy_in, co = g.copy_out;
     if (tag < 0 || tag >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "tag %d out of range [0,%d)", tag, N_TAG);
     if (n_walk < 0) return fail(GPLUM_B200_ERR_ARG, "n_walk < 0");
     WalkSet &ws = g.slots[tag];
     if (ws.pending) return fail(GPLUM_B200_ERR_STATE, "dispatch(tag=%d) while a previous dispatch is not retrieved", tag);
     // flatten the per-walk pointers into one pinned staging block
-    long long n_epi = 0, n_ae = 0, n_as = 0;
-    for (int w = 0; w < n_walk; w++) { n_epi += ni[w]; n_ae += n_epj[w]; n_as += n_spj[w]; }
-    const size_t b_epi = (size_t)n_epi * sizeof(EpiAos), b_ae = (size_t)n_ae * 4, b_as = (size_t)n_as * 4;
+    long long n_epi = 0, n_ae = 0, n_as = 0, i_ee = 0, i_es = 0, n_it_max = 0;
+    for (int w = 0; w < n_walk; w++) {
+        if (ni[w] < 0 || n_epj[w] < 0 || n_spj[w] < 0) return fail(GPLUM_B200_ERR_ARG, "negative count in walk %d", w);
+        n_epi += ni[w]; n_ae += n_epj[w]; n_as += n_spj[w];
+        i_ee += (long long)ni[w] * n_epj[w]; i_es += (long long)ni[w] * n_spj[w];
+        n_it_max += (ni[w] + 3) / 4 + 1;          // smallest tile holds 4 i-particles
+    }
+    const size_t b_epi = ((size_t)n_epi * sizeof(EpiAos) + 15) & ~(size_t)15, b_ae = (size_t)n_ae * 4, b_as = (size_t)n_as * 4;
     const size_t b_meta = (size_t)n_walk * (4 * 3 + 8 * 2);
-    if (int r = ws.h_stage.reserve(b_epi + b_ae + b_as + b_meta + 64)) return r;
+    const size_t b_lists = (b_meta + b_ae + b_as + 15) & ~(size_t)15;
+    if (int r = ws.h_stage.reserve(b_epi + b_lists + (size_t)n_it_max * sizeof(WorkItem) + 64)) return r;
     unsigned char *h = (unsigned char *)ws.h_stage.p;
     EpiAos *h_epi = (EpiAos *)h;
-    long long *h_edisp = (long long *)(h + ((b_epi + 15) & ~(size_t)15));
+    long long *h_edisp = (long long *)(h + b_epi);
     long long *h_sdisp = h_edisp + n_walk;
     int *h_off = (int *)(h_sdisp + n_walk);
     int *h_ne = h_off + n_walk, *h_ns = h_ne + n_walk;
     int *h_ae = h_ns + n_walk, *h_as = h_ae + n_ae;
+    WorkItem *h_items = (WorkItem *)(h + b_epi + b_lists);
     ws.ni_host.assign(ni, ni + n_walk);
     ws.epi_off_host.resize(n_walk);
     long long oi = 0, oe = 0, os = 0;
@@ -604,17 +689,80 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         ws.epi_off_host[w] = oi;
         oi += ni[w]; oe += n_epj[w]; os += n_spj[w];
     }
-#pragma omp parallel for schedule(static)
-    for (int w = 0; w < n_walk; w++) {
-        memcpy(h_epi + h_off[w], epi[w], (size_t)ni[w] * sizeof(EpiAos));
-        memcpy(h_ae + h_edisp[w], adr_epj[w], (size_t)n_epj[w] * 4);
-        memcpy(h_as + h_sdisp[w], adr_spj[w], (size_t)n_spj[w] * 4);
+    ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
+    ws.n_int_epep = i_ee; ws.n_int_epsp = i_es; ws.n_items = 0;
+    g.tree_built = false;
+    if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
+    if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
+    if (int r = ws.epi_off.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.n_epj.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.n_spj.reserve((size_t)n_walk * 4)) return r;
+    if (int r = ws.epj_disp.reserve((size_t)n_walk * 8)) return r;
+    if (int r = ws.spj_disp.reserve((size_t)n_walk * 8)) return r;
+    if (int r = ws.adr_epj.reserve((size_t)n_ae * 4)) return r;
+    if (int r = ws.adr_spj.reserve((size_t)n_as * 4)) return r;
+    if (int r = ws.items.reserve((size_t)n_it_max * sizeof(WorkItem))) return r;
+    if (int r = ws.h_force.reserve((size_t)std::max<long long>(n_epi, 1) * sizeof(ForceAos))) return r;
+    // sub-batches of about equal PCIe volume; small dispatches stay whole
+    const size_t bytes = (size_t)n_epi * (sizeof(EpiAos) + sizeof(ForceAos)) + b_ae + b_as;
+    const int n_sub = n_walk == 0 ? 0 : (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, bytes / (8u << 20), (size_t)n_walk}));
+    ws.sub_w0.assign(1, 0);
+    {
+        size_t acc = 0; int b = 1;
+        for (int w = 0; w < n_walk && b < n_sub; w++) {
+            acc += (size_t)ni[w] * (sizeof(EpiAos) + sizeof(ForceAos)) + 4 * ((size_t)n_epj[w] + n_spj[w]);
+            if (acc * n_sub >= bytes * b) { ws.sub_w0.push_back(w + 1); b++; }
+        }
+        if (n_walk > 0) { if (ws.sub_w0.back() != n_walk) ws.sub_w0.push_back(n_walk); }
     }
-    if (int r = upload_walks(ws, n_walk, h_epi, h_off, ws.ni_host.data(), h_ae, h_edisp, h_ne, h_as, h_sdisp, h_ns, st)) return r;
-    if (int r = launch_pass(ws, st, g.eps2)) return r;
-    if (int r = ws.h_force.reserve((size_t)std::max<long long>(ws.n_epi, 1) * sizeof(ForceAos))) return r;
-    if (ws.n_epi) CU(cudaMemcpyAsync(ws.h_force.p, ws.force.p, (size_t)ws.n_epi * sizeof(ForceAos), cudaMemcpyDeviceToHost, st));
+    const int nsb = (int)ws.sub_w0.size() - 1;
+    for (auto *v : {&ws.ev_in, &ws.ev_k, &ws.ev_out})
+        while ((int)v->size() < nsb) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); v->push_back(e); }
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+    // buffers of this tag may still be read by a kernel queued earlier on the compute stream (flat / resident forms)
+    CU(cudaEventRecord(g.ev_compute, st));
+    CU(cudaStreamWaitEvent(ci, g.ev_compute, 0));
+    if (n_walk > 0) {
+        CU(cudaMemcpyAsync(ws.epi_off.p, h_off, (size_t)n_walk * 4, H2D, ci));
+        CU(cudaMemcpyAsync(ws.n_epj.p, h_ne, (size_t)n_walk * 4, H2D, ci));
+        CU(cudaMemcpyAsync(ws.n_spj.p, h_ns, (size_t)n_walk * 4, H2D, ci));
+        CU(cudaMemcpyAsync(ws.epj_disp.p, h_edisp, (size_t)n_walk * 8, H2D, ci));
+        CU(cudaMemcpyAsync(ws.spj_disp.p, h_sdisp, (size_t)n_walk * 8, H2D, ci));
+    }
+    std::vector<WorkItem> items;
+    int item0 = 0;
+    for (int b = 0; b < nsb; b++) {
+        const int w0 = ws.sub_w0[b], w1 = ws.sub_w0[b + 1];
+#pragma omp parallel for schedule(static)
+        for (int w = w0; w < w1; w++) {
+            memcpy(h_epi + h_off[w], epi[w], (size_t)ni[w] * sizeof(EpiAos));
+            memcpy(h_ae + h_edisp[w], adr_epj[w], (size_t)n_epj[w] * 4);
+            memcpy(h_as + h_sdisp[w], adr_spj[w], (size_t)n_spj[w] * 4);
+        }
+        build_items(w1 - w0, ni + w0, n_epj + w0, n_spj + w0, items, w0);
+        const int n_it = (int)items.size();
+        if (item0 + n_it > n_it_max) return fail(GPLUM_B200_ERR_STATE, "work-item estimate too small");
+        if (n_it) memcpy(h_items + item0, items.data(), (size_t)n_it * sizeof(WorkItem));
+        const long long e0 = h_off[w0], e1 = (w1 < n_walk) ? h_off[w1] : n_epi;
+        const long long a0 = h_edisp[w0], a1 = (w1 < n_walk) ? h_edisp[w1] : n_ae;
+        const long long s0 = h_sdisp[w0], s1 = (w1 < n_walk) ? h_sdisp[w1] : n_as;
+        if (e1 > e0) CU(cudaMemcpyAsync((EpiAos *)ws.epi.p + e0, h_epi + e0, (size_t)(e1 - e0) * sizeof(EpiAos), H2D, ci));
+        if (a1 > a0) CU(cudaMemcpyAsync((int *)ws.adr_epj.p + a0, h_ae + a0, (size_t)(a1 - a0) * 4, H2D, ci));
+        if (s1 > s0) CU(cudaMemcpyAsync((int *)ws.adr_spj.p + s0, h_as + s0, (size_t)(s1 - s0) * 4, H2D, ci));
+        if (n_it) CU(cudaMemcpyAsync((WorkItem *)ws.items.p + item0, h_items + item0, (size_t)n_it * sizeof(WorkItem), H2D, ci));
+        CU(cudaEventRecord(ws.ev_in[b], ci));
+        CU(cudaStreamWaitEvent(st, ws.ev_in[b], 0));
+        ws.n_items = item0 + n_it;
+        if (int r = launch_pass(ws, st, g.eps2, item0, n_it, b == 0)) return r;
+        CU(cudaEventRecord(ws.ev_k[b], st));
+        CU(cudaStreamWaitEvent(co, ws.ev_k[b], 0));
+        if (e1 > e0) CU(cudaMemcpyAsync((ForceAos *)ws.h_force.p + e0, (const ForceAos *)ws.force.p + e0, (size_t)(e1 - e0) * sizeof(ForceAos), cudaMemcpyDeviceToHost, co));
+        CU(cudaEventRecord(ws.ev_out[b], co));
+        item0 += n_it;
+    }
     if (!ws.done) CU(cudaEventCreateWithFlags(&ws.done, cudaEventDisableTiming));
+    // `done` on the compute stream as well: work queued there after this dispatch orders behind its D2H
+    if (nsb > 0) CU(cudaStreamWaitEvent(st, ws.ev_out[nsb - 1], 0));
     CU(cudaEventRecord(ws.done, st));
     ws.pending = true;
     return 0;
@@ -628,15 +776,20 @@ int gplum_b200_retrieve(int tag, int n_walk, const int *ni, void *const *force)
     if (!ws.pending) return fail(GPLUM_B200_ERR_STATE, "retrieve(tag=%d) without dispatch", tag);
     if (n_walk != ws.n_walk) return fail(GPLUM_B200_ERR_ARG, "retrieve n_walk %d != dispatched %d", n_walk, ws.n_walk);
     CU(cudaSetDevice(g.device));
-    CU(cudaEventSynchronize(ws.done));      // later dispatches (other tags) keep running
-    ws.pending = false;
     const bool overwrite = (g.flags & GPLUM_B200_NO_ACCUMULATE) != 0;
     const ForceAos *src = (const ForceAos *)ws.h_force.p;
+    const int nsb = (int)ws.sub_w0.size() - 1;
+    for (int b = 0; b < nsb; b++) {
+        CU(cudaEventSynchronize(ws.ev_out[b]));      // later sub-batches and other tags keep running
+        const int w0 = ws.sub_w0[b], w1 = ws.sub_w0[b + 1];
 #pragma omp parallel for schedule(static)
-    for (int w = 0; w < n_walk; w++) {
-        if (ni[w] != ws.ni_host[w]) continue;
-        accumulate_force((ForceAos *)force[w], src + ws.epi_off_host[w], ni[w], overwrite);
+        for (int w = w0; w < w1; w++) {
+            if (ni[w] != ws.ni_host[w]) continue;
+            accumulate_force((ForceAos *)force[w], src + ws.epi_off_host[w], ni[w], overwrite);
+        }
     }
+    CU(cudaEventSynchronize(ws.done));
+    ws.pending = false;
     for (int w = 0; w < n_walk; w++)
         if (ni[w] != ws.ni_host[w]) return fail(GPLUM_B200_ERR_ARG, "retrieve ni[%d]=%d != dispatched %d", w, ni[w], ws.ni_host[w]);
     return 0;
