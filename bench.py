@@ -33,6 +33,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: keep NCCL's banner / debug output off it (must be set before NCCL initialises)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOP_EPEP, FLOP_EPSP = 30.0, 59.0
 METRIC = "soft-force interactions/s (EP-EP+EP-SP), N=1e6 disk"
@@ -254,9 +258,6 @@ def main():
     import ctypes as C
 
     torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: one JSON line only
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w, t_build = make_workload(args.n, args.group)

@@ -37,6 +37,7 @@ SYMBOLS = {
     "gplum_b200_peer_setup": (_i, [_i, _i, _i, _vp]),
     "gplum_b200_peer_open": (_i, [_vp]),
     "gplum_b200_peer_pack": (_i, [_vp, _i]),
+    "gplum_b200_peer_wait": (_i, []),
     "gplum_b200_peer_close": (_i, []),
     "gplum_b200_peer_free": (_i, []),
     "gplum_b200_packed_sizes": (None, [C.POINTER(_i), C.POINTER(_i)]),

@@ -125,6 +125,7 @@ constexpr int MAX_PEERS = 16;
 struct Peer {
     bool on = false;
     int world = 0, rank = 0, shift = 0, parity = 0;
+    int epoch = 0;                                      // packs so far; flags[q] of every rank reach it once q has packed
     void *slab[2] = {nullptr, nullptr};               // this rank's own slabs (cudaMalloc)
     void *mapped[2][MAX_PEERS] = {};                    // every rank's slabs in this process' address space
     DevBuf table[2];                                    // device copies of mapped[b][0..world)
@@ -342,6 +343,33 @@ struct CallSlot {
     ~CallSlot() {}
 };
 thread_local CallSlot t_slot;
+
+// ---- peer-mode barrier without a collective: every rank owns a small flag array behind its first slab;
+// after packing epoch e a rank stores e into ITS entry of EVERY rank's array (over NVLink for the others),
+// and a rank's boundary walks start once all entries of its own array have reached e ----
+__global__ void peer_signal_kernel(void *const *slab0_of, size_t flag_off, int rank, int world, int epoch)
+{
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    int *f = reinterpret_cast<int *>(static_cast<char *>(slab0_of[q]) + flag_off) + rank;
+    // the pack kernel before this one (same stream) has completed: its records are in this GPU's L2/HBM
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+}
+__global__ void peer_wait_kernel(const int *flags, int world, int epoch)
+{
+    const int q = threadIdx.x;
+    if (q >= world) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+        if (v - epoch >= 0) break;
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t - t0 > 10000000000ull) __trap();           // 10 s: a peer died; fail loudly instead of hanging
+    }
+}
 
 __global__ void iota_kernel(int *p, int n)
 {
@@ -909,9 +937,12 @@ int gplum_b200_peer_setup(int world, int rank, int shift, void *handles_out)
     Peer &pe = g.peer;
     if (pe.slab[0]) return fail(GPLUM_B200_ERR_STATE, "peer mode already set up");
     pe.world = world; pe.rank = rank; pe.shift = shift; pe.parity = 0;
+    pe.epoch = 0;
     for (int b = 0; b < 2; b++) {
-        CU(cudaMalloc(&pe.slab[b], ((size_t)1 << shift) * sizeof(EpjPacked)));
-        CU(cudaMemset(pe.slab[b], 0, ((size_t)1 << shift) * sizeof(EpjPacked)));
+        // slab 0 carries this rank's flag array (MAX_PEERS ints) behind the records
+        const size_t bytes = ((size_t)1 << shift) * sizeof(EpjPacked) + (b == 0 ? 256 : 0);
+        CU(cudaMalloc(&pe.slab[b], bytes));
+        CU(cudaMemset(pe.slab[b], 0, bytes));
         CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handles_out + b, pe.slab[b]));
     }
     CU(cudaDeviceSynchronize());
@@ -950,6 +981,23 @@ int gplum_b200_peer_pack(const void *epj_aos_dev, int n)
         CU(cudaGetLastError());
         g.launches++;
     }
+    pe.epoch++;
+    peer_signal_kernel<<<1, 32, 0, g.stream>>>((void *const *)pe.table[0].p, ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_peer_wait(void)
+{
+    if (int r = ensure_init()) return r;
+    Peer &pe = g.peer;
+    if (!pe.on) return fail(GPLUM_B200_ERR_STATE, "peer_wait without peer_open");
+    CU(cudaSetDevice(g.device));
+    const int *flags = reinterpret_cast<const int *>(static_cast<const char *>(pe.slab[0]) + ((size_t)1 << pe.shift) * sizeof(EpjPacked));
+    peer_wait_kernel<<<1, 32, 0, g.stream>>>(flags, pe.world, pe.epoch);
+    CU(cudaGetLastError());
+    g.launches++;
     return 0;
 }
 

@@ -16,14 +16,25 @@ from ._lib import check, lib
 from .shard import HaloShard, Shard
 
 
+class _PeerFlags:
+    """What exchange() returns in peer mode: wait() enqueues the flag-wait kernel on the library stream."""
+
+    def __init__(self, L):
+        self.L = L
+
+    def wait(self):
+        check(self.L.gplum_b200_peer_wait())
+
+
 class MultiGpuPass:
     """`exchange` =
-    "peer"      no data moves ahead of time: every rank packs into its own slab, the slabs are
-                mapped into every process with CUDA IPC and boundary walks gather the records they
-                need straight from the owner's HBM over NVLink, tile by tile, inside the force
-                kernel; the only collective is one tiny all-reduce per step that orders "all slabs
-                packed" before "boundary walks start" (slabs are double-buffered, so one barrier
-                per step also covers the write-after-read hazard);
+    "peer"      no data moves ahead of time and no collective runs per step: every rank packs into
+                its own slab, the slabs are mapped into every process with CUDA IPC and boundary
+                walks gather the records they need straight from the owner's HBM over NVLink, tile
+                by tile, inside the force kernel.  "All slabs packed" is signalled through flag
+                words the ranks store into each other's memory over NVLink after packing; a
+                one-warp kernel on the boundary stream waits for them (slabs are double-buffered,
+                so this one barrier per step also covers the write-after-read hazard);
     "halo"      one all-to-all of only the records other ranks' boundary walks read;
     "allgather" in-place all-gather of every rank's packed slab."""
 
@@ -70,8 +81,7 @@ class MultiGpuPass:
             dist.all_gather_into_tensor(every, mine)
             self._handles = every.cpu().numpy().tobytes()
             check(L.gplum_b200_peer_open(self._handles))
-            self.flag = torch.zeros(1, dtype=torch.int32, device="cuda")
-            self.exchange_bytes = 4
+            self.exchange_bytes = 4 * world
             dist.barrier()
         else:
             # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
@@ -91,8 +101,8 @@ class MultiGpuPass:
         """Pack own EPJ, start the NCCL exchange; returns the async work handle."""
         L, vp = self.L, (lambda t: C.c_void_p(t.data_ptr()))
         if self.exchange_kind == "peer":
-            check(L.gplum_b200_peer_pack(vp(self.d_epj_raw), len(self.lw.epj_all)))
-            return dist.all_reduce(self.flag, async_op=True)       # barrier: every slab is packed
+            check(L.gplum_b200_peer_pack(vp(self.d_epj_raw), len(self.lw.epj_all)))    # pack + signal the peers
+            return _PeerFlags(L)
         check(L.gplum_b200_pack_epj_dev(vp(self.d_epj_raw), len(self.lw.epj_all), vp(self.my_slab)))
         if self.exchange_kind == "halo":
             check(L.gplum_b200_gather_epj_packed_dev(vp(self.my_slab), vp(self.d_send_idx), len(self.sh.send_idx),
@@ -117,11 +127,11 @@ class MultiGpuPass:
         if trace is not None:
             ev["int_end"].record(stream)
         with torch.cuda.stream(side):
-            work.wait()                    # the side stream waits for NCCL ...
-            side.wait_event(self.ev_pack)  # ... and for the packed SPJ
+            side.wait_event(self.ev_pack)  # the side stream waits for the packed SPJ ...
+            self._use(side)
+            work.wait()                    # ... and for the exchange (NCCL work, or the peers' flags)
             if trace is not None:
                 ev["side_ready"].record(side)
-            self._use(side)
             F.walks_select(1)
             F.walks_run(repack=False)      # boundary walks read the other ranks' particles
             self.ev_side.record(side)

@@ -128,14 +128,21 @@ void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes);
  * Every rank owns two slabs (double buffer) of 2^shift packed records; EP list indices are
  * (owner_rank << shift) | index_in_owner_slab.  peer_setup allocates the slabs and writes this
  * rank's two CUDA IPC handles (2 x 64 bytes) to handles_out; the caller all-gathers the handles
- * (rank-major) and passes them to peer_open.  peer_pack flips the buffer and packs n AoS records
- * (device pointer) into this rank's slab on the library stream; the caller then runs ONE barrier
- * collective per step before launching walks that read other ranks' slabs.  Replaces the EPJ part
- * of FDPS's LET exchange (FDPS/src/tree_for_force_impl_exlet.hpp:343-403) without moving data
- * ahead of time.  peer_close unmaps, peer_free (after a barrier) releases the slabs. */
+ * (rank-major) and passes them to peer_open.  peer_pack flips the buffer, packs n AoS records
+ * (device pointer) into this rank's slab on the library stream and then stores the new epoch into
+ * this rank's entry of EVERY rank's flag array (kept behind slab 0; remote ones over NVLink).
+ * peer_wait enqueues, on the library stream, a one-warp kernel that spins until every rank's entry
+ * of the local flag array has reached the epoch of the last peer_pack: walks launched after it may
+ * read the other ranks' slabs.  No collective library call is on the path.  Because a rank only
+ * packs epoch e+1 after its own walks of epoch e, having seen all flags at e+1 also means every
+ * peer is done reading this rank's slab of epoch e -- the double buffer needs no second barrier.
+ * Every rank must call peer_pack the same number of times.  Replaces the EPJ part of FDPS's LET
+ * exchange (FDPS/src/tree_for_force_impl_exlet.hpp:343-403) without moving data ahead of time.
+ * peer_close unmaps, peer_free (after a barrier) releases the slabs. */
 int gplum_b200_peer_setup(int world, int rank, int shift, void *handles_out);
 int gplum_b200_peer_open(const void *all_handles);
 int gplum_b200_peer_pack(const void *epj_aos_dev, int n);
+int gplum_b200_peer_wait(void);
 int gplum_b200_peer_close(void);
 int gplum_b200_peer_free(void);
 

@@ -1,8 +1,7 @@
 #!/bin/bash
-# 8-GPU box: strong-scaling bench at N=8 and N=4 (peer exchange), N=8 halo for comparison
+# 8-GPU box: strong-scaling bench at N=8 and N=4 (peer exchange)
 mkdir -p gpurun_out
 for n in 8 4; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/bench_n${n}_peer.json 2> gpurun_out/bench_n${n}_peer.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 20 --warmup 3 > gpurun_out/bench_n${n}_peer.json 2> gpurun_out/bench_n${n}_peer.err
 done
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 20 --warmup 3 --exchange halo > gpurun_out/bench_n8_halo.json 2> gpurun_out/bench_n8_halo.err
-for f in n8_peer n4_peer n8_halo; do tail -c 300 gpurun_out/bench_$f.err; cut -c1-300 gpurun_out/bench_$f.json; echo; done
+for f in n8_peer n4_peer; do tail -c 300 gpurun_out/bench_$f.err; cut -c1-300 gpurun_out/bench_$f.json; echo; done
