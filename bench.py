@@ -54,6 +54,7 @@ def make_workload(n, group, seed=0, a_in=0.9, a_out=1.1):
     w.epj_all["id"] = order
     t_build = time.time() - t0
     w.raw = {"pos": d["pos"], "mass": d["mass"], "r_out": r_out, "r_search": r_search}     # the particles themselves
+    w.raw_vel = d["vel"]
     t0 = time.time()
     tree.build_walks(d["pos"], d["mass"], r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=group)
     w.t_host_lists = time.time() - t0            # host builder alone (all host threads), lists copied out
@@ -223,6 +224,64 @@ def soft_step_leg(args, w, F, S, L, check):
                    "pinned host buffers"}
 
 
+def resident_step_leg(args, w, F, S, L, check):
+    """SURVEY 8f-3 on top of f1 + f2: the particles stay in HBM across steps.  One step, all inside the timed
+    region: velKick, Kepler drift of the isolated particles, the particles that need the host's hard part
+    (neighbours, eccentric orbits) pulled to pinned host memory and pushed back (stand-in for the Hermite
+    integration the reference does there), tree + lists on the GPU, force pass with capture, changeover
+    correction, second velKick.  The reference: one iteration of src/main_p3t.cpp:423-708 without the hard part."""
+    import ctypes as C
+    import torch
+    from gplum_b200 import state as ST
+    n = args.n
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    epj = ST.make_epj(w.raw["pos"], w.raw_vel, w.raw["mass"], w.raw["r_out"], w.raw["r_search"])
+    prm_c, prm_i = S.corr_params(), ST.iso_params()
+    dt_tree = float(prm_i["dt_tree"][0])
+    cap = n
+    p_rec, p_idx = pin(np.zeros(cap, dtype=S.EPJ)), pin(np.zeros(cap, dtype=np.int32))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n_host = C.c_int(0)
+    sz = np.zeros(8, dtype=np.int64)
+
+    def force():
+        check(L.gplum_b200_state_tree_build(0.5, 8, args.group, vp(sz)))
+        F.walks_run(repack=False)
+        F.correct_long_run(prm_c)
+
+    def one(k):
+        ST.kick(dt_tree)
+        ST.drift(prm_i, k * dt_tree, (k + 1) * dt_tree)
+        check(L.gplum_b200_state_pull_unhandled(vp(p_rec), vp(p_idx), cap, C.byref(n_host)))
+        check(L.gplum_b200_state_push(vp(p_rec), vp(p_idx), n_host.value))
+        force()
+        ST.kick(dt_tree)
+
+    F.soft_corr_enable(True)
+    try:
+        ST.upload(epj, np.zeros(n), np.zeros(n))
+        force()
+        for k in range(3):
+            one(k)
+        torch.cuda.synchronize()
+        reps = max(3, args.steps // 2)
+        t0 = time.perf_counter()
+        for k in range(3, 3 + reps):
+            one(k)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+    finally:
+        F.soft_corr_enable(False)
+    n_int = int(sz[6] + sz[7])
+    return {"ms_per_step": dt * 1e3, "interactions_per_s": n_int / dt, "interactions_last_step": n_int,
+            "particles_to_host_per_step": int(n_host.value),
+            "h2d_bytes_per_step": int(n_host.value) * 116, "d2h_bytes_per_step": int(n_host.value) * 116 + 4,
+            "api": "state_kick + state_drift + state_pull_unhandled/_push + state_tree_build + walks_run + "
+                   "correct_long_run + state_kick; particles resident in HBM"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,6 +416,7 @@ def main():
     soft_step = None
     if world == 1:
         soft_step = soft_step_leg(args, w, F, S, L, check)
+        soft_step["resident"] = resident_step_leg(args, w, F, S, L, check)
         F.walks_upload(w)                        # back to the host-built set for the legs below
     peak_tf, _ = F.fp32_peak(10)
     my_ee, my_es = (ee, es) if world == 1 else sh.local.n_interactions()

@@ -52,6 +52,13 @@ SYMBOLS = {
     "gplum_b200_tree_copy_gpu": (_i, [_vp] * 12),
     "gplum_b200_tree_gpu_times": (_i, [C.POINTER(_f)]),
     "gplum_b200_tree_gpu_stamps": (_i, [_vp, _i]),
+    "gplum_b200_state_upload": (_i, [_i, _vp, _vp, _vp]),
+    "gplum_b200_state_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "gplum_b200_state_tree_build": (_i, [C.c_double, _i, _i, _vp]),
+    "gplum_b200_state_kick": (_i, [_i, _i, C.c_double]),
+    "gplum_b200_state_drift": (_i, [_vp, C.c_double, C.c_double, _i, _vp, _vp]),
+    "gplum_b200_state_pull_unhandled": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
+    "gplum_b200_state_push": (_i, [_vp, _vp, _i]),
     "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
     "gplum_b200_soft_corr_enable": (_i, [_i, _ll]),
     "gplum_b200_correct_long_run": (_i, [_i, _vp, _i]),

@@ -21,6 +21,7 @@
 #include "items.h"
 #include "soft_corr.h"
 #include "dev_tree.h"
+#include "iso_step.h"
 
 namespace {
 
@@ -155,6 +156,10 @@ struct Ctx {
     DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
     PinBuf tree_pin;            // pinned staging of pageable SoA inputs
     bool tree_built = false;    // the selected slot + j-set hold a GPU-built tree
+    // device-resident particle state (iso_step.cu): EPJGrav[n] with particle k at slot k, + time, dt, acc0, flags
+    DevBuf st_epj, st_time, st_dt, st_acc0, st_iso, st_star, st_handled, st_rec, st_idx, st_cnt;
+    PinBuf st_pin;
+    int st_n = 0;
 };
 Ctx g;
 
@@ -505,6 +510,8 @@ int gplum_b200_finalize(void)
     gplum_b200_peer_free();
     g.jset.release();
     g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release();
+    for (DevBuf *b : {&g.st_epj, &g.st_time, &g.st_dt, &g.st_acc0, &g.st_iso, &g.st_star, &g.st_handled, &g.st_rec, &g.st_idx, &g.st_cnt}) b->release();
+    g.st_pin.release(); g.st_n = 0;
     gbt::tree_release();
     g.tree_built = false;
     for (auto &s : g.slots) s.release();
@@ -1316,6 +1323,142 @@ int gplum_b200_tree_gpu_times(float *ms6)
     CU(cudaSetDevice(g.device));
     CU(cudaStreamSynchronize(g.stream));
     gbt::tree_phase_ms(ms6);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- device-resident particle state: kick + Kepler drift of isolated particles (iso_step.cu) ----
+extern "C" {
+
+int gplum_b200_state_upload(int n, const void *epj, const double *time, const double *dt)
+{
+    if (n <= 0 || !epj) return fail(GPLUM_B200_ERR_ARG, "state_upload: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    const size_t N = (size_t)n;
+    if (int r = g.st_epj.reserve(N * sizeof(EpjAos))) return r;
+    for (DevBuf *b : {&g.st_time, &g.st_dt, &g.st_acc0}) if (int r = b->reserve(N * 8)) return r;
+    for (DevBuf *b : {&g.st_iso, &g.st_handled}) if (int r = b->reserve(N * 4)) return r;
+    if (int r = g.st_star.reserve(N * sizeof(gplum_b200_star))) return r;
+    if (int r = g.st_cnt.reserve(16)) return r;
+    g.st_n = n;
+    CU(cudaMemcpyAsync(g.st_epj.p, epj, N * sizeof(EpjAos), cudaMemcpyHostToDevice, st));
+    if (time) CU(cudaMemcpyAsync(g.st_time.p, time, N * 8, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(g.st_time.p, 0, N * 8, st));
+    if (dt) CU(cudaMemcpyAsync(g.st_dt.p, dt, N * 8, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(g.st_dt.p, 0, N * 8, st));
+    CU(cudaMemsetAsync(g.st_acc0.p, 0, N * 8, st));
+    CU(cudaMemsetAsync(g.st_iso.p, 0, N * 4, st));
+    CU(cudaMemsetAsync(g.st_handled.p, 0, N * 4, st));
+    CU(cudaMemsetAsync(g.st_star.p, 0, N * sizeof(gplum_b200_star), st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int gplum_b200_state_download(void *epj_out, double *time, double *dt, void *star_out, int *handled_out)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_download: no resident state");
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamSynchronize(g.stream));
+    const size_t N = (size_t)g.st_n;
+    const cudaMemcpyKind D2H = cudaMemcpyDeviceToHost;
+    if (epj_out) CU(cudaMemcpy(epj_out, g.st_epj.p, N * sizeof(EpjAos), D2H));
+    if (time) CU(cudaMemcpy(time, g.st_time.p, N * 8, D2H));
+    if (dt) CU(cudaMemcpy(dt, g.st_dt.p, N * 8, D2H));
+    if (star_out) CU(cudaMemcpy(star_out, g.st_star.p, N * sizeof(gplum_b200_star), D2H));
+    if (handled_out) CU(cudaMemcpy(handled_out, g.st_handled.p, N * 4, D2H));
+    return 0;
+}
+
+int gplum_b200_state_tree_build(double theta, int n_leaf_limit, int n_group_limit, long long *sizes)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_tree_build: no resident state");
+    return gplum_b200_tree_build_gpu_epj(g.st_n, g.st_epj.p, 1, theta, n_leaf_limit, n_group_limit, sizes);
+}
+
+int gplum_b200_state_kick(int slot, int use_corr, double dt_tree)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_kick: no resident state");
+    if (slot < 0 || slot >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "state_kick(slot=%d)", slot);
+    WalkSet &ws = g.slots[slot];
+    if (ws.n_epi != g.st_n) return fail(GPLUM_B200_ERR_STATE, "state_kick: walk set holds %lld i-particles, the state %d", ws.n_epi, g.st_n);
+    if (use_corr && !ws.corrected) return fail(GPLUM_B200_ERR_STATE, "state_kick: no correction in slot %d", slot);
+    CU(cudaSetDevice(g.device));
+    const int e = gbi::iso_kick(g.st_n, g.st_epj.p, ws.epi.p, ws.force.p, use_corr ? ws.corr_out.p : nullptr, 0.5 * dt_tree, g.stream);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_kick -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t1, int slot,
+                           const int *isolated, const double *acc0)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_drift: no resident state");
+    if (!prm) return fail(GPLUM_B200_ERR_ARG, "state_drift: NULL parameters");
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    const size_t N = (size_t)g.st_n;
+    if (isolated) {
+        CU(cudaMemcpyAsync(g.st_iso.p, isolated, N * 4, cudaMemcpyHostToDevice, st));
+        if (acc0) CU(cudaMemcpyAsync(g.st_acc0.p, acc0, N * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));           // the caller's arrays may be pageable and short-lived
+    } else {
+        if (slot < 0 || slot >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "state_drift(slot=%d)", slot);
+        WalkSet &ws = g.slots[slot];
+        if (!ws.corrected || ws.n_epi != g.st_n) return fail(GPLUM_B200_ERR_STATE, "state_drift: slot %d holds no correction of this state", slot);
+        const int e = gbi::iso_flags_from_corr(g.st_n, ws.corr_out.p, (int *)g.st_iso.p, (double *)g.st_acc0.p, st);
+        if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_flags -> %s", cudaGetErrorString((cudaError_t)e));
+        g.launches++;
+    }
+    const int e = gbi::iso_drift(g.st_n, g.st_epj.p, (double *)g.st_time.p, (double *)g.st_dt.p, (const double *)g.st_acc0.p,
+                                 (const int *)g.st_iso.p, t0, t1, *prm, g.st_star.p, (int *)g.st_handled.p, st);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_drift -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches++;
+    return 0;
+}
+
+int gplum_b200_state_pull_unhandled(void *rec_out, int *idx_out, int cap, int *n_out)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_pull: no resident state");
+    if (!rec_out || !idx_out || !n_out || cap < 0) return fail(GPLUM_B200_ERR_ARG, "state_pull: bad argument");
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    if (int r = g.st_rec.reserve((size_t)std::max(cap, 1) * sizeof(EpjAos))) return r;
+    if (int r = g.st_idx.reserve((size_t)std::max(cap, 1) * 4)) return r;
+    if (int r = g.st_pin.reserve(16)) return r;
+    CU(cudaMemsetAsync(g.st_cnt.p, 0, 4, st));
+    const int e = gbi::iso_pull_unhandled(g.st_n, g.st_epj.p, (const int *)g.st_handled.p, g.st_rec.p, (int *)g.st_idx.p, (int *)g.st_cnt.p, cap, st);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_pull -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches++;
+    int *h_cnt = (int *)g.st_pin.p;
+    CU(cudaMemcpyAsync(h_cnt, g.st_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = *h_cnt;
+    if (*h_cnt > cap) return fail(GPLUM_B200_ERR_OVERFLOW, "state_pull: %d particles need the host, buffers hold %d", *h_cnt, cap);
+    if (*h_cnt > 0) {
+        CU(cudaMemcpyAsync(rec_out, g.st_rec.p, (size_t)*h_cnt * sizeof(EpjAos), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(idx_out, g.st_idx.p, (size_t)*h_cnt * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int gplum_b200_state_push(const void *rec, const int *idx, int n_rec)
+{
+    if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_push: no resident state");
+    if (n_rec < 0 || (n_rec > 0 && (!rec || !idx))) return fail(GPLUM_B200_ERR_ARG, "state_push: bad argument");
+    if (n_rec == 0) return 0;
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    if (int r = g.st_rec.reserve((size_t)n_rec * sizeof(EpjAos))) return r;
+    if (int r = g.st_idx.reserve((size_t)n_rec * 4)) return r;
+    CU(cudaMemcpyAsync(g.st_rec.p, rec, (size_t)n_rec * sizeof(EpjAos), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g.st_idx.p, idx, (size_t)n_rec * 4, cudaMemcpyHostToDevice, st));
+    const int e = gbi::iso_push(n_rec, g.st_rec.p, (const int *)g.st_idx.p, g.st_epj.p, st);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_push -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches++;
     return 0;
 }
 

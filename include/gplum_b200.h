@@ -231,6 +231,32 @@ int gplum_b200_tree_gpu_times(float *ms6);
  * returns the number of stamps written (<= cap) */
 int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap);
 
+/* ---- device-resident particle state: the isolated-particle half of a soft step ----
+ * The state is EPJGrav[n] with particle k at slot k (id_local == k, myrank = this rank) plus FPGrav::time
+ * and FPGrav::dt per particle.  With it a whole soft step runs without the particles leaving HBM:
+ *   state_kick   FPGrav::velKick (src/particle.h:878-884): vel += 0.5*dt_tree*acc with
+ *                acc = (F64)ForceGrav::acc [+ the changeover correction] of the walk set in `slot`
+ *                (src/particle.h:761-766, src/gravity_soft.h:366-367);
+ *   state_drift  the isolated-particle loop of the hard part (src/hard.h:793-817): particles without
+ *                neighbours and with eccentricity < 0.8 move along their Kepler orbit
+ *                (timeIntegrateKepler_isolated, src/hermite.h:787-816; src/kepler.h), get phi_s/acc_s/jerk_s
+ *                (calcStarGravity, src/gravity_hard.h:5-39) and their next hard time step (calcDeltatInitial,
+ *                src/particle.h:886-914).  isolated / acc0 come from the correction of `slot`
+ *                (number == 0, acc0), or from host arrays (particle order) when `isolated` != NULL;
+ *   state_pull_unhandled / state_push   the particles the drift did not take (neighbours -> hard clusters,
+ *                eccentric orbits -> Hermite) as EPJGrav records + indices, for the host's hard part, and back;
+ *   state_tree_build = gplum_b200_tree_build_gpu_epj on the resident state. */
+typedef struct { double m_sun, dt_tree, eta_0, eta_sun0, alpha2, dt_min, eps2_sun; } gplum_b200_iso_params;
+typedef struct { double phi_s; double acc_s[3]; double jerk_s[3]; double dt; } gplum_b200_star;        /* 64 B */
+int gplum_b200_state_upload(int n, const void *epj, const double *time, const double *dt);
+int gplum_b200_state_download(void *epj_out, double *time, double *dt, void *star_out, int *handled_out);
+int gplum_b200_state_tree_build(double theta, int n_leaf_limit, int n_group_limit, long long *sizes);
+int gplum_b200_state_kick(int slot, int use_corr, double dt_tree);
+int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t1, int slot,
+                           const int *isolated, const double *acc0);
+int gplum_b200_state_pull_unhandled(void *rec_out, int *idx_out, int cap, int *n_out);
+int gplum_b200_state_push(const void *rec, const int *idx, int n_rec);
+
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */
 int gplum_b200_fp32_peak(int iters, float *tflops, float *ms);

@@ -15,6 +15,8 @@
 //   ref_tree_*        build the reference's FDPS tree on given particles and record the
 //                     interaction lists it hands to the multi-walk-index accelerator interface
 //                     (FDPS/src/tree_for_force_impl_force.hpp:63-266)
+//   ref_vel_kick / ref_kepler_isolated   FPGrav::velKick and the isolated-particle Kepler drift of the hard
+//                     part (src/hard.h:793-817, src/hermite.h:787-816) on particle arrays
 //   ref_main          the reference program itself (argc/argv), for energy-history runs
 #define main gplum_reference_main
 #include "main_p3t.cpp"
@@ -330,6 +332,53 @@ long long ref_correct_long(int n, const double *pos, const double *vel, const do
     }
     if (off != n_ngb_tot) return -3;
     return off;
+}
+
+// ---- the isolated-particle half of a soft step: the reference's own velKick and Kepler drift ----
+// ref_vel_kick: FPGrav::velKick (src/particle.h:878-884) on n particles.
+void ref_vel_kick(int n, double *vel, const double *acc, double dt_tree)
+{
+    FP_t::dt_tree = dt_tree;
+    for (int i = 0; i < n; i++) {
+        FP_t p;
+        p.vel = PS::F64vec(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        p.acc = PS::F64vec(acc[3 * i], acc[3 * i + 1], acc[3 * i + 2]);
+        p.velKick();
+        vel[3 * i] = p.vel.x; vel[3 * i + 1] = p.vel.y; vel[3 * i + 2] = p.vel.z;
+    }
+}
+
+// ref_kepler_isolated: the loop of src/hard.h:793-817 -- particles with neighbor.number == 0 and
+// getEccentricity() < 0.8 (and eps2_sun == 0) go through timeIntegrateKepler_isolated
+// (src/hermite.h:787-816).  prm = {m_sun, dt_tree, eta_0, eta_sun0, alpha2, dt_min, eps2_sun};
+// star[i*8 ..] = {phi_s, acc_s xyz, jerk_s xyz, dt}; handled[i] = 1 where the branch was taken.
+int ref_kepler_isolated(int n, double *pos, double *vel, double *time, double *dt, const double *acc0,
+                        const int *isolated, double t0, double t1, const double *prm, double *star, int *handled)
+{
+    FP_t::m_sun = prm[0]; FP_t::dt_tree = prm[1]; FP_t::eta_0 = prm[2]; FP_t::eta_sun0 = prm[3];
+    FP_t::alpha2 = prm[4]; FP_t::dt_min = prm[5]; FP_t::eps2_sun = prm[6];
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        handled[i] = 0;
+        FP_t p;
+        p.pos = PS::F64vec(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        p.vel = PS::F64vec(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        p.time = time[i]; p.dt = dt[i]; p.acc0 = acc0[i];
+        p.neighbor.number = isolated[i] ? 0 : 1;
+        if (p.neighbor.number) continue;
+        if (!(p.getEccentricity() < 0.8 && FP_t::eps2_sun == 0.)) continue;
+        timeIntegrateKepler_isolated(p, t0, t1);
+        pos[3 * i] = p.pos.x; pos[3 * i + 1] = p.pos.y; pos[3 * i + 2] = p.pos.z;
+        vel[3 * i] = p.vel.x; vel[3 * i + 1] = p.vel.y; vel[3 * i + 2] = p.vel.z;
+        time[i] = p.time; dt[i] = p.dt;
+        double *o = star + 8 * (size_t)i;
+        o[0] = p.phi_s; o[1] = p.acc_s.x; o[2] = p.acc_s.y; o[3] = p.acc_s.z;
+        o[4] = p.jerk_s.x; o[5] = p.jerk_s.y; o[6] = p.jerk_s.z; o[7] = p.dt;
+        if (p.phi_d != 0. || p.acc_d.x != 0. || p.jerk_d.x != 0.) return -1;
+        handled[i] = 1;
+        cnt++;
+    }
+    return cnt;
 }
 
 // The reference program, unmodified (src/main_p3t.cpp:83).  Runs in the current directory.

@@ -68,6 +68,19 @@ def corr_fixture(path, n=1500, seed=2):
           int((f_tree["number"] > 2).sum()), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
+def iso_fixture(path):
+    """velKick + the isolated-particle Kepler drift by the reference's own functions (ref_shim)."""
+    import iso_cases
+    c = iso_cases.make_case()
+    prm = O.iso_params()
+    v1 = O.vel_kick(c["vel"], c["acc"], float(prm["dt_tree"][0]), lib="scalar")
+    pos, vel, time, dt, star, handled = O.kepler_isolated(c["pos"], v1, c["time"], c["dt"], c["acc0"], c["isolated"],
+                                                          c["t0"], c["t1"], prm, lib="scalar")
+    np.savez_compressed(path, prm=prm, vel_kicked=v1, pos=pos, vel=vel, time=time, dt=dt, star=star, handled=handled,
+                        **{"in_" + k: np.asarray(v) for k, v in c.items()})
+    print(path, "handled", int(handled.sum()), "of", len(handled), "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
 def main():
     assert O.have_ref("scalar"), "build oracle/_ref first: make -C oracle ref"
     d = np.loadtxt(REF_SAMPLE, skiprows=1)
@@ -77,6 +90,7 @@ def main():
     walks_fixture(os.path.join(HERE, "disk2k_g256.npz"), dk["pos"], dk["vel"], dk["mass"], 256)
 
     corr_fixture(os.path.join(HERE, "corr_long.npz"))
+    iso_fixture(os.path.join(HERE, "iso_step.npz"))
 
     cases = {}
     specs = [(1, 1, 1, 0, 0.0, 1), (24, 157, 166, 1, 0.0, 1), (64, 301, 200, 2, 0.0, 2),

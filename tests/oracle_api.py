@@ -205,3 +205,54 @@ def ref_correct_long(pos, vel, acc_d, mass, r_out, r_search, ids, prm, theta=0.5
            "in_domain": oi[:, 2]}
     lists = [ngb[oi[i, 3]:oi[i, 3] + oi[i, 1]] for i in range(n)]
     return w, force, res, lists
+
+
+# ------------------------------------------------------------------ isolated-particle step
+ISO_PARAMS = np.dtype([("m_sun", "<f8"), ("dt_tree", "<f8"), ("eta_0", "<f8"), ("eta_sun0", "<f8"),
+                       ("alpha2", "<f8"), ("dt_min", "<f8"), ("eps2_sun", "<f8")])
+ISO_STAR = np.dtype([("phi_s", "<f8"), ("acc_s", "<f8", (3,)), ("jerk_s", "<f8", (3,)), ("dt", "<f8")])
+
+
+def iso_params(m_sun=1.0, dt_tree=2.0 ** -6, eta_0=0.002, eta_sun0=0.002, alpha=1.0, dt_min=2.0 ** -30, eps2_sun=0.0):
+    """sample/parameter.dat's values (lines 52-60)."""
+    p = np.zeros(1, dtype=ISO_PARAMS)
+    p["m_sun"], p["dt_tree"], p["eta_0"], p["eta_sun0"] = m_sun, dt_tree, eta_0, eta_sun0
+    p["alpha2"], p["dt_min"], p["eps2_sun"] = alpha * alpha, dt_min, eps2_sun
+    return p
+
+
+def _c(a, dt=np.float64):
+    return np.ascontiguousarray(a, dtype=dt).copy()
+
+
+def vel_kick(vel, acc, dt_tree, lib="oracle"):
+    v, a = _c(vel), _c(acc)
+    L = oracle() if lib == "oracle" else ref(lib)
+    fn = L.oracle_vel_kick if lib == "oracle" else L.ref_vel_kick
+    fn.argtypes = [_i, _vp, _vp, C.c_double]
+    fn(len(v), _ptr(v), _ptr(a), float(dt_tree))
+    return v
+
+
+def kepler_isolated(pos, vel, time, dt, acc0, isolated, t0, t1, prm, lib="oracle"):
+    """The loop of src/hard.h:793-817 on arrays: returns pos, vel, time, dt, star, handled."""
+    n = len(pos)
+    pos, vel, time, dt, acc0 = _c(pos), _c(vel), _c(time), _c(dt), _c(acc0)
+    iso = _c(isolated, np.int32)
+    star = np.zeros(n, dtype=ISO_STAR)
+    handled = np.zeros(n, dtype=np.int32)
+    if lib == "oracle":
+        fn = oracle().oracle_kepler_isolated
+        fn.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp]
+        fn.restype = _i
+        cnt = fn(n, _ptr(pos), _ptr(vel), _ptr(time), _ptr(dt), _ptr(acc0), _ptr(iso), float(t0), float(t1), _ptr(prm),
+                 _ptr(star), _ptr(handled))
+    else:
+        fn = ref(lib).ref_kepler_isolated
+        fn.argtypes = [_i, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp]
+        fn.restype = _i
+        pv = np.array([prm[k][0] for k in ISO_PARAMS.names], dtype=np.float64)
+        cnt = fn(n, _ptr(pos), _ptr(vel), _ptr(time), _ptr(dt), _ptr(acc0), _ptr(iso), float(t0), float(t1), _ptr(pv),
+                 _ptr(star), _ptr(handled))
+    assert cnt == int(handled.sum()) and cnt >= 0
+    return pos, vel, time, dt, star, handled
