@@ -740,7 +740,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
     if (int r = ws.h_force.reserve((size_t)std::max<long long>(n_epi, 1) * sizeof(ForceAos))) return r;
     // sub-batches of about equal PCIe volume; small dispatches stay whole
     const size_t bytes = (size_t)n_epi * (sizeof(EpiAos) + sizeof(ForceAos)) + b_ae + b_as;
-    const int n_sub = n_walk == 0 ? 0 : (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, bytes / (8u << 20), (size_t)n_walk}));
+    const int n_sub = n_walk == 0 ? 0 : (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, bytes / (4u << 20), (size_t)n_walk}));
     ws.sub_w0.assign(1, 0);
     {
         size_t acc = 0; int b = 1;

@@ -136,6 +136,51 @@ def test_dispatch_retrieve_matches_flat_pass():
     synth.assert_force_close(force, want, RTOL, "dispatch/retrieve")
 
 
+def test_pipelined_dispatch_many_sub_batches_and_tags():
+    """A dispatch large enough to be cut into several PCIe sub-batches (copy-in / compute / copy-out streams),
+    two tags in flight, accumulate semantics: bit-identical to the flat pass of the same lists (a walk's
+    result does not depend on how the walks are batched)."""
+    from gplum_b200 import disk, tree
+    n = 300000
+    d = disk.make_disk(n, a_in=0.9, a_out=1.1, seed=4)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=256)
+    F.set_params(0.0, True, 0)
+    want = F.calc_walks(w)
+    half = w.n_walk // 2
+    force = S.cleared_force(n)
+    force["acc"] = 0.5; force["phi"] = -2.0; force["number"] = 1; force["id_max"] = 5; force["id_min"] = 2
+    start = force.copy()
+    F.dispatch(0, None, None, None, w.epj_all, w.spj_all, send_all=True)
+    lists = []
+    for tag, ws in ((0, range(0, half)), (1, range(half, w.n_walk))):
+        epi_l = [w.epi[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws]
+        ae_l = [w.adr_epj[w.epj_disp[k]:w.epj_disp[k] + w.n_epj[k]] for k in ws]
+        as_l = [w.adr_spj[w.spj_disp[k]:w.spj_disp[k] + w.n_spj[k]] for k in ws]
+        lists.append([force[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws])
+        F.dispatch(tag, epi_l, ae_l, as_l, w.epj_all, w.spj_all)        # both tags queued before any retrieve
+    F.retrieve(1, lists[1])
+    F.retrieve(0, lists[0])
+    # retrieve ACCUMULATES (PIKG/src/CUDA.rb:488-494): += on acc/phi/number/rank, max/min on the ids
+    assert np.array_equal(force["acc"], start["acc"] + want["acc"]) and np.array_equal(force["phi"], start["phi"] + want["phi"])
+    assert np.array_equal(force["number"], start["number"] + want["number"])
+    assert np.array_equal(force["id_max"], np.maximum(start["id_max"], want["id_max"]))
+    assert np.array_equal(force["id_min"], np.minimum(start["id_min"], want["id_min"]))
+    # and the overwrite mode FDPS's clear=true corresponds to
+    F.set_params(0.0, True, F.NO_ACCUMULATE)
+    try:
+        F.dispatch(0, None, None, None, w.epj_all, w.spj_all, send_all=True)
+        ws = range(w.n_walk)
+        F.dispatch(2, [w.epi[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws],
+                   [w.adr_epj[w.epj_disp[k]:w.epj_disp[k] + w.n_epj[k]] for k in ws],
+                   [w.adr_spj[w.spj_disp[k]:w.spj_disp[k] + w.n_spj[k]] for k in ws], w.epj_all, w.spj_all)
+        out = S.cleared_force(n)
+        F.retrieve(2, [out[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws])
+    finally:
+        F.set_params(0.0, True, 0)
+    assert out.tobytes() == want.tobytes()
+
+
 def test_device_resident_pass_and_counters():
     w, _, eps2 = _load_walks("disk2k_g256.npz")
     F.set_params(eps2, True, 0)
