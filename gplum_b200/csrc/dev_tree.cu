@@ -152,10 +152,16 @@ __global__ void __launch_bounds__(TPB) bbox_kernel(const EpjAos *__restrict__ p,
 __global__ void bbox_final_kernel(const double *__restrict__ part, int n_part, KP P)
 {
     __shared__ double sm[6];
-    if (threadIdx.x < 6) {
-        double v = part[threadIdx.x];
-        for (int b = 1; b < n_part; b++) v = threadIdx.x < 3 ? fmin(v, part[b * 6 + threadIdx.x]) : fmax(v, part[b * 6 + threadIdx.x]);
-        sm[threadIdx.x] = v;
+    {   // one warp: lanes stride over the blocks' partial boxes, then a shuffle reduction (min / max: any order)
+        double v[6] = {1e300, 1e300, 1e300, -1e300, -1e300, -1e300};
+        for (int b = threadIdx.x; b < n_part; b += 32)
+            for (int k = 0; k < 6; k++) v[k] = k < 3 ? fmin(v[k], part[b * 6 + k]) : fmax(v[k], part[b * 6 + k]);
+        for (int k = 0; k < 6; k++)
+            for (int d = 16; d > 0; d >>= 1) {
+                const double o = __shfl_xor_sync(FULL, v[k], d);
+                v[k] = k < 3 ? fmin(v[k], o) : fmax(v[k], o);
+            }
+        if (threadIdx.x == 0) for (int k = 0; k < 6; k++) sm[k] = v[k];
     }
     __syncthreads();
     if (threadIdx.x == 0) {

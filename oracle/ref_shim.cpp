@@ -334,6 +334,37 @@ long long ref_correct_long(int n, const double *pos, const double *vel, const do
     return off;
 }
 
+// ---- snapshot wire format: layout of the raw records the reference dumps ----
+// snap_tmp.dat = FileHeader (src/energy.h:70-127, fwrite of the struct) + n_body x FPGrav (src/particle.h:860-876).
+// out[] = sizeof(FileHeader), sizeof(Energy), offsetof(FileHeader: n_body, id_next, time, e_init, e_now),
+//         sizeof(FPGrav), then offsetof(FPGrav: id_local, myrank, pos, r_out, r_search, id, mass, vel, acc_d,
+//         acc, acc_s, jerk_d, jerk_s, acc_gd, phi, phi_d, phi_s, v_disp, r_out_inv, time, dt, acc0, r_planet, f,
+//         neighbor, id_cluster, n_cluster, inDomain, isSent, isDead, isMerged); returns the count written.
+int ref_snapshot_layout(int *out)
+{
+    int k = 0;
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Winvalid-offsetof"
+    out[k++] = (int)sizeof(FileHeader); out[k++] = (int)sizeof(Energy);
+    out[k++] = (int)offsetof(FileHeader, n_body); out[k++] = (int)offsetof(FileHeader, id_next);
+    out[k++] = (int)offsetof(FileHeader, time); out[k++] = (int)offsetof(FileHeader, e_init);
+    out[k++] = (int)offsetof(FileHeader, e_now);
+    out[k++] = (int)sizeof(FP_t);
+    out[k++] = (int)offsetof(FP_t, id_local); out[k++] = (int)offsetof(FP_t, myrank); out[k++] = (int)offsetof(FP_t, pos);
+    out[k++] = (int)offsetof(FP_t, r_out); out[k++] = (int)offsetof(FP_t, r_search); out[k++] = (int)offsetof(FP_t, id);
+    out[k++] = (int)offsetof(FP_t, mass); out[k++] = (int)offsetof(FP_t, vel); out[k++] = (int)offsetof(FP_t, acc_d);
+    out[k++] = (int)offsetof(FP_t, acc); out[k++] = (int)offsetof(FP_t, acc_s); out[k++] = (int)offsetof(FP_t, jerk_d);
+    out[k++] = (int)offsetof(FP_t, jerk_s); out[k++] = (int)offsetof(FP_t, acc_gd); out[k++] = (int)offsetof(FP_t, phi);
+    out[k++] = (int)offsetof(FP_t, phi_d); out[k++] = (int)offsetof(FP_t, phi_s); out[k++] = (int)offsetof(FP_t, v_disp);
+    out[k++] = (int)offsetof(FP_t, r_out_inv); out[k++] = (int)offsetof(FP_t, time); out[k++] = (int)offsetof(FP_t, dt);
+    out[k++] = (int)offsetof(FP_t, acc0); out[k++] = (int)offsetof(FP_t, r_planet); out[k++] = (int)offsetof(FP_t, f);
+    out[k++] = (int)offsetof(FP_t, neighbor); out[k++] = (int)offsetof(FP_t, id_cluster); out[k++] = (int)offsetof(FP_t, n_cluster);
+    out[k++] = (int)offsetof(FP_t, inDomain); out[k++] = (int)offsetof(FP_t, isSent); out[k++] = (int)offsetof(FP_t, isDead);
+    out[k++] = (int)offsetof(FP_t, isMerged);
+#pragma GCC diagnostic pop
+    return k;
+}
+
 // ---- the isolated-particle half of a soft step: the reference's own velKick and Kepler drift ----
 // ref_vel_kick: FPGrav::velKick (src/particle.h:878-884) on n particles.
 void ref_vel_kick(int n, double *vel, const double *acc, double dt_tree)

@@ -81,6 +81,25 @@ def iso_fixture(path):
     print(path, "handled", int(handled.sum()), "of", len(handled), "%.0f kB" % (os.path.getsize(path) / 1e3))
 
 
+def snapshot_fixture(path, keep=96):
+    """Files written by the reference program itself (oracle/_ref/gplum_ref.out on config 1, 4 steps):
+    the binary restart file and the ASCII snapshot of the same instant, truncated to `keep` particles."""
+    import shutil
+    import tempfile
+    import gplum_run
+    d = tempfile.mkdtemp(prefix="gplum_snap_")
+    try:
+        gplum_run.run("gplum_ref.out", d, t_end="2^-4", dt_snap="2^-5", threads=4)
+        raw = open(os.path.join(d, "TEST", "snap_tmp.dat"), "rb").read()
+        txt = open(os.path.join(d, "TEST", "snap000002.dat"), "rb").read().split(b"\n")
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    np.savez_compressed(path, binary=np.frombuffer(raw[:128 + 344 * keep], dtype=np.uint8),
+                        ascii=np.frombuffer(b"\n".join(txt[:1 + keep]) + b"\n", dtype=np.uint8), keep=np.int32(keep),
+                        n_body=np.int32((len(raw) - 128) // 344))
+    print(path, "%.0f kB" % (os.path.getsize(path) / 1e3))
+
+
 def main():
     assert O.have_ref("scalar"), "build oracle/_ref first: make -C oracle ref"
     d = np.loadtxt(REF_SAMPLE, skiprows=1)
@@ -91,6 +110,7 @@ def main():
 
     corr_fixture(os.path.join(HERE, "corr_long.npz"))
     iso_fixture(os.path.join(HERE, "iso_step.npz"))
+    snapshot_fixture(os.path.join(HERE, "snapshot_ref.npz"))
 
     cases = {}
     specs = [(1, 1, 1, 0, 0.0, 1), (24, 157, 166, 1, 0.0, 1), (64, 301, 200, 2, 0.0, 2),
