@@ -87,6 +87,7 @@ struct WalkSet {
     long long n_int_epep = 0, n_int_epsp = 0;
     std::vector<int> ni_host;                    // for retrieve()
     std::vector<long long> epi_off_host;
+    bool has_split = false;                      // the work list holds EP/SP-split tiles: launches start from a zeroed ForceGrav
     bool pending = false;
     cudaEvent_t done = nullptr;                  // recorded after the D2H of a dispatch: retrieve(tag) waits on it only
     // dispatch() pipeline: the walks of one dispatch are cut into sub-batches; sub-batch b's lists go up on the
@@ -151,6 +152,8 @@ struct Ctx {
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
+    int epsp_split = -1;        // EP/SP split of full-width tiles: -1 = passes with less than one wave of items, 0 = never,
+                                // 1 = always (GPLUM_B200_EPSP_SPLIT)
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
     long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
     DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
@@ -171,7 +174,9 @@ int ensure_init()
 }
 
 // ---- work list: split every walk into i-tiles, choose a tile shape, longest first (items.h) ----
-void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items, int walk_base = 0)
+// returns true when the list contains EP/SP-split tiles (their ForceGrav range must be zeroed before the launch)
+bool build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items, int walk_base = 0,
+                 bool allow_split = true)
 {
     items.clear();
     std::vector<std::pair<double, WorkItem>> tmp;
@@ -197,17 +202,38 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
             rem -= n; i0 += n;
         }
     }
+    // a pass with less than one wave of items: issue every full-width tile twice, EP tiles and SP tiles apart
+    // (twice the warps on the issue ports, half the serial chain per item; kernels.cuh, `part`)
+    bool has_split = false;
+    if (allow_split && g.rmax <= 2 && g.epsp_split != 0 && (g.epsp_split > 0 || (long long)tmp.size() < g.warp_slots)) {
+        const size_t n0 = tmp.size();
+        for (size_t k = 0; k < n0; k++) {
+            WorkItem it = tmp[k].second;
+            const int w = it.walk;
+            if (it.cfg > 1 || n_epj[w] == 0 || n_spj[w] == 0) continue;
+            const int shape = it.cfg == 1 ? 64 : 32;
+            tmp[k] = {tile_cost_ep(n_epj[w], shape), WorkItem{w, it.i0, it.ni, it.cfg | TILE_EP_ONLY}};
+            tmp.push_back({tile_cost_sp(n_spj[w], shape), WorkItem{w, it.i0, it.ni, it.cfg | TILE_SP_ONLY}});
+            has_split = true;
+        }
+    }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
     items.reserve(tmp.size());
     for (auto &t : tmp) { t.second.walk += walk_base; items.push_back(t.second); }
+    return has_split;
 }
 
 // Launches the force kernel on items [item0, item0 + n_items) of the set (default: all).  `first` resets the
 // candidate capture and counts the pass's interactions; sub-batch launches of one pass pass first = false.
-int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_items = -1, bool first = true)
+int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_items = -1, bool first = true,
+                long long zero_e0 = -1, long long zero_e1 = -1)
 {
     if (n_items < 0) n_items = ws.n_items;
     if (n_items == 0) return 0;
+    // split tiles add their halves into ForceGrav (kernels.cuh, `part`): start from zero.  Default: the whole set
+    // when its list holds split tiles; dispatch() passes the i-range of a sub-batch instead.
+    if (zero_e0 < 0 && ws.has_split) { zero_e0 = 0; zero_e1 = ws.n_epi; }
+    if (zero_e1 > zero_e0) CU(cudaMemsetAsync((ForceAos *)ws.force.p + zero_e0, 0, (size_t)(zero_e1 - zero_e0) * sizeof(ForceAos), st));
     PassParams p;
     p.epi = (const EpiAos *)ws.epi.p;
     p.epi_off = (const int *)ws.epi_off.p;
@@ -297,7 +323,7 @@ int upload_walks(WalkSet &ws, int n_walk, const void *epi_all, const int *epi_of
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es;
     g.tree_built = false;
     std::vector<WorkItem> items;
-    build_items(n_walk, ni, n_epj, n_spj, items);
+    ws.has_split = build_items(n_walk, ni, n_epj, n_spj, items);
     ws.n_items = (int)items.size();
     if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
@@ -409,7 +435,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     std::vector<WorkItem> items;
     const int zero = 0;
     const int ne = which == 0 ? nj : 0, ns = which == 1 ? nj : 0;
-    build_items(1, &ni, &ne, &ns, items);
+    build_items(1, &ni, &ne, &ns, items, 0, false);
     struct Meta { int epi_off, n_epj, n_spj, pad; long long epj_disp, spj_disp; } meta = {zero, ne, ns, 0, 0, 0};
     const size_t meta_bytes = sizeof(Meta) + items.size() * sizeof(WorkItem);
     if (int r = s.meta.reserve(meta_bytes)) return r;
@@ -484,6 +510,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : (atoi(e) <= 1 ? 1 : 2);
     if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_EPSP_SPLIT")) g.epsp_split = atoi(e);
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
@@ -702,7 +729,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         if (ni[w] < 0 || n_epj[w] < 0 || n_spj[w] < 0) return fail(GPLUM_B200_ERR_ARG, "negative count in walk %d", w);
         n_epi += ni[w]; n_ae += n_epj[w]; n_as += n_spj[w];
         i_ee += (long long)ni[w] * n_epj[w]; i_es += (long long)ni[w] * n_spj[w];
-        n_it_max += (ni[w] + 3) / 4 + 1;          // smallest tile holds 4 i-particles
+        n_it_max += 2 * ((ni[w] + 3) / 4 + 1);    // smallest tile holds 4 i-particles; x2: EP/SP split
     }
     const size_t b_epi = ((size_t)n_epi * sizeof(EpiAos) + 15) & ~(size_t)15, b_ae = (size_t)n_ae * 4, b_as = (size_t)n_as * 4;
     const size_t b_meta = (size_t)n_walk * (4 * 3 + 8 * 2);
@@ -726,6 +753,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
     }
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es; ws.n_items = 0;
+    ws.has_split = false;                        // per sub-batch below
     g.tree_built = false;
     if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
@@ -774,7 +802,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
             memcpy(h_ae + h_edisp[w], adr_epj[w], (size_t)n_epj[w] * 4);
             memcpy(h_as + h_sdisp[w], adr_spj[w], (size_t)n_spj[w] * 4);
         }
-        build_items(w1 - w0, ni + w0, n_epj + w0, n_spj + w0, items, w0);
+        const bool split_b = build_items(w1 - w0, ni + w0, n_epj + w0, n_spj + w0, items, w0);
         const int n_it = (int)items.size();
         if (item0 + n_it > n_it_max) return fail(GPLUM_B200_ERR_STATE, "work-item estimate too small");
         if (n_it) memcpy(h_items + item0, items.data(), (size_t)n_it * sizeof(WorkItem));
@@ -788,7 +816,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         CU(cudaEventRecord(ws.ev_in[b], ci));
         CU(cudaStreamWaitEvent(st, ws.ev_in[b], 0));
         ws.n_items = item0 + n_it;
-        if (int r = launch_pass(ws, st, g.eps2, item0, n_it, b == 0)) return r;
+        if (int r = launch_pass(ws, st, g.eps2, item0, n_it, b == 0, split_b ? e0 : 0, split_b ? e1 : 0)) return r;
         CU(cudaEventRecord(ws.ev_k[b], st));
         CU(cudaStreamWaitEvent(co, ws.ev_k[b], 0));
         if (e1 > e0) CU(cudaMemcpyAsync((ForceAos *)ws.h_force.p + e0, (const ForceAos *)ws.force.p + e0, (size_t)(e1 - e0) * sizeof(ForceAos), cudaMemcpyDeviceToHost, co));
@@ -1228,6 +1256,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     ws.n_adr_epj = c.n_adr_epj; ws.n_adr_spj = c.n_adr_spj;
     ws.n_int_epep = c.n_int_epep; ws.n_int_epsp = c.n_int_epsp;
     ws.ni_host.clear(); ws.epi_off_host.clear();
+    ws.has_split = false;                        // the device work-list builder issues whole tiles only
     ws.pending = false; ws.captured = false; ws.corrected = false;
     j.ext_epj = j.ext_spj = nullptr;
     j.n_epj = n; j.n_spj = c.n_cells;

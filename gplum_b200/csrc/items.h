@@ -35,6 +35,11 @@ GB_HD double tile_cost(int n_epj, int n_spj, int shape)
     return cost_j * shape / 32.0 + cost_tiles;
 }
 
+// EP/SP split of full-width tiles (kernels.cuh: warp_force, `part`): cfg bits
+constexpr int TILE_EP_ONLY = 16, TILE_SP_ONLY = 32;
+GB_HD double tile_cost_ep(int n_epj, int shape) { return 18.5 * n_epj * shape / 32.0 + 90.0 * ((n_epj + 63) / 64) + 200.0; }
+GB_HD double tile_cost_sp(int n_spj, int shape) { return 37.0 * n_spj * shape / 32.0 + 90.0 * ((n_spj + 63) / 64) + 200.0; }
+
 // Tile capacity of a pass: 64 i-particles per warp is the most efficient shape (staging is amortised
 // over the most pairs), and measured on 1/4- and 1/8-size shards it stays the fastest even at 0.6 waves.
 // Only a pass that cannot give every fourth warp slot an item (per-call functor form, a small boundary

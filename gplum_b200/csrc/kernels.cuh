@@ -230,9 +230,17 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     const int *adr_sp = p.adr_spj + p.spj_disp[w];
     const int nt_ep = (nj_ep + JW - 1) / JW, nt_sp = (nj_sp + JW - 1) / JW;
     const int nt = nt_ep + nt_sp;
+    // EP/SP split (cfg bits 4, 5): in a pass with less than one wave of items every full-width tile is issued
+    // twice, once for the walk's EP tiles and once for its SP tiles, so that twice as many warps share the
+    // issue ports and the serial chain of an item halves.  The two halves add into a zeroed ForceGrav with
+    // one atomic each: 0 + x + y has one rounding whichever comes first, so the result is deterministic.
+    const int part = (it.cfg >> 4) & 3;             // 0 = whole list, 1 = EP tiles only, 2 = SP tiles only
+    const int t_begin = part == 2 ? nt_ep : 0;
+    const int t_end = part == 1 ? nt_ep : nt;
 
     // list index of slot (lane + 32k) of tile t, or -1 for padding
     auto slot_index = [&](int t, int k) -> int {
+        if (t >= t_end) return -1;
         if (t < nt_ep) { const int j = t * JW + lane + 32 * k; return j < nj_ep ? adr_ep[j] : -1; }
         if (t < nt) { const int j = (t - nt_ep) * JW + lane + 32 * k; return j < nj_sp ? adr_sp[j] : -1; }
         return -1;
@@ -277,9 +285,9 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     };
 
     // ---- prologue: start tile 0, load this warp's i-particles meanwhile ----
-    int idx0 = slot_index(0, 0), idx1 = slot_index(0, 1);
-    issue(0, 0, idx0); issue(0, 1, idx1);
-    int nidx0 = slot_index(1, 0), nidx1 = slot_index(1, 1);
+    int idx0 = slot_index(t_begin, 0), idx1 = slot_index(t_begin, 1);
+    issue(t_begin, 0, idx0); issue(t_begin, 1, idx1);
+    int nidx0 = slot_index(t_begin + 1, 0), nidx1 = slot_index(t_begin + 1, 1);
 
     float xi[R], yi[R], zi[R], ro2i[R], rs2i[R];
     float ax[R], ay[R], az[R], ph[R];
@@ -307,10 +315,10 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     }
     float tmax = 0.0f;
     cp_async_commit_wait_all();
-    if (nt > 0) tmax = fmaxf(convert(0, 0, idx0), convert(0, 1, idx1));
+    if (t_end > t_begin) tmax = fmaxf(convert(t_begin, 0, idx0), convert(t_begin, 1, idx1));
     __syncwarp();
 
-    for (int t = 0; t < nt; t++) {
+    for (int t = t_begin; t < t_end; t++) {
         // stage tile t+1 while computing tile t
         idx0 = nidx0; idx1 = nidx1;
         issue(t + 1, 0, idx0); issue(t + 1, 1, idx1);
@@ -432,7 +440,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
         cp_async_commit_wait_all();
         __syncwarp();                     // every lane is done reading tile t
         tmax = 0.0f;
-        if (t + 1 < nt) tmax = fmaxf(convert(t + 1, 0, idx0), convert(t + 1, 1, idx1));
+        if (t + 1 < t_end) tmax = fmaxf(convert(t + 1, 0, idx0), convert(t + 1, 1, idx1));
         __syncwarp();
     }
 
@@ -459,8 +467,15 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
             const int i = lane + 32 * r;
             if (i < it.ni) {
                 float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
-                out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
-                reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+                if (part == 0) {
+                    out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
+                } else {                       // half of a split tile: the pass zeroed ForceGrav before the launch
+                    float *f = reinterpret_cast<float *>(out);
+                    atomicAdd(f + 0, 0.125f * ax[r]); atomicAdd(f + 1, 0.125f * ay[r]);
+                    atomicAdd(f + 2, 0.125f * az[r]); atomicAdd(f + 3, 0.5f * ph[r]);
+                }
+                if (part != 2)
+                    reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
             }
         }
     }
@@ -479,9 +494,11 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
     const int item = blockIdx.x * WPB + wid;
     if (item >= n_items) return;
     const WorkItem it = p.items[item];
-    // cfg: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = j-split tile, G = 2^k lane groups
-    if (it.cfg >= 8) {
-        switch (it.cfg) {
+    // cfg & 15: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = j-split tile, G = 2^k lane groups;
+    // cfg bits 4 / 5 (full-width tiles only): EP tiles only / SP tiles only (items.h: TILE_EP_ONLY, TILE_SP_ONLY)
+    const int kcfg = it.cfg & 15;
+    if (kcfg >= 8) {
+        switch (kcfg) {
             case 9: warp_force<1, 2>(p, it, s); break;
             case 10: warp_force<1, 4>(p, it, s); break;
             default: warp_force<1, 8>(p, it, s); break;
@@ -489,10 +506,10 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
         return;
     }
     if (RMAX <= 2) {
-        if (it.cfg == 0) warp_force<1, 1>(p, it, s);
+        if (kcfg == 0) warp_force<1, 1>(p, it, s);
         else warp_force<2, 1>(p, it, s);
     } else {
-        switch (it.cfg) {
+        switch (kcfg) {
             case 0: warp_force<1, 1>(p, it, s); break;
             case 1: warp_force<2, 1>(p, it, s); break;
             case 2: warp_force<3, 1>(p, it, s); break;

@@ -138,8 +138,9 @@ def test_dispatch_retrieve_matches_flat_pass():
 
 def test_pipelined_dispatch_many_sub_batches_and_tags():
     """A dispatch large enough to be cut into several PCIe sub-batches (copy-in / compute / copy-out streams),
-    two tags in flight, accumulate semantics: bit-identical to the flat pass of the same lists (a walk's
-    result does not depend on how the walks are batched)."""
+    two tags in flight, accumulate semantics: equal to the flat pass of the same lists -- neighbour info
+    exactly, acc/phi to the path's FP32 bar (a small sub-batch may issue its tiles EP/SP-split, which changes
+    the order of the last additions; items.h)."""
     from gplum_b200 import disk, tree
     n = 300000
     d = disk.make_disk(n, a_in=0.9, a_out=1.1, seed=4)
@@ -162,7 +163,8 @@ def test_pipelined_dispatch_many_sub_batches_and_tags():
     F.retrieve(1, lists[1])
     F.retrieve(0, lists[0])
     # retrieve ACCUMULATES (PIKG/src/CUDA.rb:488-494): += on acc/phi/number/rank, max/min on the ids
-    assert np.array_equal(force["acc"], start["acc"] + want["acc"]) and np.array_equal(force["phi"], start["phi"] + want["phi"])
+    assert np.allclose(force["acc"], start["acc"] + want["acc"], rtol=1e-6, atol=0)
+    assert np.allclose(force["phi"], start["phi"] + want["phi"], rtol=1e-6, atol=0)
     assert np.array_equal(force["number"], start["number"] + want["number"])
     assert np.array_equal(force["id_max"], np.maximum(start["id_max"], want["id_max"]))
     assert np.array_equal(force["id_min"], np.minimum(start["id_min"], want["id_min"]))
@@ -178,7 +180,9 @@ def test_pipelined_dispatch_many_sub_batches_and_tags():
         F.retrieve(2, [out[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws])
     finally:
         F.set_params(0.0, True, 0)
-    assert out.tobytes() == want.tobytes()
+    # the path-wide FP32 bar: near- and far-field sums cancel, so a changed summation order shows at 1e-5..1e-4
+    synth.assert_force_close(out, want, RTOL, "pipelined dispatch vs flat pass")
+    assert np.array_equal(out["rank"], want["rank"])
 
 
 def test_device_resident_pass_and_counters():
