@@ -1492,3 +1492,23 @@ int gplum_b200_state_push(const void *rec, const int *idx, int n_rec)
 }
 
 }  // extern "C"
+
+// ---- host work-list builder, exposed for tests (no device needed) ----
+extern "C" int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj,
+                                            long long warp_slots, int tile_cap, int jsplit, int epsp_split,
+                                            int *items_out, int cap_items, int *n_items_out, int *has_split_out)
+{
+    if (n_walk < 0 || !ni || !n_epj || !n_spj || !n_items_out) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: bad argument");
+    const long long ws0 = g.warp_slots; const int tc0 = g.tile_cap, js0 = g.jsplit, es0 = g.epsp_split;
+    g.warp_slots = warp_slots; g.tile_cap = tile_cap; g.jsplit = jsplit; g.epsp_split = epsp_split;
+    std::vector<WorkItem> items;
+    const bool hs = build_items(n_walk, ni, n_epj, n_spj, items);
+    g.warp_slots = ws0; g.tile_cap = tc0; g.jsplit = js0; g.epsp_split = es0;
+    *n_items_out = (int)items.size();
+    if (has_split_out) *has_split_out = hs ? 1 : 0;
+    if (items_out) {
+        if ((int)items.size() > cap_items) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: %zu items, room for %d", items.size(), cap_items);
+        memcpy(items_out, items.data(), items.size() * sizeof(WorkItem));
+    }
+    return 0;
+}

@@ -257,6 +257,13 @@ int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t
 int gplum_b200_state_pull_unhandled(void *rec_out, int *idx_out, int cap, int *n_out);
 int gplum_b200_state_push(const void *rec, const int *idx, int n_rec);
 
+/* The host work-list builder of the force pass, for tests (needs no device): cuts every walk into i-tiles
+ * {walk, i0, ni, cfg} (4 ints each; cfg & 15: 0 = 32 i, 1 = 64 i, 9/10/11 = 16/8/4 i with the j-list split over
+ * 2/4/8 lane groups; cfg & 16 / & 32: EP tiles only / SP tiles only), longest first. */
+int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj,
+                                 long long warp_slots, int tile_cap, int jsplit, int epsp_split,
+                                 int *items_out, int cap_items, int *n_items_out, int *has_split_out);
+
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */
 int gplum_b200_fp32_peak(int iters, float *tflops, float *ms);
