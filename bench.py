@@ -9,7 +9,8 @@ sample/parameter.dat tree parameters, n_group_limit per --group.
   value     interactions/s with raw particles + lists resident in HBM (CUDA events, max over ranks)
   e2e       same metric through the reference-facing C ABI (gplum_b200_dispatch/retrieve, the
             FDPS multi-walk-index functors) with pinned HOST buffers: H2D of j-particles, walks
-            and lists, kernels, D2H of forces, all inside the timed region
+            and lists, kernels, D2H of forces, all inside the timed region; at N>1 every rank ships
+            what its rank of an MPI-FDPS run holds (own walks, local + LET particles, its SPJ)
   roofline  dominant kernel (force_pass_kernel): algorithmic flop (30/EP-EP pair, 59/EP-SP pair,
             SURVEY 8d) / its CUDA-event time, against the FP32 FFMA peak measured in the same run
   cpu_baseline  the reference's own functors (oracle/_ref, AVX2+OpenMP build) on a bounded sample
@@ -33,6 +34,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun defaults OMP_NUM_THREADS to 1 per rank; the plugin's host side (list flattening, force accumulation in
+# dispatch/retrieve) is OpenMP code like the reference's: give every rank its share of the host cores
+if os.environ.get("LOCAL_WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // int(os.environ["LOCAL_WORLD_SIZE"])))
 # stdout carries ONE JSON line: keep NCCL's banner / debug output off it (must be set before NCCL initialises)
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
@@ -445,11 +450,10 @@ def main():
     if world == 1:
         lw = w
     else:
-        # each rank ships its own walks; j-particles of the whole system (reference: LET) from host
-        lw = type(w)(w.epi[sh.epi_range[0]:sh.epi_range[1]], sh.local.epi_off, sh.local.ni,
-                     w.adr_epj[sh.adr_epj_range[0]:sh.adr_epj_range[1]], sh.local.epj_disp, sh.local.n_epj,
-                     w.adr_spj[sh.adr_spj_range[0]:sh.adr_spj_range[1]], sh.local.spj_disp, sh.local.n_spj,
-                     w.epj_all, w.spj_all)
+        # each rank ships what its rank of an MPI-FDPS run holds: its own walks, epj_sorted_ = local particles + LET
+        # imports, spj_sorted_ = the superparticles its walks reference (gplum_b200/shard.py: rank_inputs)
+        from gplum_b200.shard import HaloShard
+        lw = HaloShard(w, world, rank).rank_inputs(w)
     keep = []
     def pin(a):
         b, t = pinned_like(a); keep.append(t); return b

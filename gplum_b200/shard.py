@@ -172,3 +172,14 @@ class HaloShard:
         self.walks_boundary = self.subset(np.nonzero(~self.interior)[0])
 
     subset = Shard.subset
+
+    def rank_inputs(self, w):
+        """What this rank of an MPI-FDPS run would hand to the dispatch functor: its own walks, with
+        `epj_sorted_` = its local particles followed by its LET imports (the halo records, in the order the
+        lists index them) and `spj_sorted_` = the superparticles its walks reference
+        (FDPS/src/tree_for_force_impl_exlet.hpp:343-403).  Same lists, same records, so the forces of these
+        walks equal the single-rank pass bit for bit."""
+        lw = self.local
+        epj = np.concatenate([lw.epj_all, w.epj_all[self.need]])
+        return Walks(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj, lw.spj_disp, lw.n_spj,
+                     epj, lw.spj_all)

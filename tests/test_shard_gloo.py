@@ -113,3 +113,27 @@ def test_split_is_contiguous_and_balanced():
         cost = w.ni.astype(np.int64) * (w.n_epj * 20 + w.n_spj * 38)
         per = [cost[a:b].sum() for a, b in r]
         assert max(per) <= 1.35 * (sum(per) / world) + cost.max()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_rank_inputs_reproduce_the_single_rank_pass(world):
+    """The per-rank dispatch inputs of bench.py's multi-GPU e2e leg (own walks, local + LET particles, trimmed
+    SPJ): evaluated rank by rank with the oracle they give the single-rank forces bit for bit."""
+    import oracle_api as O
+    from gplum_b200 import disk, tree
+    from gplum_b200.shard import HaloShard
+    d = disk.make_disk(6000, a_in=0.97, a_out=1.03, seed=11)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs * 2.0, n_group_limit=64)
+    want, n_int = O.calc_walks(w, 0.0)
+    seen, tot = 0, 0
+    for r in range(world):
+        sh = HaloShard(w, world, r)
+        lw = sh.rank_inputs(w)
+        assert len(lw.epj_all) == sh.n_own + sh.n_halo < len(w.epj_all) or world == 1
+        assert lw.adr_epj.max(initial=0) < len(lw.epj_all) and lw.adr_spj.max(initial=0) < len(lw.spj_all)
+        got, n = O.calc_walks(lw, 0.0)
+        e0, e1 = sh.epi_range
+        assert got.tobytes() == want[e0:e1].tobytes(), r
+        seen += e1 - e0; tot += n
+    assert seen == len(w.epi) and tot == n_int
