@@ -166,7 +166,8 @@ def soft_step_leg(args, w, F, S, L, check):
     """Next rows of the path (SURVEY 8f-1 + 8f-2): one whole soft-force evaluation without host-side
     lists.  Per step, inside the timed region: raw particles (pinned host SoA, 48 B each) -> device,
     tree + i-groups + interaction lists built on the GPU (dev_tree.cu), force pass with candidate
-    capture, changeover correction, forces + corrections + neighbour lists back to pinned host memory.
+    capture, changeover correction, forces + the corrections of the particles that have neighbours + neighbour
+    lists back to pinned host memory.
     The reference: setParticleLocalTree .. calcForceAllAndWriteBack + correctForceLong
     (src/main_p3t.cpp:583-593)."""
     import ctypes as C
@@ -183,7 +184,7 @@ def soft_step_leg(args, w, F, S, L, check):
     p_ngb = pin(np.zeros(ngb_cap, dtype=S.NGB))
     prm = S.corr_params()
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    n_slots, n_pairs = C.c_longlong(0), C.c_longlong(0)
+    n_slots, n_pairs, n_corr = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
     sizes = [None]
 
     def one():
@@ -192,7 +193,8 @@ def soft_step_leg(args, w, F, S, L, check):
         F.walks_run(repack=False)
         F.correct_long_run(prm)
         check(L.gplum_b200_walks_download(vp(p_force)))
-        check(L.gplum_b200_correct_long_download(0, vp(p_corr), None, vp(p_ngb), ngb_cap, C.byref(n_slots), C.byref(n_pairs)))
+        check(L.gplum_b200_correct_long_download_compact(0, vp(p_corr), n, C.byref(n_corr), vp(p_ngb), ngb_cap,
+                                                         C.byref(n_slots), C.byref(n_pairs)))
 
     F.soft_corr_enable(True)
     try:
@@ -220,13 +222,14 @@ def soft_step_leg(args, w, F, S, L, check):
     n_int = int(sz[6] + sz[7])
     assert (int(sz[6]), int(sz[7])) == w.n_interactions(), "GPU-built lists differ from the host builder's"
     return {"ms_per_step": dt * 1e3, "interactions_per_s": n_int / dt,
-            "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int((32 + 64) * n + 16 * n_slots.value),
+            "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int(32 * n + 64 * n_corr.value + 16 * n_slots.value),
+            "particles_with_neighbours": int(n_corr.value),
             "list_build_ms_wall": dt_build * 1e3, "list_build_gpu_phases_ms": {k: round(v, 4) for k, v in phases.items()},
             "list_build_ms_host_builder": w.t_host_lists * 1e3,
             "force_pass_ms_on_gpu_lists": k_ms, "n_walks": int(sz[0]), "n_cells": int(sz[5]),
             "neighbour_pairs": int(n_pairs.value),
-            "api": "gplum_b200_tree_build_gpu + walks_run + correct_long_run + walks_download + correct_long_download, "
-                   "pinned host buffers"}
+            "api": "gplum_b200_tree_build_gpu + walks_run + correct_long_run + walks_download + "
+                   "correct_long_download_compact, pinned host buffers"}
 
 
 def resident_step_leg(args, w, F, S, L, check):

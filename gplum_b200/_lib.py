@@ -64,6 +64,7 @@ SYMBOLS = {
     "gplum_b200_soft_corr_enable": (_i, [_i, _ll]),
     "gplum_b200_correct_long_run": (_i, [_i, _vp, _i]),
     "gplum_b200_correct_long_download": (_i, [_i, _vp, _vp, _vp, _ll, C.POINTER(_ll), C.POINTER(_ll)]),
+    "gplum_b200_correct_long_download_compact": (_i, [_i, _vp, _ll, C.POINTER(_ll), _vp, _ll, C.POINTER(_ll), C.POINTER(_ll)]),
     "gplum_b200_correct_long_time": (_i, [_i, _vp, _i, _i, C.POINTER(_f)]),
 }
 

@@ -95,7 +95,7 @@ struct WalkSet {
     std::vector<int> sub_w0;                     // first walk of each sub-batch (+ n_walk at the end)
     std::vector<cudaEvent_t> ev_in, ev_k, ev_out;
     // changeover correction (soft_corr.cu): candidate capture of the last pass + work/result buffers
-    DevBuf self_adr, pairs, corr_meta, cnt, off, cursor, csr, corr_out, corr_init, ngb, scan_temp;
+    DevBuf self_adr, pairs, corr_meta, cnt, off, cursor, csr, corr_out, corr_init, ngb, scan_temp, corr_compact;
     unsigned int pair_cap = 0;
     bool captured = false, corrected = false, corrected_initial = false;
     void release()
@@ -103,7 +103,7 @@ struct WalkSet {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
         for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force,
-                          &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp})
+                          &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp, &corr_compact})
             b->release();
         h_force.release(); h_stage.release();
     }
@@ -1155,6 +1155,54 @@ int gplum_b200_correct_long_download(int slot, void *corr_out, void *init_out, v
         if (total > ngb_cap) return fail(GPLUM_B200_ERR_ARG, "ngb_out holds %lld entries, %d needed", ngb_cap, total);
         CU(cudaMemcpy(ngb_out, ws.ngb.p, (size_t)total * sizeof(SoftNgb), cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+// Like correct_long_download, but only the particles that have neighbours cross PCIe (stable order);
+// corr_out holds room for corr_cap records, *n_corr receives how many were written.
+int gplum_b200_correct_long_download_compact(int slot, void *corr_out, long long corr_cap, long long *n_corr,
+                                             void *ngb_out, long long ngb_cap, long long *n_ngb_slots, long long *n_pairs)
+{
+    if (int r = ensure_init()) return r;
+    if (slot < 0 || slot >= N_TAG || !corr_out || !n_corr) return fail(GPLUM_B200_ERR_ARG, "correct_long_download_compact: bad argument");
+    WalkSet &ws = g.slots[slot];
+    if (!ws.corrected) return fail(GPLUM_B200_ERR_STATE, "correct_long_download_compact before correct_long_run");
+    CU(cudaSetDevice(g.device));
+    const int n = (int)ws.n_epi;
+    *n_corr = 0;
+    if (n_ngb_slots) *n_ngb_slots = 0;
+    if (n_pairs) *n_pairs = 0;
+    if (n == 0) return 0;
+    cudaStream_t st = g.stream;
+    const size_t tb = soft_corr_compact_temp_bytes(n);
+    if (int r = ws.scan_temp.reserve(tb)) return r;
+    if (int r = ws.corr_compact.reserve((size_t)n * sizeof(SoftCorr) + 16)) return r;
+    int *d_cnt = (int *)((char *)ws.corr_compact.p + (size_t)n * sizeof(SoftCorr));
+    const int e = soft_corr_compact(n, (const SoftCorr *)ws.corr_out.p, (SoftCorr *)ws.corr_compact.p, d_cnt, ws.scan_temp.p, ws.scan_temp.cap, st);
+    if (e) return fail(GPLUM_B200_ERR_CUDA, "soft_corr_compact -> %s", cudaGetErrorString((cudaError_t)e));
+    g.launches++;
+    unsigned int meta[4] = {0, 0, 0, 0};
+    int total = 0, m = 0;
+    CU(cudaMemcpyAsync(meta, ws.corr_meta.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&total, (const int *)ws.off.p + n, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&m, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_pairs) *n_pairs = meta[0];
+    if (meta[1] > 0)
+        return fail(GPLUM_B200_ERR_OVERFLOW, "%u candidate pairs dropped: pair buffer holds %u, pass produced %u", meta[1], ws.pair_cap, meta[0]);
+    if (meta[2] > 0)
+        return fail(GPLUM_B200_ERR_STATE, "%u i-particles are not in their own EP list (not an FDPS interaction list)", meta[2]);
+    if ((long long)total != (long long)meta[0])
+        return fail(GPLUM_B200_ERR_STATE, "candidate counts (%d) and captured pairs (%u) disagree", total, meta[0]);
+    if (m > corr_cap) return fail(GPLUM_B200_ERR_ARG, "corr_out holds %lld records, %d needed", corr_cap, m);
+    *n_corr = m;
+    if (n_ngb_slots) *n_ngb_slots = total;
+    if (m > 0) CU(cudaMemcpyAsync(corr_out, ws.corr_compact.p, (size_t)m * sizeof(SoftCorr), cudaMemcpyDeviceToHost, st));
+    if (ngb_out && total > 0) {
+        if (total > ngb_cap) return fail(GPLUM_B200_ERR_ARG, "ngb_out holds %lld entries, %d needed", ngb_cap, total);
+        CU(cudaMemcpyAsync(ngb_out, ws.ngb.p, (size_t)total * sizeof(SoftNgb), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
     return 0;
 }
 

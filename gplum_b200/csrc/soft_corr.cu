@@ -14,6 +14,7 @@
 // terms cancel (rinv*W - r_min, r3inv*K - r_min^3).
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <stdint.h>
 
 #include "soft_corr.h"
@@ -234,6 +235,23 @@ int soft_corr_launch(const SoftCorrArgs &a, void *scan_temp, size_t scan_temp_by
     corr_apply_kernel<<<(a.n_epi + 127) / 128, 128, 0, st>>>(a);
     if (launches) *launches += 4;      // count, scan (CUB, >= 1 kernel), scatter, apply
     return (int)cudaGetLastError();
+}
+
+// ---- compact result: only the particles that have neighbours (the others carry the self term alone:
+// acc = 0, phi = m / r_out, acc0 = 0, id_cluster = id, number = 0), in walk order (stable select) ----
+struct HasNeighbour { __host__ __device__ bool operator()(const SoftCorr &c) const { return c.number > 0; } };
+
+size_t soft_corr_compact_temp_bytes(int n_epi)
+{
+    size_t bytes = 0;
+    cub::DeviceSelect::If(nullptr, bytes, (const SoftCorr *)nullptr, (SoftCorr *)nullptr, (int *)nullptr, n_epi, HasNeighbour());
+    return bytes;
+}
+
+int soft_corr_compact(int n_epi, const SoftCorr *corr, SoftCorr *out, int *n_out_dev, void *temp, size_t temp_bytes, cudaStream_t st)
+{
+    if (n_epi <= 0) return 0;
+    return (int)cub::DeviceSelect::If(temp, temp_bytes, corr, out, n_out_dev, n_epi, HasNeighbour(), st);
 }
 
 }  // namespace gb

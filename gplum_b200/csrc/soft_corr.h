@@ -28,6 +28,9 @@ struct SoftCorrArgs {
 };
 
 size_t soft_corr_scan_temp_bytes(int n_epi);
+size_t soft_corr_compact_temp_bytes(int n_epi);
+// out[0 .. *n_out_dev) = the records of corr with number > 0, order kept; returns the CUDA error (0 = ok)
+int soft_corr_compact(int n_epi, const SoftCorr *corr, SoftCorr *out, int *n_out_dev, void *temp, size_t temp_bytes, cudaStream_t st);
 int soft_corr_launch(const SoftCorrArgs &a, void *scan_temp, size_t scan_temp_bytes, cudaStream_t st, int *launches);
 
 }  // namespace gb

@@ -159,6 +159,18 @@ def correct_long_download(n_epi, initial=False, slot=0, ngb_cap=None):
     return corr, init, ngb[:n_slots.value]
 
 
+def correct_long_download_compact(n_epi, slot=0, corr_cap=None, ngb_cap=None):
+    """(corr[m], ngb): only the particles with neighbours (walk order); the rest carry the self term alone."""
+    cc = int(corr_cap) if corr_cap is not None else n_epi
+    corr = np.zeros(cc, dtype=S.CORR)
+    cap = int(ngb_cap) if ngb_cap is not None else 4 * n_epi + (1 << 20)
+    ngb = np.zeros(cap, dtype=S.NGB)
+    m, n_slots, n_pairs = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+    check(lib().gplum_b200_correct_long_download_compact(int(slot), _p(corr), cc, C.byref(m), _p(ngb), cap,
+                                                         C.byref(n_slots), C.byref(n_pairs)))
+    return corr[:m.value], ngb[:n_slots.value]
+
+
 def correctForceLong(w, prm, initial=False):
     """Tree force + changeover correction of the walks `w` through host buffers: returns
     (force, corr, init, ngb).  The reference: calcForceAllAndWriteBack followed by

@@ -177,6 +177,11 @@ int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int
  * NULL.  ngb_cap = capacity of ngb_out in entries. */
 int gplum_b200_correct_long_download(int slot, void *corr_out, void *init_out, void *ngb_out,
                                      long long ngb_cap, long long *n_ngb_slots, long long *n_pairs);
+/* Same, but only the records of particles that HAVE neighbours are copied (in walk order); every other particle
+ * carries the self term alone (acc = 0, phi = mass / r_out, acc0 = 0, id_cluster = id, number = 0,
+ * src/gravity_soft.h:280,368), which the caller applies itself.  *n_corr = records written (<= corr_cap). */
+int gplum_b200_correct_long_download_compact(int slot, void *corr_out, long long corr_cap, long long *n_corr,
+                                             void *ngb_out, long long ngb_cap, long long *n_ngb_slots, long long *n_pairs);
 /* mean milliseconds of `iters` correction launches (CUDA events on the library stream) */
 int gplum_b200_correct_long_time(int slot, const gplum_b200_corr_params *prm, int initial, int iters, float *ms);
 

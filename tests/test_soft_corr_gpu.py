@@ -124,3 +124,32 @@ def test_run_without_capture_fails_loudly():
     F.calc_walks(w)
     with pytest.raises(Exception, match="captured"):
         F.correct_long_run(z["long_prm"])
+
+
+def test_compact_download_equals_the_filtered_full_download():
+    """Only particles with neighbours cross PCIe; the others carry the self term alone (checked here too)."""
+    n = 8000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=3)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    w, order = tree.build_walks(d["pos"], d["mass"], ro, rs * 1.5, n_group_limit=64)
+    w.epj_all["id"] = np.arange(n) * 2 + 1
+    prm = S.corr_params()
+    F.soft_corr_enable(True)
+    try:
+        F.calc_walks(w)
+        F.correct_long_run(prm)
+        full, _, ngb = F.correct_long_download(n)
+        comp, ngb2 = F.correct_long_download_compact(n)
+    finally:
+        F.soft_corr_enable(False)
+    has = full["number"] > 0
+    assert 0 < has.sum() < n
+    assert comp.tobytes() == full[has].tobytes() and ngb2.tobytes() == ngb.tobytes()
+    rest = full[~has]
+    assert (rest["acc"] == 0).all() and (rest["acc0"] == 0).all()
+    lut = np.empty(n, np.int64); lut[w.epj_all["id_local"]] = np.arange(n)
+    k = lut[rest["id_local"]]
+    assert np.array_equal(rest["phi"], w.epj_all["mass"][k] * (1.0 / w.epj_all["r_out"][k]))
+    assert np.array_equal(rest["id_cluster"], w.epj_all["id"][k])
+    with pytest.raises(Exception, match="records"):
+        F.correct_long_download_compact(n, corr_cap=3)
