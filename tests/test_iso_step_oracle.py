@@ -66,3 +66,25 @@ def test_kepler_drift_conserves_the_orbit():
         period = 2 * np.pi * ax[i] ** 1.5
         p, v, *_ = O.kepler_isolated(c["pos"][i:i + 1], c["vel"][i:i + 1], [0.0], [0.0], [0.0], [1], 0.0, period, prm)
         assert np.abs(p - c["pos"][i]).max() < 1e-11 and np.abs(v - c["vel"][i]).max() < 1e-11
+
+
+@pytest.mark.skipif(not O.have_ref("scalar"), reason="oracle/_ref not built")
+def test_edge_orbits_equal_compiled_reference():
+    """Exactly circular (ecc == 0 takes the u = 0 branch of posVel2OrbitalElement), exactly at rest in the
+    frame (falls to the Sun: ecc = 1), unbound (ax < 0), softened Sun (eps2_sun != 0: nobody drifts on a
+    Kepler orbit), and a particle with neighbours."""
+    pos = np.array([[1.0, 0, 0], [0, 2.0, 0], [1.0, 0, 0], [0.7, 0.1, 0.01], [1.0, 0.5, 0.0]])
+    vel = np.array([[0, 1.0, 0], [-np.sqrt(0.5), 0, 0], [0, 0, 0], [0, 2.5, 0], [0.1, 0.9, 0.02]])
+    n = len(pos)
+    args = (np.zeros(n), np.array([0.0, 2.0 ** -9, 0.0, 0.0, 2.0 ** -12]), np.full(n, 1e-5), np.array([1, 1, 1, 1, 0]), 0.0, 2.0 ** -6)
+    for eps2_sun in (0.0, 1e-8):
+        prm = O.iso_params(eps2_sun=eps2_sun)
+        a = O.kepler_isolated(pos, vel, *args, prm)
+        b = O.kepler_isolated(pos, vel, *args, prm, lib="scalar")
+        for x, y, name in zip(a, b, ("pos", "vel", "time", "dt", "star", "handled")):
+            assert x.tobytes() == y.tobytes(), (name, eps2_sun)
+        if eps2_sun == 0.0:
+            assert a[5].tolist() == [1, 1, 0, 0, 0]
+            assert np.allclose(np.sqrt((a[0][0] ** 2).sum()), 1.0, rtol=1e-15)        # stays on the unit circle
+        else:
+            assert a[5].sum() == 0 and np.array_equal(a[0], pos)
