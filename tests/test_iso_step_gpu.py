@@ -78,6 +78,28 @@ def test_drift_vs_oracle(n, seed, t0):
     check_drift(got, *want, c)
 
 
+def test_edge_orbits():
+    """Exactly circular (the ecc == 0 branch), free fall (ecc = 1), unbound, a particle with neighbours, and a
+    softened Sun (nobody takes the Kepler branch)."""
+    pos = np.array([[1.0, 0, 0], [0, 2.0, 0], [1.0, 0, 0], [0.7, 0.1, 0.01], [1.0, 0.5, 0.0]])
+    vel = np.array([[0, 1.0, 0], [-np.sqrt(0.5), 0, 0], [0, 0, 0], [0, 2.5, 0], [0.1, 0.9, 0.02]])
+    n = len(pos)
+    c = {"pos": pos, "vel": vel, "time": np.zeros(n), "dt": np.array([0.0, 2.0 ** -9, 0.0, 0.0, 2.0 ** -12]),
+         "acc0": np.full(n, 1e-5), "isolated": np.array([1, 1, 1, 1, 0], np.int32), "t0": 0.0, "t1": 2.0 ** -6}
+    for eps2_sun in (0.0, 1e-8):
+        want = O.kepler_isolated(pos, vel, c["time"], c["dt"], c["acc0"], c["isolated"], c["t0"], c["t1"],
+                                 O.iso_params(eps2_sun=eps2_sun))
+        epj = ST.make_epj(pos, vel, np.full(n, 1e-10), np.full(n, 1e-3), np.full(n, 1.2e-3))
+        ST.upload(epj, c["time"], c["dt"])
+        ST.drift(ST.iso_params(eps2_sun=eps2_sun), c["t0"], c["t1"], isolated=c["isolated"], acc0=c["acc0"])
+        got = ST.download(n)
+        assert got[4].tolist() == ([1, 1, 0, 0, 0] if eps2_sun == 0.0 else [0] * 5)
+        if eps2_sun == 0.0:
+            check_drift(got, *want, c)
+        else:
+            assert np.array_equal(got[0]["pos"], pos) and np.array_equal(got[0]["vel"], vel)
+
+
 def test_whole_resident_step_matches_the_host_sequence():
     """kick - drift - tree - force - correction - kick on the resident state against the same sequence
     assembled from parts that are pinned individually: oracle kick / drift on the host, the GPU force +
