@@ -488,7 +488,10 @@ template <int RMAX>
 __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass_kernel(const PassParams p, int n_items)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wid = threadIdx.x >> 5;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps &smem[warp] in a uniform
+    // register instead of re-deriving it from the thread id inside the pair loops (9 of 167 instructions of the
+    // EP-EP hot path at the 80-register cap; profiles/r1_force_pass_analysis.md)
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     using Smem = WarpSmem<32 * RMAX>;
     Smem &s = reinterpret_cast<Smem *>(smem_raw)[wid];
     const int item = blockIdx.x * WPB + wid;
