@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -98,6 +99,7 @@ struct WalkSet {
     DevBuf self_adr, pairs, corr_meta, cnt, off, cursor, csr, corr_out, corr_init, ngb, scan_temp, corr_compact;
     unsigned int pair_cap = 0;
     bool captured = false, corrected = false, corrected_initial = false;
+    bool corr_checked = false;                   // the status words of the last correction have been read and were clean
     void release()
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
@@ -229,6 +231,27 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
                 long long zero_e0 = -1, long long zero_e1 = -1)
 {
     if (n_items < 0) n_items = ws.n_items;
+    // the bookkeeping of a pass's first launch happens even when that launch is empty (a dispatch whose first
+    // sub-batch holds no i-particles): later sub-batches append to THIS pass's capture, not to the previous one's
+    if (first) {
+        ws.captured = false; ws.corrected = false; ws.corr_checked = false;
+        g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp;
+        if (g.corr_on && ws.n_epi > 0) {
+            const long long cap = g.corr_cap > 0 ? g.corr_cap : 4 * ws.n_epi + (1 << 20);
+            if (cap > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "pair capacity %lld exceeds 2^31", cap);
+            if (int r = ws.self_adr.reserve((size_t)ws.n_epi * 4)) return r;
+            if (int r = ws.pairs.reserve((size_t)cap * sizeof(int2))) return r;
+            if (int r = ws.corr_meta.reserve(16)) return r;
+            ws.pair_cap = (unsigned int)cap;
+            CU(cudaMemsetAsync(ws.self_adr.p, 0xff, (size_t)ws.n_epi * 4, st));
+            CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
+            // i-particles no walk covers keep number = 0 (and trip the "not in its own EP list" status) instead of
+            // feeding uninitialised counts into the correction's scan
+            if (!ws.has_split && zero_e0 < 0)
+                CU(cudaMemsetAsync(ws.force.p, 0, (size_t)ws.n_epi * sizeof(ForceAos), st));
+            ws.captured = true;
+        }
+    }
     if (n_items == 0) return 0;
     // split tiles add their halves into ForceGrav (kernels.cuh, `part`): start from zero.  Default: the whole set
     // when its list holds split tiles; dispatch() passes the i-range of a sub-batch instead.
@@ -247,29 +270,16 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
-    if (first) { ws.captured = false; ws.corrected = false; }
-    if (g.corr_on) {
-        if (first) {
-            const long long cap = g.corr_cap > 0 ? g.corr_cap : 4 * ws.n_epi + (1 << 20);
-            if (cap > 0x7fffffffLL) return fail(GPLUM_B200_ERR_ARG, "pair capacity %lld exceeds 2^31", cap);
-            if (int r = ws.self_adr.reserve((size_t)ws.n_epi * 4)) return r;
-            if (int r = ws.pairs.reserve((size_t)cap * sizeof(int2))) return r;
-            if (int r = ws.corr_meta.reserve(16)) return r;
-            ws.pair_cap = (unsigned int)cap;
-            CU(cudaMemsetAsync(ws.self_adr.p, 0xff, (size_t)ws.n_epi * 4, st));
-            CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
-        }
+    if (g.corr_on && ws.captured) {
         p.self_adr = (int *)ws.self_adr.p;
         p.pairs = (int2 *)ws.pairs.p;
         p.pair_count = (unsigned int *)ws.corr_meta.p;
         p.pair_cap = ws.pair_cap;
-        ws.captured = true;
     }
     if (g.rmax <= 2) force_pass_kernel<2><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
     else force_pass_kernel<4><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
     CU(cudaGetLastError());
     g.launches++;
-    if (first) { g.n_epep += ws.n_int_epep; g.n_epsp += ws.n_int_epsp; }
     return 0;
 }
 
@@ -1075,6 +1085,32 @@ int gplum_b200_pack_spj_dev(const void *spj_aos_dev, int n, void *spj_packed_dev
 }
 
 // ---- changeover correction (soft_corr.cu) ----
+namespace {
+// Reads the correction's status words (16 B, one stream sync; once per correction): dropped pairs and i-particles
+// missing from their own EP list make every consumer of corr_out fail, not only the download calls.
+int corr_status_check(WalkSet &ws, unsigned int *meta_out = nullptr, int *total_out = nullptr)
+{
+    unsigned int meta[4] = {0, 0, 0, 0};
+    int total = 0;
+    const int n = (int)ws.n_epi;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(meta, ws.corr_meta.p, 16, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaMemcpyAsync(&total, (const int *)ws.off.p + n, 4, cudaMemcpyDeviceToHost, g.stream));
+        CU(cudaStreamSynchronize(g.stream));
+    }
+    if (meta_out) memcpy(meta_out, meta, 16);
+    if (total_out) *total_out = total;
+    if (meta[1] > 0)
+        return fail(GPLUM_B200_ERR_OVERFLOW, "%u candidate pairs dropped: pair buffer holds %u, pass produced %u", meta[1], ws.pair_cap, meta[0]);
+    if (meta[2] > 0)
+        return fail(GPLUM_B200_ERR_STATE, "%u i-particles are not in their own EP list (not an FDPS interaction list)", meta[2]);
+    if ((long long)total != (long long)meta[0])
+        return fail(GPLUM_B200_ERR_STATE, "candidate counts (%d) and captured pairs (%u) disagree", total, meta[0]);
+    ws.corr_checked = true;
+    return 0;
+}
+}  // namespace
+
 int gplum_b200_soft_corr_enable(int on, long long pair_cap)
 {
     if (pair_cap < 0) return fail(GPLUM_B200_ERR_ARG, "pair_cap < 0");
@@ -1093,7 +1129,7 @@ int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int
         return fail(GPLUM_B200_ERR_STATE, "the correction needs the raw EPJGrav array of the pass on this device");
     CU(cudaSetDevice(g.device));
     const int n = (int)ws.n_epi;
-    if (n == 0) { ws.corrected = true; return 0; }
+    if (n == 0) { ws.corrected = true; ws.corr_checked = true; return 0; }
     if (int r = ws.cnt.reserve((size_t)(n + 1) * 4)) return r;
     if (int r = ws.off.reserve((size_t)(n + 1) * 4)) return r;
     if (int r = ws.cursor.reserve((size_t)(n + 1) * 4)) return r;
@@ -1119,7 +1155,7 @@ int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int
     const int e = soft_corr_launch(a, ws.scan_temp.p, ws.scan_temp.cap, g.stream, &launched);
     if (e) return fail(GPLUM_B200_ERR_CUDA, "soft_corr_launch -> %s", cudaGetErrorString((cudaError_t)e));
     g.launches += launched;
-    ws.corrected = true; ws.corrected_initial = initial != 0;
+    ws.corrected = true; ws.corrected_initial = initial != 0; ws.corr_checked = false;
     return 0;
 }
 
@@ -1138,18 +1174,11 @@ int gplum_b200_correct_long_download(int slot, void *corr_out, void *init_out, v
     if (n == 0) return 0;
     unsigned int meta[4] = {0, 0, 0, 0};
     int total = 0;
-    CU(cudaMemcpyAsync(meta, ws.corr_meta.p, 16, cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaMemcpyAsync(&total, (const int *)ws.off.p + n, 4, cudaMemcpyDeviceToHost, g.stream));
     if (corr_out) CU(cudaMemcpyAsync(corr_out, ws.corr_out.p, (size_t)n * sizeof(SoftCorr), cudaMemcpyDeviceToHost, g.stream));
     if (init_out) CU(cudaMemcpyAsync(init_out, ws.corr_init.p, (size_t)n * sizeof(SoftCorrInit), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
+    const int rs = corr_status_check(ws, meta, &total);
     if (n_pairs) *n_pairs = meta[0];
-    if (meta[1] > 0)
-        return fail(GPLUM_B200_ERR_OVERFLOW, "%u candidate pairs dropped: pair buffer holds %u, pass produced %u", meta[1], ws.pair_cap, meta[0]);
-    if (meta[2] > 0)
-        return fail(GPLUM_B200_ERR_STATE, "%u i-particles are not in their own EP list (not an FDPS interaction list)", meta[2]);
-    if ((long long)total != (long long)meta[0])
-        return fail(GPLUM_B200_ERR_STATE, "candidate counts (%d) and captured pairs (%u) disagree", total, meta[0]);
+    if (rs) return rs;
     if (n_ngb_slots) *n_ngb_slots = total;
     if (ngb_out && total > 0) {
         if (total > ngb_cap) return fail(GPLUM_B200_ERR_ARG, "ngb_out holds %lld entries, %d needed", ngb_cap, total);
@@ -1183,17 +1212,10 @@ int gplum_b200_correct_long_download_compact(int slot, void *corr_out, long long
     g.launches++;
     unsigned int meta[4] = {0, 0, 0, 0};
     int total = 0, m = 0;
-    CU(cudaMemcpyAsync(meta, ws.corr_meta.p, 16, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&total, (const int *)ws.off.p + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&m, d_cnt, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    const int rs = corr_status_check(ws, meta, &total);
     if (n_pairs) *n_pairs = meta[0];
-    if (meta[1] > 0)
-        return fail(GPLUM_B200_ERR_OVERFLOW, "%u candidate pairs dropped: pair buffer holds %u, pass produced %u", meta[1], ws.pair_cap, meta[0]);
-    if (meta[2] > 0)
-        return fail(GPLUM_B200_ERR_STATE, "%u i-particles are not in their own EP list (not an FDPS interaction list)", meta[2]);
-    if ((long long)total != (long long)meta[0])
-        return fail(GPLUM_B200_ERR_STATE, "candidate counts (%d) and captured pairs (%u) disagree", total, meta[0]);
+    if (rs) return rs;
     if (m > corr_cap) return fail(GPLUM_B200_ERR_ARG, "corr_out holds %lld records, %d needed", corr_cap, m);
     *n_corr = m;
     if (n_ngb_slots) *n_ngb_slots = total;
@@ -1463,6 +1485,7 @@ int gplum_b200_state_kick(int slot, int use_corr, double dt_tree)
     if (ws.n_epi != g.st_n) return fail(GPLUM_B200_ERR_STATE, "state_kick: walk set holds %lld i-particles, the state %d", ws.n_epi, g.st_n);
     if (use_corr && !ws.corrected) return fail(GPLUM_B200_ERR_STATE, "state_kick: no correction in slot %d", slot);
     CU(cudaSetDevice(g.device));
+    if (use_corr && !ws.corr_checked) if (int r = corr_status_check(ws)) return r;    // incomplete corrections must not be kicked in
     const int e = gbi::iso_kick(g.st_n, g.st_epj.p, ws.epi.p, ws.force.p, use_corr ? ws.corr_out.p : nullptr, 0.5 * dt_tree, g.stream);
     if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_kick -> %s", cudaGetErrorString((cudaError_t)e));
     g.launches++;
@@ -1474,6 +1497,10 @@ int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t
 {
     if (!g.ready || g.st_n <= 0) return fail(GPLUM_B200_ERR_STATE, "state_drift: no resident state");
     if (!prm) return fail(GPLUM_B200_ERR_ARG, "state_drift: NULL parameters");
+    // the reference's step-halving loop (src/hermite.h, `while (fmod(time, dt) != 0) dt *= 0.5`) never ends on
+    // these inputs; one host thread would hang there, here the whole stream would
+    if (!(prm->dt_tree > 0.0) || !std::isfinite(prm->dt_tree) || !std::isfinite(t0) || !std::isfinite(t1))
+        return fail(GPLUM_B200_ERR_ARG, "state_drift: dt_tree = %g, t0 = %g, t1 = %g (need dt_tree > 0 and finite times)", prm->dt_tree, t0, t1);
     CU(cudaSetDevice(g.device));
     cudaStream_t st = g.stream;
     const size_t N = (size_t)g.st_n;
@@ -1485,6 +1512,7 @@ int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t
         if (slot < 0 || slot >= N_TAG) return fail(GPLUM_B200_ERR_ARG, "state_drift(slot=%d)", slot);
         WalkSet &ws = g.slots[slot];
         if (!ws.corrected || ws.n_epi != g.st_n) return fail(GPLUM_B200_ERR_STATE, "state_drift: slot %d holds no correction of this state", slot);
+        if (!ws.corr_checked) if (int r = corr_status_check(ws)) return r;
         const int e = gbi::iso_flags_from_corr(g.st_n, ws.corr_out.p, (int *)g.st_iso.p, (double *)g.st_acc0.p, st);
         if (e) return fail(GPLUM_B200_ERR_CUDA, "iso_flags -> %s", cudaGetErrorString((cudaError_t)e));
         g.launches++;

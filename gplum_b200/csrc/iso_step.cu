@@ -166,15 +166,22 @@ __global__ void __launch_bounds__(TPB) drift_kernel(int n, EpjAos *__restrict__ 
             const double d1b = calc_dt2nd(prm.eta_sun0, prm.alpha2, 0., st.acc_s, st.jerk_s);
             const double dt_1 = (d1b < d1a) ? d1b : d1a;
             double rem = fmod(tm, dt_next);
-            while (rem != 0.0) { dt_next *= 0.5; rem = fmod(tm, dt_next); }
-            const double dt_old = dt_[k];
-            if (dt_old > 0.) while (2. * dt_old < dt_next) dt_next *= 0.5;
-            while (dt_1 < dt_next) dt_next *= 0.5;
-            if (dt_next < 2. * prm.dt_min) dt_next = prm.dt_min;
-            st.dt = dt_next;
-            for (int q = 0; q < 3; q++) { p.pos[q] = pos[q]; p.vel[q] = vel[q]; p.acc_d[q] = 0.; }
-            time_[k] = tm; dt_[k] = dt_next;
-            star[k] = st;
+            // the reference's loop has no bound: a NaN/Inf time (caller-supplied state) never satisfies it and
+            // would hang the stream.  2^-1100 underflows to zero, so a finite time leaves within 1100 halvings;
+            // anything else stays unhandled and goes to the host like a clustered particle.
+            int halvings = 0;
+            while (rem != 0.0 && halvings < 1100) { dt_next *= 0.5; rem = fmod(tm, dt_next); halvings++; }
+            if (rem != 0.0) h = 0;
+            else {
+                const double dt_old = dt_[k];
+                if (dt_old > 0.) while (2. * dt_old < dt_next) dt_next *= 0.5;
+                while (dt_1 < dt_next) dt_next *= 0.5;
+                if (dt_next < 2. * prm.dt_min) dt_next = prm.dt_min;
+                st.dt = dt_next;
+                for (int q = 0; q < 3; q++) { p.pos[q] = pos[q]; p.vel[q] = vel[q]; p.acc_d[q] = 0.; }
+                time_[k] = tm; dt_[k] = dt_next;
+                star[k] = st;
+            }
         }
     }
     handled[k] = h;

@@ -335,6 +335,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
             float T = -1.0f;                       // one threshold per lane: max over its i-slots and the tile's j
 #pragma unroll
             for (int r = 0; r < R; r++) T = fmaxf(T, (rs2i[r] < 0.0f) ? -1.0f : fmaxf(rs2i[r] * 1.0000153f, tmax));
+            unsigned int pend = 0u;                // blocks of UNROLL j of this tile in which this lane saw a candidate
 #pragma unroll 1
             for (int jj = j_first; jj < n_pad; jj += UNROLL * G) {
                 float rmin = 3.0e38f;
@@ -370,19 +371,29 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
                         for (int r = 0; r < R; r++) rmin = fminf(rmin, r2[r]);
                     }
                 }
-                const bool hit = rmin < T;
-                if (__any_sync(0xffffffffu, hit)) {
+                // candidate blocks are only noted here (one predicated OR); they are re-tested after the tile's
+                // pair loop, every lane on ITS OWN blocks.  A warp-wide re-test at this point would run for every
+                // block that holds one of the tile's own i-particles (each i meets itself at r2 == eps2): 16 warp-wide
+                // re-tests per 64-wide item instead of the 2-3 per lane the deferred form needs.
+                pend |= (rmin < T) ? (1u << (jj / UNROLL)) : 0u;
+            }
+            while (__any_sync(0xffffffffu, pend != 0u)) {
+                if (pend != 0u) {
+                    const int j0 = (__ffs(pend) - 1) * UNROLL;
+                    pend &= pend - 1u;
                     // exact re-test, reference evaluation order, no FMA contraction
+#pragma unroll 1
                     for (int u = 0; u < UNROLL; u++) {
-                        const int j = jj + u;
+                        const int j = j0 + u;
                         const float4 pj = s.j4[j];
+                        const float rs2j = s.ep.rs2[j];
 #pragma unroll
                         for (int r = 0; r < R; r++) {
                             const int il = lane + 32 * r;
                             const float dx = xi[r] - pj.x, dy = yi[r] - pj.y, dz = zi[r] - pj.z;
                             const float r2e = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)),
                                                                   __fmul_rn(dz, dz)), eps2);
-                            const float rs2 = fmaxf(rs2i[r], s.ep.rs2[j]);
+                            const float rs2 = fmaxf(rs2i[r], rs2j);
                             if (rs2i[r] >= 0.0f && r2e < rs2) {
                                 const int idj = s.ep.id[j], rkj = s.ep.rank[j];
                                 const int idi = s.i_id[il], rki = s.i_rank[il];

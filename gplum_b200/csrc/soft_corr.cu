@@ -85,12 +85,20 @@ __global__ void corr_scatter_kernel(const int2 *__restrict__ pairs, const unsign
                                     int *__restrict__ csr, unsigned int *__restrict__ status)
 {
     const unsigned int total = *pair_count;
-    const unsigned int n = min(total, pair_cap);
-    if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = total - n;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    // Overflow: off[] comes from ForceGrav::number (the true pair count) while csr / ngb hold pair_cap entries,
+    // so nothing may be scattered or applied; the host reports GPLUM_B200_ERR_OVERFLOW from status[0] and the
+    // caller enlarges the buffer and repeats the pass.
+    if (total > pair_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = total - pair_cap;
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[0] = 0;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
         const int2 pr = pairs[k];
         const int slot = atomicAdd(&cursor[pr.x], 1);
-        csr[off[pr.x] + slot] = pr.y;
+        const long long at = (long long)off[pr.x] + slot;
+        if (at >= 0 && at < (long long)pair_cap) csr[at] = pr.y;     // counts and pairs always agree for FDPS lists
+        else atomicAdd(&status[0], 1u);
     }
 }
 
@@ -115,16 +123,19 @@ __global__ void __launch_bounds__(128) corr_apply_kernel(SoftCorrArgs a)
     }
     const EpjAos *epj = (const EpjAos *)a.epj_aos;
     const int base = a.off[i];
-    const int n_cand = min(a.cursor[i], a.off[i + 1] - base);      // == ForceGrav::number unless pairs were dropped
+    const bool overflow = *a.pair_count > a.pair_cap || a.off[a.n_epi] < 0 || (unsigned int)a.off[a.n_epi] > a.pair_cap;
+    const int n_cand = overflow ? 0 : min(a.cursor[i], a.off[i + 1] - base);   // == ForceGrav::number
     SoftCorr out;
     out.id_local = ((const EpiAos *)a.epi)[i].id_local;
-    out.ngb_off = base;
+    out.ngb_off = overflow ? 0 : base;
     const int sa = a.self_adr[i];
-    if (sa < 0) {               // cannot happen with FDPS lists (a group's own particles are in its EP list)
-        atomicAdd(&a.status[1], 1u);
+    if (sa < 0 || overflow) {   // sa < 0 cannot happen with FDPS lists (a group's own particles are in its EP list);
+                                // overflow: neutral record, nothing outside the buffers is touched (scatter kernel)
+        if (!overflow) atomicAdd(&a.status[1], 1u);
         out.acc[0] = out.acc[1] = out.acc[2] = 0.; out.phi = 0.; out.acc0 = 0.;
         out.id_cluster = -1; out.number = 0; out.in_domain = 1;
         a.out[i] = out;
+        if (a.init_out) { SoftCorrInit ci = {}; a.init_out[i] = ci; }
         return;
     }
     const EpjAos self = epj[sa];
