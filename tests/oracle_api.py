@@ -117,6 +117,20 @@ def calc_walks(w, eps2, flags=CANONICAL, lib="oracle", n_threads=0, clear=True, 
     return f, n
 
 
+def calc_walks_abs(w, eps2=0.0, n_threads=0):
+    """Per i-particle sums of the pair terms' MAGNITUDES (FP64): (sum_j |f_ij|, sum_j |phi_ij|) -- the
+    conditioning of the force sums, used as the floor of the per-particle tolerance (synth.assert_force_close)."""
+    lib = oracle()
+    lib.oracle_calc_walks_abs.restype = None
+    lib.oracle_calc_walks_abs.argtypes = [_i] + [_vp] * 13 + [C.c_double, _i, _i]
+    n = len(w.epi)
+    sa, sp = np.zeros(n), np.zeros(n)
+    lib.oracle_calc_walks_abs(w.n_walk, _ptr(w.epi), _ptr(w.epi_off), _ptr(w.ni), _ptr(w.adr_epj), _ptr(w.epj_disp),
+                              _ptr(w.n_epj), _ptr(w.adr_spj), _ptr(w.spj_disp), _ptr(w.n_spj), _ptr(w.epj_all),
+                              _ptr(w.spj_all), _ptr(sa), _ptr(sp), float(eps2), int(w.quad), n_threads)
+    return sa, sp
+
+
 def ref_tree_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=64,
                    n_walk_limit=200, eps2=0.0, vel=None, kind="scalar", with_force=False):
     """Interaction lists produced by the reference's own FDPS tree (multi-walk-index interface)."""

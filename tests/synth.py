@@ -39,18 +39,34 @@ def make_group(ni, nj, ns, seed=0, box=0.02, r_out=2.0e-3, spread_sp=0.5, n_rank
     return epi, epj, spj
 
 
-def assert_force_close(got, want, rtol=1e-4, what=""):
+COND_K = 8.0      # floor of the per-particle tolerance in units of 2^-24 * sum_j |f_ij| (see assert_force_close)
+
+
+def assert_force_close(got, want, rtol=1e-4, what="", cond=None):
     """acc / phi within rtol of |acc| and |phi| per particle; neighbour info bit-exact
-    (rank compared as rank==0, the only way the reference reads it: src/particle.h:67)."""
+    (rank compared as rank==0, the only way the reference reads it: src/particle.h:67).
+
+    cond = (sum_j |f_ij|, sum_j |phi_ij|) from oracle_api.calc_walks_abs switches on the conditioning floor the
+    large-N tests need: tolerance_i = max(rtol * |acc_i|, COND_K * 2^-24 * sum_j |f_ij|).  Every FP32 evaluation
+    of the reference's kernel rounds each pair term to ~2^-24 of its size; the reference's own two CPU variants (DSL
+    order vs fallback order of dx^2+dy^2+dz^2) differ by up to 4.5 * 2^-24 * sum|f| per particle = 0.95e-4 of |acc|
+    on a 3e5-particle disk (tests/test_oracle_vs_ref.py::test_fp32_noise_floor_of_the_reference_variants).  The
+    floor only exceeds rtol * |acc| for particles whose force sum cancels below 1/210 of its terms."""
     import numpy as np
     assert len(got) == len(want)
     an = np.linalg.norm(want["acc"].astype(np.float64), axis=1)
     da = np.linalg.norm(got["acc"].astype(np.float64) - want["acc"].astype(np.float64), axis=1)
     scale = np.maximum(an, 1e-30)
-    assert (da <= rtol * scale).all(), "%s acc rel err max %.3e" % (what, (da / scale).max())
+    tol = rtol * scale
+    if cond is not None:
+        tol = np.maximum(tol, COND_K * 2.0 ** -24 * cond[0])
+    assert (da <= tol).all(), "%s acc err / tolerance max %.3f (rel err max %.3e)" % (what, (da / tol).max(), (da / scale).max())
     dp = np.abs(got["phi"].astype(np.float64) - want["phi"].astype(np.float64))
     ps = np.maximum(np.abs(want["phi"].astype(np.float64)), 1e-30)
-    assert (dp <= rtol * ps).all(), "%s phi rel err max %.3e" % (what, (dp / ps).max())
+    tolp = rtol * ps
+    if cond is not None:
+        tolp = np.maximum(tolp, COND_K * 2.0 ** -24 * cond[1])
+    assert (dp <= tolp).all(), "%s phi rel err max %.3e" % (what, (dp / ps).max())
     for k in ("number", "id_max", "id_min"):
         bad = np.nonzero(got[k] != want[k])[0]
         assert len(bad) == 0, "%s %s differs at %s: got %s want %s" % (what, k, bad[:5], got[k][bad[:5]], want[k][bad[:5]])

@@ -148,6 +148,7 @@ def test_pipelined_dispatch_many_sub_batches_and_tags():
     w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=256)
     F.set_params(0.0, True, 0)
     want, _ = O.calc_walks(w, 0.0, n_threads=0)
+    cond = O.calc_walks_abs(w, 0.0)          # 3e5 particles: some force sums cancel to 1e-3 of their terms
     half = w.n_walk // 2
     force = S.cleared_force(n)
     force["acc"] = -0.5 * want["acc"]; force["phi"] = 0.25 * want["phi"]
@@ -172,7 +173,7 @@ def test_pipelined_dispatch_many_sub_batches_and_tags():
     added["number"] = force["number"] - start["number"]
     added["rank"] = force["rank"] - start["rank"]
     added["id_max"] = want["id_max"]; added["id_min"] = want["id_min"]
-    synth.assert_force_close(added, want, RTOL, "pipelined dispatch, accumulated part vs oracle")
+    synth.assert_force_close(added, want, RTOL, "pipelined dispatch, accumulated part vs oracle", cond=cond)
     assert np.array_equal(force["id_max"], np.maximum(start["id_max"], want["id_max"]))
     assert np.array_equal(force["id_min"], np.minimum(start["id_min"], want["id_min"]))
     # and the overwrite mode FDPS's clear=true corresponds to
@@ -187,10 +188,10 @@ def test_pipelined_dispatch_many_sub_batches_and_tags():
         F.retrieve(2, [out[w.epi_off[k]:w.epi_off[k] + w.ni[k]] for k in ws])
     finally:
         F.set_params(0.0, True, 0)
-    synth.assert_force_close(out, want, RTOL, "pipelined dispatch (overwrite) vs oracle")
+    synth.assert_force_close(out, want, RTOL, "pipelined dispatch (overwrite) vs oracle", cond=cond)
     assert np.array_equal(out["rank"] == 0, want["rank"] == 0)
     # the flat pass of the same lists: same bar against the oracle
-    synth.assert_force_close(F.calc_walks(w), want, RTOL, "flat pass vs oracle")
+    synth.assert_force_close(F.calc_walks(w), want, RTOL, "flat pass vs oracle", cond=cond)
 
 
 def test_force_parity_at_the_benchmark_configuration():
@@ -205,12 +206,19 @@ def test_force_parity_at_the_benchmark_configuration():
     ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
     w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, theta=0.5, n_leaf_limit=8, n_group_limit=512)
     want, n_int = O.calc_walks(w, 0.0, n_threads=0)
+    cond = O.calc_walks_abs(w, 0.0)
     F.set_params(0.0, True, 0)
     F.walks_upload(w)
     F.walks_run(repack=True)
     got = F.walks_download(n)
     assert n_int == sum(w.n_interactions())
-    synth.assert_force_close(got, want, RTOL, "N=1e6 g=512 resident pass")
+    synth.assert_force_close(got, want, RTOL, "N=1e6 g=512 resident pass", cond=cond)
+    # how much of the disk needs the conditioning floor at all, and how far the plain bar is missed
+    an = np.linalg.norm(want["acc"].astype(np.float64), axis=1)
+    rel = np.linalg.norm(got["acc"].astype(np.float64) - want["acc"], axis=1) / an
+    print("N=1e6 g=512: rel err of acc vs oracle: max %.3e, 99.99%% %.3e, particles above 1e-4: %d of %d"
+          % (rel.max(), np.quantile(rel, 0.9999), int((rel > RTOL).sum()), n))
+    assert (rel > RTOL).sum() <= 1e-4 * n and rel.max() < 1e-3
     assert want["number"].sum() > 50000          # the disk has real neighbour pairs: the exact path is exercised
     # one rank's share of an 8-way run: a pass with less than one wave of items (split work list)
     m = w.n_walk // 8
@@ -220,7 +228,7 @@ def test_force_parity_at_the_benchmark_configuration():
     F.walks_run(repack=False)
     n_sub = int((sub.epi_off + sub.ni).max())
     got8 = F.walks_download(n_sub)
-    synth.assert_force_close(got8, want[:n_sub], RTOL, "N=1e6 g=512, 1/8 shard (split items)")
+    synth.assert_force_close(got8, want[:n_sub], RTOL, "N=1e6 g=512, 1/8 shard (split items)", cond=(cond[0][:n_sub], cond[1][:n_sub]))
 
 
 def test_device_resident_pass_and_counters():
