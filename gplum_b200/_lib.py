@@ -44,9 +44,6 @@ SYMBOLS = {
     "gplum_b200_set_stream": (_i, [_vp]),
     "gplum_b200_synchronize": (_i, []),
     "gplum_b200_counters": (None, [C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), _i]),
-    "gplum_b200_tree_build": (_i, [_i, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _vp]),
-    "gplum_b200_tree_copy": (_i, [_vp] * 11 + [_i, _i, _vp]),
-    "gplum_b200_tree_free": (None, []),
     "gplum_b200_tree_build_gpu": (_i, [_i, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _vp]),
     "gplum_b200_tree_build_gpu_epj": (_i, [_i, _vp, _i, C.c_double, _i, _i, _vp]),
     "gplum_b200_tree_copy_gpu": (_i, [_vp] * 12),

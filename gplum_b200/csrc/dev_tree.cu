@@ -45,8 +45,9 @@ using gb::WorkItem;
 
 namespace {
 
-constexpr int MAX_LEVEL = 21;
-constexpr int N_LVL = MAX_LEVEL + 2;       // lvl_start[l] .. lvl_start[l+1] = cells of level l, l = 0..21
+constexpr int MAX_LEVEL = 42;              // TREE_LEVEL_LIMIT of FDPS's 128-bit key (FDPS/src/ps_defs.hpp:206)
+constexpr int LEVEL_HI = 21;               // levels 1..21 live in the sorted 63-bit key word, deeper ones are re-derived
+constexpr int N_LVL = MAX_LEVEL + 2;       // lvl_start[l] .. lvl_start[l+1] = cells of level l, l = 0..42
 constexpr int NB = 444;                    // blocks of the cooperative tree kernel (3 per SM on 148 SMs)
 constexpr int TPB = 256;
 constexpr int WALK_WPB = 8;                // warps per block of the walk kernels
@@ -71,7 +72,7 @@ struct Buf {
 
 // device-side scalars of a build
 struct Meta {
-    double org[3], inv, len;               // root cube: origin corner, 2^21 / len, edge length
+    double cen[3], hlen, nf, len;          // root cube: centre, half edge, (1 / edge) * 2^42, edge (FDPS/src/key.hpp:160-165)
     int lvl_start[N_LVL + 1];
     int fcount[N_LVL];                     // cells of level l that split
     int overflow;
@@ -122,15 +123,30 @@ __device__ __forceinline__ uint64_t spread3(uint64_t x)
     return x;
 }
 
-// ---- root cube: bbox of pos +- 1.1*r_search (FDPS/src/tree_for_force_impl.hpp:846-866) ----
+// 42-bit grid coordinates of a position (FDPS/src/key.hpp:166-181): (U64)((pos - centre + half) * nfactor), clamped
+__device__ __forceinline__ void grid_coords(const double *pos, const Meta *m, uint64_t c[3])
+{
+    const uint64_t nmax = (1ULL << MAX_LEVEL) - 1;
+    for (int k = 0; k < 3; k++) {
+        const double f = (pos[k] - m->cen[k] + m->hlen) * m->nf;
+        uint64_t v = f < 0.0 ? 0 : (f >= 9.2e18 ? nmax : (uint64_t)f);
+        c[k] = v > nmax ? nmax : v;
+    }
+}
+// the 21 levels below the sorted key word (FDPS's KeyT::lo_)
+__device__ __forceinline__ uint64_t key_lo(const uint64_t c[3])
+{
+    return spread3(c[0] & 0x1fffff) << 2 | spread3(c[1] & 0x1fffff) << 1 | spread3(c[2] & 0x1fffff);
+}
+
+// ---- root cube: bbox of the POSITIONS (FDPS/src/tree_for_force_impl.hpp:770-868; GetMyRSearch yields 0 for EPJGrav) ----
 __global__ void __launch_bounds__(TPB) bbox_kernel(const EpjAos *__restrict__ p, int n, double *__restrict__ part)
 {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
-        const double r = 1.1 * p[i].r_search * 1.000001;
         for (int k = 0; k < 3; k++) {
-            lo[k] = fmin(lo[k], p[i].pos[k] - r);
-            hi[k] = fmax(hi[k], p[i].pos[k] + r);
+            lo[k] = fmin(lo[k], p[i].pos[k]);
+            hi[k] = fmax(hi[k], p[i].pos[k]);
         }
     }
     __shared__ double sm[TPB / 32][6];
@@ -166,19 +182,21 @@ __global__ void bbox_final_kernel(const double *__restrict__ part, int n_part, K
     __syncthreads();
     if (threadIdx.x == 0) {
         const double *lo = sm, *hi = sm + 3;
-        double full = 0, cen[3];
-        for (int k = 0; k < 3; k++) { cen[k] = 0.5 * (lo[k] + hi[k]); full = fmax(full, hi[k] - lo[k]); }
+        double length = 0, cen[3], len_dim[3];
+        for (int k = 0; k < 3; k++) { cen[k] = (hi[k] + lo[k]) * 0.5; len_dim[k] = hi[k] - lo[k]; length = fmax(length, len_dim[k]); }
         // a dimension much thinner than the cube (a disk's z) is pushed wholly into one half
-        for (int k = 0; k < 3; k++) if (hi[k] - lo[k] < 0.1 * full) cen[k] -= (hi[k] - lo[k]) * 0.51;
-        double half = 0.5 * full * 1.000001;
-        if (half <= 0) half = 1.0;
-        const double len = 2.0 * half;
+        for (int k = 0; k < 3; k++) if (len_dim[k] < 0.1 * length) cen[k] -= len_dim[k] * 0.51;
+        length *= 1.000001;
+        if (!(length > 0)) length = 1.0;
+        const double hlen = length * 0.5;
         Meta *m = P.meta;
-        for (int k = 0; k < 3; k++) m->org[k] = cen[k] - half;
-        m->len = len;
-        m->inv = (double)(1u << MAX_LEVEL) / len;
-        // the root cell and the level table
-        for (int l = 0; l <= N_LVL; l++) m->lvl_start[l] = l == 0 ? 0 : 1;
+        for (int k = 0; k < 3; k++) m->cen[k] = cen[k];
+        m->hlen = hlen;
+        m->len = hlen * 2.0;
+        m->nf = (1.0 / (hlen * 2.0)) * (double)(1ULL << MAX_LEVEL);
+        // the root cell, FDPS's seven unused cells behind it (LinkCell: tc_array[1..7]) and the level table
+        for (int l = 0; l <= N_LVL; l++) m->lvl_start[l] = l == 0 ? 0 : 8;
+        for (int c = 1; c < 8; c++) P.c_meta[c] = make_int4(0, 0, -1, 0);
         for (int l = 0; l < N_LVL; l++) m->fcount[l] = 0;
         const bool root_splits = P.n > P.n_leaf;
         m->fcount[0] = root_splits ? 1 : 0;
@@ -194,13 +212,39 @@ __global__ void __launch_bounds__(TPB) key_kernel(const EpjAos *__restrict__ p, 
     const int i = blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     uint64_t c[3];
-    for (int k = 0; k < 3; k++) {
-        double f = (p[i].pos[k] - m->org[k]) * m->inv;
-        f = fmin(fmax(f, 0.0), (double)((1u << MAX_LEVEL) - 1));
-        c[k] = (uint64_t)f;
-    }
-    key[i] = spread3(c[0]) << 2 | spread3(c[1]) << 1 | spread3(c[2]);
+    grid_coords(p[i].pos, m, c);
+    key[i] = spread3(c[0] >> LEVEL_HI) << 2 | spread3(c[1] >> LEVEL_HI) << 1 | spread3(c[2] >> LEVEL_HI);   // KeyT::hi_
     idx[i] = i;
+}
+
+// FDPS sorts by (hi, lo); the radix sort above orders by hi only (stable: ties in particle order).  Particles that
+// share all 21 upper levels are closer than 2^-21 of the root edge -- rare --, so the runs of equal hi are put
+// into (lo, particle index) order here, one thread per run.
+__global__ void __launch_bounds__(TPB) tie_fix_kernel(const EpjAos *__restrict__ raw, int n, const Meta *__restrict__ m,
+                                                      const uint64_t *__restrict__ key, int *__restrict__ idx)
+{
+    const int i = blockIdx.x * TPB + threadIdx.x;
+    if (i >= n - 1) return;
+    const uint64_t k = key[i];
+    if (key[i + 1] != k || (i > 0 && key[i - 1] == k)) return;      // not the first element of a run of >= 2
+    int e = i + 2;
+    while (e < n && key[e] == k) e++;
+    for (int a = i + 1; a < e; a++) {                                // insertion sort of idx[i..e) by (lo, index)
+        const int va = idx[a];
+        uint64_t c[3];
+        grid_coords(raw[va].pos, m, c);
+        const uint64_t la = key_lo(c);
+        int b = a - 1;
+        while (b >= i) {
+            const int vb = idx[b];
+            grid_coords(raw[vb].pos, m, c);
+            const uint64_t lb = key_lo(c);
+            if (lb < la || (lb == la && vb < va)) break;
+            idx[b + 1] = vb;
+            b--;
+        }
+        idx[b + 1] = va;
+    }
 }
 
 // sorted EPJ (112 B records moved as 7 x 16 B) and the EPI of the same particle
@@ -249,11 +293,22 @@ __device__ __forceinline__ void child_range(const KP &P, const int *fr, int f, i
     const int end = first + n;
     ub = end;
     if (o < 7 && n > 0) {
-        const int shift = 3 * (MAX_LEVEL - 1 - L);
         int lo = first, hi = end;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((int)((P.key[mid] >> shift) & 7) <= o) lo = mid + 1; else hi = mid;
+        if (L < LEVEL_HI) {                                  // child level L+1 <= 21: a digit of the sorted key word
+            const int shift = 3 * (LEVEL_HI - 1 - L);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)((P.key[mid] >> shift) & 7) <= o) lo = mid + 1; else hi = mid;
+            }
+        } else {                                             // deeper (particles closer than 2^-21 of the root edge):
+            const int bit = MAX_LEVEL - 1 - L;               // the digit is re-derived from the position
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                uint64_t c[3];
+                grid_coords(P.epj[mid].pos, P.meta, c);
+                const int dg = (int)(((c[0] >> bit) & 1) << 2 | ((c[1] >> bit) & 1) << 1 | ((c[2] >> bit) & 1));
+                if (dg <= o) lo = mid + 1; else hi = mid;
+            }
         }
         ub = lo;
     }
@@ -312,7 +367,8 @@ __device__ __forceinline__ void moment_cell(const KP &P, int c)
                     }
                 }
             }
-            for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
+            { const double inv_m = 1.0 / mass;       // PS::F64vec / F64 multiplies by the reciprocal (FDPS/src/vector3.hpp:217-220)
+              for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] * inv_m : 0.0; }
             for (int i0 = m.x; i0 < end; i0 += 4) {
                 double mi[4], x[4][3];
 #pragma unroll
@@ -347,7 +403,8 @@ __device__ __forceinline__ void moment_cell(const KP &P, int c)
                 olo[0] = fmin(olo[0], b3.x); olo[1] = fmin(olo[1], b3.y); olo[2] = fmin(olo[2], b4.x);
                 ohi[0] = fmax(ohi[0], b4.y); ohi[1] = fmax(ohi[1], b5.x); ohi[2] = fmax(ohi[2], b5.y);
             }
-            for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] / mass : 0.0;
+            { const double inv_m = 1.0 / mass;       // PS::F64vec / F64 multiplies by the reciprocal (FDPS/src/vector3.hpp:217-220)
+              for (int k = 0; k < 3; k++) com[k] = (mass != 0.0) ? com[k] * inv_m : 0.0; }
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 const double2 a = __ldcg(cm0 + o * 5), b2 = __ldcg(cm0 + o * 5 + 1), q01 = __ldcg(cm0 + o * 5 + 2),
@@ -733,14 +790,15 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         *launches += 3;
         size_t tb = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t *)S.keys_a.p, (uint64_t *)S.keys_b.p,
-                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * MAX_LEVEL, st));
+                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * LEVEL_HI, st));
         CK(S.cub_temp.reserve(tb));
         CK(cub::DeviceRadixSort::SortPairs(S.cub_temp.p, tb, (const uint64_t *)S.keys_a.p, (uint64_t *)S.keys_b.p,
-                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * MAX_LEVEL, st));
+                                           (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * LEVEL_HI, st));
+        tie_fix_kernel<<<nblk(n, TPB), TPB, 0, st>>>(raw, n, P.meta, (const uint64_t *)S.keys_b.p, (int *)S.idx_b.p);
         gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)raw, (const int *)S.idx_b.p, n,
                                                                    (uint4 *)epj_sorted, (EpiAos *)epi);
         CK(cudaGetLastError());
-        *launches += 1;
+        *launches += 2;
         CK(cudaEventRecord(S.ev[1], st));
 
         // cells + moments: one cooperative launch; frontier arrays ping-pong, level 0's frontier is the root

@@ -1,12 +1,38 @@
-"""Interaction lists from the host-side builder in libgplum_b200.so (csrc/let_tree.cpp): the
-single-rank caller side of the force pass (FDPS semantics, own implementation)."""
+"""Interaction lists: from the host-side builder (libgplum_lists.so, csrc/let_tree.cpp -- workload tooling, FDPS's
+tree list for list) and from the GPU builder inside libgplum_b200.so (csrc/dev_tree.cu)."""
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import structs as S
 from ._lib import check, lib
 from .walks import Walks
+
+LISTS_PATH = os.environ.get("GPLUM_B200_LISTS_LIB", os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgplum_lists.so"))
+_lists = None
+
+
+def lists_lib():
+    """libgplum_lists.so (include/gplum_b200_lists.h): host code only, loads without a GPU."""
+    global _lists
+    if _lists is None:
+        if not os.path.exists(LISTS_PATH):
+            raise RuntimeError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'`" % LISTS_PATH)
+        h = C.CDLL(LISTS_PATH)
+        vp, i = C.c_void_p, C.c_int
+        h.gplum_b200_tree_build.restype = i
+        h.gplum_b200_tree_build.argtypes = [i, vp, vp, vp, vp, C.c_double, i, i, vp]
+        h.gplum_b200_tree_copy.restype = i
+        h.gplum_b200_tree_copy.argtypes = [vp] * 11 + [i, i, vp]
+        h.gplum_b200_tree_free.restype = None
+        _lists = h
+    return _lists
+
+
+def _check_lists(rc):
+    if rc != 0:
+        raise RuntimeError("libgplum_lists error %d" % rc)
 
 
 def _p(a):
@@ -22,8 +48,9 @@ def build_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_l
     r_out = np.ascontiguousarray(np.broadcast_to(r_out, (n,)), dtype=np.float64)
     r_search = np.ascontiguousarray(np.broadcast_to(r_search, (n,)), dtype=np.float64)
     sz = np.zeros(8, dtype=np.int64)
-    check(lib().gplum_b200_tree_build(n, _p(pos), _p(mass), _p(r_out), _p(r_search), float(theta),
-                                      int(n_leaf_limit), int(n_group_limit), _p(sz)))
+    L = lists_lib()
+    _check_lists(L.gplum_b200_tree_build(n, _p(pos), _p(mass), _p(r_out), _p(r_search), float(theta),
+                                         int(n_leaf_limit), int(n_group_limit), _p(sz)))
     nw = int(sz[0])
     epi = np.zeros(n, dtype=S.EPI)
     epj = np.zeros(n, dtype=S.EPJ)
@@ -33,9 +60,9 @@ def build_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_l
     ed = np.zeros(nw, np.int64); sd = np.zeros(nw, np.int64)
     ne = np.zeros(nw, np.int32); ns = np.zeros(nw, np.int32)
     order = np.zeros(n, np.int32)
-    check(lib().gplum_b200_tree_copy(_p(epi), _p(epi_off), _p(ni), _p(adr_e), _p(ed), _p(ne), _p(adr_s), _p(sd),
-                                     _p(ns), _p(epj), _p(spj), int(quad), int(rank), _p(order)))
-    lib().gplum_b200_tree_free()
+    _check_lists(L.gplum_b200_tree_copy(_p(epi), _p(epi_off), _p(ni), _p(adr_e), _p(ed), _p(ne), _p(adr_s), _p(sd),
+                                        _p(ns), _p(epj), _p(spj), int(quad), int(rank), _p(order)))
+    L.gplum_b200_tree_free()
     w = Walks(epi, epi_off, ni, adr_e, ed, ne, adr_s, sd, ns, epj, spj)
     assert w.n_interactions() == (int(sz[6]), int(sz[7]))
     return w, order

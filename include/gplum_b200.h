@@ -194,22 +194,8 @@ int gplum_b200_synchronize(void);
  * (sum ni*(n_epj+n_spj), FDPS's n_interaction_ep_ep_local_ + n_interaction_ep_sp_local_). */
 void gplum_b200_counters(long long *kernel_launches, long long *n_epep, long long *n_epsp, int reset);
 
-/* ---- host-side interaction-list builder (gplum_b200/csrc/let_tree.cpp) ----
- * The caller side of the path, single rank: Morton sort, octree (n_leaf_limit), moments, i-groups
- * (n_group_limit) and the symmetric-search tree walk, with the semantics of
- * FDPS/src/tree_walk.hpp:545-583,706-785 and tree_for_force_utils.hpp:619-650.  pos is [n][3].
- * sizes[8] = n_walk, n_epi, n_adr_epj, n_adr_spj, n_epj_all, n_spj_all, n_int_epep, n_int_epsp.
- * tree_copy writes the reference's AoS layouts; any output pointer may be NULL. */
-int gplum_b200_tree_build(int n, const double *pos, const double *mass, const double *r_out,
-                          const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
-                          long long *sizes);
-int gplum_b200_tree_copy(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,
-                         int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
-                         int quad, int rank, int *sorted_to_original);
-void gplum_b200_tree_free(void);
-
 /* ---- interaction-list builder on the GPU (gplum_b200/csrc/dev_tree.cu) ----
- * Same semantics, cell numbering and FP64 results as gplum_b200_tree_build, but every stage runs on the
+ * Same semantics, cell numbering and FP64 results as the host builder (include/gplum_b200_lists.h), but every stage runs on the
  * device: Morton keys, radix sort, cells level by level (FDPS LinkCell, tree_for_force_utils.hpp:289),
  * moments + in/out boxes bottom-up (utils_moment.hpp:6,189), i-groups (MakeIPGroup, utils.hpp:619-650),
  * one warp per group for the symmetric-search walk (tree_walk.hpp:545-583,706-785), work items.  The

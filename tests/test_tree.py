@@ -1,5 +1,5 @@
-"""Host-side interaction-list builder (csrc/let_tree.cpp): the guarantees the force pass relies
-on and agreement with the reference's FDPS tree.  CPU only."""
+"""Host-side interaction-list builder (csrc/let_tree.cpp, libgplum_lists.so): the guarantees the force pass
+relies on and identity, list for list, with the reference's FDPS tree.  CPU only."""
 import numpy as np
 import pytest
 
@@ -68,19 +68,75 @@ def test_quadrupole_moments_of_cells():
     assert np.allclose(root["quad"], q, rtol=1e-9, atol=1e-22)
 
 
+def _init3000():
+    """config 1's particles from the committed golden fixture (written by the compiled reference from
+    sample/INIT3000.dat): positions, masses and radii of the 3000 planetesimals, in FDPS's tree order."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init3000_g64.npz"))
+    e = z["epj_all"]
+    o = np.argsort(e["id_local"])
+    return e["pos"][o], e["mass"][o], e["r_out"][o], e["r_search"][o], z
+
+
 @pytest.mark.skipif(not O.have_ref("scalar"), reason="oracle/_ref not built")
-def test_statistics_match_reference_fdps_tree():
-    """Same group / list statistics as the reference's tree on the same disk (SURVEY 8a numbers)."""
-    d, ro, rs = _disk(20000, seed=6, a_in=0.9, a_out=1.1)
-    for g in (64, 512):
-        w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=g)
-        wr = O.ref_tree_walks(d["pos"], d["mass"], ro, rs, n_group_limit=g, vel=d["vel"])
-        assert abs(w.n_walk - wr.n_walk) <= 0.03 * wr.n_walk
-        a, b = w.n_interactions(), wr.n_interactions()
-        assert abs(a[0] - b[0]) <= 0.03 * b[0] and abs(a[1] - b[1]) <= 0.03 * b[1]
-        # and the forces the two list sets produce agree at tree-approximation level
-        f1, _ = O.calc_walks(w, 0.0); f2, _ = O.calc_walks(wr, 0.0)
-        a1 = np.zeros((20000, 3)); a2 = np.zeros((20000, 3))
-        a1[w.epi["id_local"]] = f1["acc"]; a2[wr.epi["id_local"]] = f2["acc"]
-        rel = np.linalg.norm(a1 - a2, axis=1) / np.linalg.norm(a2, axis=1)
-        assert np.median(rel) < 1e-3
+@pytest.mark.parametrize("case", ["init3000_g64", "disk20k_g64", "disk20k_g512", "disk20k_wide_rs", "disk5k_leaf4_theta03",
+                                  "disk3k_clumps_below_level_21"])
+def test_lists_identical_to_reference_fdps_tree(case):
+    """The host builder IS FDPS's tree, list for list: same particle order, same i-groups, the same EP and SP
+    index lists in the same order, the same cell numbering, and the same EPI / SPJ records bit for bit as the
+    reference's own TreeForForce (oracle/ref_shim.cpp: ref_tree_build drives calcForceAllAndWriteBackMultiWalkIndex
+    of the unmodified FDPS and records what it hands to the dispatch functor)."""
+    kw = dict(theta=0.5, n_leaf_limit=8, n_group_limit=64)
+    if case == "init3000_g64":
+        pos, mass, ro, rs, _ = _init3000()
+        vel = np.zeros_like(pos)
+    else:
+        n = 5000 if case.startswith("disk5k") else 20000
+        d, ro, rs = _disk(n, seed=6, a_in=0.9, a_out=1.1)
+        pos, mass, vel = d["pos"], d["mass"], d["vel"]
+        if case == "disk20k_g512":
+            kw["n_group_limit"] = 512
+        if case == "disk20k_wide_rs":
+            rs = rs * 3.0
+        if case == "disk5k_leaf4_theta03":
+            kw.update(theta=0.3, n_leaf_limit=4, n_group_limit=16)
+        if case == "disk3k_clumps_below_level_21":
+            # distinct particles closer than 2^-21 of the root edge: ordered and split by the LOWER word of FDPS's key
+            rng = np.random.default_rng(13)
+            pos, mass, vel, ro, rs = pos[:3000].copy(), mass[:3000], vel[:3000], ro[:3000], rs[:3000]
+            pos[100:130] = pos[100] + (rng.random((30, 3)) - 0.5) * 2e-9
+            pos[500:512] = pos[500] + (rng.random((12, 3)) - 0.5) * 1e-11
+            kw["n_group_limit"] = 32
+    w, order = tree.build_walks(pos, mass, ro, rs, **kw)
+    wr = O.ref_tree_walks(pos, mass, ro, rs, vel=vel, **kw)
+    assert w.n_walk == wr.n_walk and w.n_interactions() == wr.n_interactions()
+    assert np.array_equal(order, wr.epi["id_local"])
+    for k in ("epi_off", "ni", "n_epj", "n_spj", "epj_disp", "spj_disp", "adr_epj", "adr_spj"):
+        assert np.array_equal(getattr(w, k), getattr(wr, k)), k
+    assert w.epi.tobytes() == wr.epi.tobytes()
+    assert w.spj_all.tobytes() == wr.spj_all.tobytes()
+    for f in ("id_local", "myrank", "pos", "r_out", "r_search", "mass"):
+        assert np.array_equal(w.epj_all[f], wr.epj_all[f]), f
+    # hence the oracle's forces on the two list sets are the same bits
+    f1, _ = O.calc_walks(w, 0.0); f2, _ = O.calc_walks(wr, 0.0)
+    assert f1.tobytes() == f2.tobytes()
+
+
+@pytest.mark.skipif(not O.have_ref("scalar"), reason="oracle/_ref not built")
+def test_golden_init3000_lists_are_reproduced():
+    """The committed fixture of config 1 (lists recorded from the reference's tree) is what the host builder gives."""
+    pos, mass, ro, rs, z = _init3000()
+    w, _ = tree.build_walks(pos, mass, ro, rs, theta=0.5, n_leaf_limit=8, n_group_limit=64)
+    for k in ("epi_off", "ni", "n_epj", "n_spj", "adr_epj", "adr_spj"):
+        assert np.array_equal(getattr(w, k), z[k]), k
+    assert w.spj_all.tobytes() == z["spj_all"].tobytes()
+
+
+def test_lists_library_is_not_the_product_library():
+    """The host builder lives in libgplum_lists.so; libgplum_b200.so neither exports nor needs it."""
+    import ctypes as C
+    from gplum_b200 import _lib
+    assert tree.LISTS_PATH != _lib.LIB_PATH
+    h = C.CDLL(_lib.LIB_PATH)
+    for name in ("gplum_b200_tree_build", "gplum_b200_tree_copy", "gplum_b200_tree_free"):
+        assert hasattr(tree.lists_lib(), name) and not hasattr(h, name), name

@@ -73,7 +73,7 @@ def test_lists_equal_host_builder(n, group, leaf, theta, rs_scale, seed):
 
 
 def test_coincident_particles_reach_the_deepest_level():
-    """More than n_leaf_limit particles at one point: the cell chain runs to level 21 and ends in a big leaf."""
+    """More than n_leaf_limit particles at one point: the cell chain runs to level 42 (FDPS's TREE_LEVEL_LIMIT) and ends in a big leaf."""
     d, ro, rs = _disk(2000, seed=11)
     pos = d["pos"].copy()
     pos[100:140] = pos[100]
@@ -81,6 +81,24 @@ def test_coincident_particles_reach_the_deepest_level():
     sz = tree.build_walks_gpu(pos, d["mass"], ro, rs, n_group_limit=32)
     g, og = tree.copy_walks_gpu(sz)
     assert_same_walks(g, h, og, oh)
+
+
+def test_particles_closer_than_the_21_level_grid():
+    """Clumps of distinct particles closer than 2^-21 of the root edge share the sorted 63-bit key word: their order
+    comes from the lower 21 levels of FDPS's 128-bit key (tie_fix_kernel) and their cells from digits re-derived
+    from the positions, down to level 42."""
+    d, ro, rs = _disk(3000, seed=13)
+    rng = np.random.default_rng(13)
+    pos = d["pos"].copy()
+    pos[100:130] = pos[100] + (rng.random((30, 3)) - 0.5) * 2e-9          # root edge ~2 AU: 2^-21 of it is 1e-6
+    pos[500:512] = pos[500] + (rng.random((12, 3)) - 0.5) * 1e-11
+    pos[700:703] = pos[700]                                                # and exactly coincident ones
+    for group in (32, 4):
+        h, oh = tree.build_walks(pos, d["mass"], ro, rs, n_group_limit=group)
+        sz = tree.build_walks_gpu(pos, d["mass"], ro, rs, n_group_limit=group)
+        g, og = tree.copy_walks_gpu(sz)
+        assert_same_walks(g, h, og, oh)
+    assert len(h.spj_all) > 3000 * 0.7 + 8 * 20            # the clumps really made deep cell chains
 
 
 def test_monopole_spj_records():
