@@ -383,14 +383,19 @@ def main():
         k_ms = F.walks_time(max(3, args.steps), repack=False)      # CUDA events on the launching stream
     else:
         F.walks_select(0); k_int = F.walks_time(max(3, args.steps), repack=False)
-        F.walks_select(1); k_bnd = F.walks_time(max(3, args.steps), repack=False)
+        if args.exchange == "peer":
+            k_bnd = 0.0                     # one work list, one launch: interior and boundary items together
+        else:
+            F.walks_select(1); k_bnd = F.walks_time(max(3, args.steps), repack=False)
         k_ms = k_int + k_bnd
         # phase timings (this rank), for the scaling analysis: the all-gather alone, the two kernels alone
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ea.record(stream)
         for _ in range(10):
-            exchange().wait()
+            h = exchange()
+            if h is not None:
+                h.wait()
         eb.record(stream)
         torch.cuda.synchronize()
         my_step_ms = ms / args.steps

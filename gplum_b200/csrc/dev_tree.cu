@@ -25,6 +25,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/block/block_scan.cuh>
+#include <cub/block/block_reduce.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include <stdint.h>
 
@@ -41,6 +43,7 @@ using gb::EpiAos;
 using gb::EpjAos;
 using gb::SpjMonoAos;
 using gb::SpjQuadAos;
+using gb::BaseItem;
 using gb::WorkItem;
 
 namespace {
@@ -88,7 +91,7 @@ struct State {
     Buf bbox_part, meta, blk_cnt;
     Buf c_meta, c_mom, c_box, fr_a, fr_b, grp_at, walk_cell;
     Buf w_epi_off, w_ni, w_ne, w_ns, w_ed, w_sd, w_nitems, w_ioff;
-    Buf item_key_a, item_key_b, item_a;
+    Buf item_key_a, item_key_b, item_a, item_b, item_cum, item_seg;
     Meta *h_meta = nullptr;                // pinned
     Meta *h_meta_stamps = nullptr;         // = h_meta once a build has completed
     int coop_blocks = 0, cell_cap = 0, n = 0, n_walk = 0, n_cells = 0, n_levels = 0, lvl_start[N_LVL + 1] = {};
@@ -625,7 +628,7 @@ struct NonNeg { __host__ __device__ bool operator()(const int &v) const { return
 
 __global__ void __launch_bounds__(1024) totals_kernel(int n_walk, const int *__restrict__ ni, const int *__restrict__ ne,
                                                       const int *__restrict__ ns, Meta *m, long long warp_slots,
-                                                      int tile_cap, int jsplit, int rmax)
+                                                      int tile_cap, int jsplit, int rmax, int split_m)
 {
     long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // adr_epj, adr_spj, int_ee, int_es, items at cap 64..4
     for (int w = threadIdx.x; w < n_walk; w += 1024) {
@@ -643,6 +646,7 @@ __global__ void __launch_bounds__(1024) totals_kernel(int n_walk, const int *__r
         for (int k = 0; k < 9; k++) { t[k] = 0; for (int w = 0; w < 32; w++) t[k] += sm[w][k]; }
         m->n_adr_epj = t[0]; m->n_adr_spj = t[1]; m->n_int_epep = t[2]; m->n_int_epsp = t[3];
         m->cap = gb::tile_cap_choose(t + 4, warp_slots, tile_cap, jsplit != 0, rmax);
+        if (split_m > 0 && rmax == 2 && tile_cap == 0) m->cap = 64;      // a small pass is laid out in segments (items.h)
         m->n_walk = n_walk;
     }
 }
@@ -668,7 +672,7 @@ __device__ __forceinline__ uint64_t cost_key(double c) { return (uint64_t)__doub
 __global__ void __launch_bounds__(TPB) item_emit_kernel(int n_walk, const int *__restrict__ ni, const int *__restrict__ ne,
                                                         const int *__restrict__ ns, const int *__restrict__ ioff,
                                                         const Meta *__restrict__ m, int jsplit,
-                                                        WorkItem *__restrict__ items, uint64_t *__restrict__ keys)
+                                                        BaseItem *__restrict__ items, uint64_t *__restrict__ keys)
 {
     const int w = blockIdx.x * TPB + threadIdx.x;
     if (w >= n_walk) return;
@@ -677,9 +681,95 @@ __global__ void __launch_bounds__(TPB) item_emit_kernel(int n_walk, const int *_
     while (rem > 0) {
         int n, shape;
         gb::tile_next(rem, cap, jsplit != 0, n, shape);
-        items[k] = WorkItem{w, i0, n, gb::tile_cfg_of(shape)};
+        items[k] = BaseItem{w, i0, n, gb::tile_cfg_of(shape)};
         keys[k] = cost_key(gb::tile_cost(ne[w], ns[w], shape));
         rem -= n; i0 += n; k++;
+    }
+}
+
+// ---- base items (sorted, longest first) -> work items.  A pass with many items: one work item per base item. ----
+__global__ void __launch_bounds__(TPB) item_widen_kernel(int n, const BaseItem *__restrict__ base, WorkItem *__restrict__ out)
+{
+    const int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= n) return;
+    const BaseItem b = base[k];
+    out[k] = WorkItem{b.walk, b.i0, b.ni, b.cfg, 0, -1, 0, 0};
+}
+
+// A pass with less than two waves of items is laid out as one wave of equal segments (items.h: seg_cut_begin /
+// seg_cut_next, the same code the host work-list builder runs -> the same work list).  One block: the list is short
+// by definition.  out holds n_out_cap items; the ones behind the last part are empty (ni = 0).
+constexpr int SPLIT_TPB = 1024;
+__global__ void __launch_bounds__(SPLIT_TPB) item_split_kernel(int n, const BaseItem *__restrict__ base, const uint64_t *__restrict__ keys,
+                                                               const int *__restrict__ ne, const int *__restrict__ ns,
+                                                               long long n_seg, long long *__restrict__ cum, int *__restrict__ seg_of_item,
+                                                               WorkItem *__restrict__ out, int n_out_cap, int *__restrict__ seg_off)
+{
+    typedef cub::BlockScan<long long, SPLIT_TPB> ScanLL;
+    typedef cub::BlockScan<int, SPLIT_TPB> Scan;
+    __shared__ union { typename ScanLL::TempStorage l; typename Scan::TempStorage s; } tmp;
+    __shared__ long long s_runll;
+    __shared__ int s_run[3];
+    if (threadIdx.x == 0) { s_runll = 0; s_run[0] = s_run[1] = s_run[2] = 0; }
+    __syncthreads();
+    // pass 1: cost units before every base item, and their total
+    for (int b0 = 0; b0 < n; b0 += SPLIT_TPB) {
+        const int k = b0 + threadIdx.x;
+        const long long c = k < n ? gb::item_cost_units(__longlong_as_double((long long)keys[k])) : 0;
+        long long o, t;
+        ScanLL(tmp.l).ExclusiveSum(c, o, t);
+        if (k < n) cum[k] = o + s_runll;
+        __syncthreads();
+        if (threadIdx.x == 0) s_runll += t;
+        __syncthreads();
+    }
+    const long long W = s_runll;
+    // pass 2: count the parts of every item, scan, emit
+    for (int b0 = 0; b0 < n; b0 += SPLIT_TPB) {
+        const int k = b0 + threadIdx.x;
+        BaseItem b = BaseItem{0, 0, 0, 0};
+        int K = 0, e = 0, sp = 0;
+        long long C = 0, c = 0;
+        if (k < n) {
+            b = base[k];
+            e = ne[b.walk]; sp = ns[b.walk];
+            C = cum[k]; c = gb::item_cost_units(__longlong_as_double((long long)keys[k]));
+            gb::SegCut q;
+            gb::seg_cut_begin(q, W, n_seg, C, c, b.cfg, e, sp);
+            int t0, t1; long long sg;
+            while (gb::seg_cut_next(q, t0, t1, sg)) K++;
+        }
+        int o_item, o_slot, o_group, t_item, t_slot, t_group;
+        Scan(tmp.s).ExclusiveSum(K, o_item, t_item);
+        __syncthreads();
+        Scan(tmp.s).ExclusiveSum(K > 1 ? K : 0, o_slot, t_slot);
+        __syncthreads();
+        Scan(tmp.s).ExclusiveSum(K > 1 ? 1 : 0, o_group, t_group);
+        __syncthreads();
+        o_item += s_run[0]; o_slot += s_run[1]; o_group += s_run[2];
+        if (k < n) {
+            gb::SegCut q;
+            gb::seg_cut_begin(q, W, n_seg, C, c, b.cfg, e, sp);
+            int t0, t1; long long sg;
+            for (int p = 0; gb::seg_cut_next(q, t0, t1, sg); p++) {
+                if (o_item + p >= n_out_cap) break;
+                const bool whole = K == 1;
+                out[o_item + p] = WorkItem{b.walk, b.i0, b.ni, b.cfg | (whole ? 0 : (K << 8) | (p << 16)), whole ? 0 : t0, whole ? -1 : t1,
+                                           whole ? 0 : o_slot, whole ? 0 : o_group};
+                seg_of_item[o_item + p] = (int)sg;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_run[0] += t_item; s_run[1] += t_slot; s_run[2] += t_group; }
+        __syncthreads();
+    }
+    const int n_parts = min(s_run[0], n_out_cap);
+    for (int k = n_parts + threadIdx.x; k < n_out_cap; k += SPLIT_TPB) out[k] = WorkItem{0, 0, 0, 0, 0, 0, 0, 0};
+    // seg_off[s] = first part of segment s (segments are non-decreasing along the list)
+    for (long long sgm = threadIdx.x; sgm <= n_seg; sgm += SPLIT_TPB) {
+        int lo = 0, hi = n_parts;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg_of_item[mid] < (int)sgm) lo = mid + 1; else hi = mid; }
+        seg_off[sgm] = sgm == n_seg ? n_parts : lo;
     }
 }
 
@@ -722,7 +812,7 @@ void tree_release()
 {
     for (Buf *b : {&S.keys_a, &S.keys_b, &S.idx_a, &S.idx_b, &S.cub_temp, &S.bbox_part, &S.meta, &S.blk_cnt,
                    &S.c_meta, &S.c_mom, &S.c_box, &S.fr_a, &S.fr_b, &S.grp_at, &S.walk_cell, &S.w_epi_off, &S.w_ni, &S.w_ne,
-                   &S.w_ns, &S.w_ed, &S.w_sd, &S.w_nitems, &S.w_ioff, &S.item_key_a, &S.item_key_b, &S.item_a})
+                   &S.w_ns, &S.w_ed, &S.w_sd, &S.w_nitems, &S.w_ioff, &S.item_key_a, &S.item_key_b, &S.item_a, &S.item_b, &S.item_cum, &S.item_seg})
         b->release();
     if (S.h_meta) { cudaFreeHost(S.h_meta); S.h_meta = nullptr; S.h_meta_stamps = nullptr; }
     if (S.ev_ok) { for (auto &e : S.ev) cudaEventDestroy(e); S.ev_ok = false; }
@@ -850,7 +940,7 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb, ne_ll, (long long *)S.w_ed.p, nw, st));
         CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb, ns_ll, (long long *)S.w_sd.p, nw, st));
         totals_kernel<<<1, 1024, 0, st>>>(nw, (const int *)S.w_ni.p, (const int *)S.w_ne.p, (const int *)S.w_ns.p, P.meta,
-                                          cfg.warp_slots, cfg.tile_cap, cfg.jsplit, cfg.rmax);
+                                          cfg.warp_slots, cfg.tile_cap, cfg.jsplit, cfg.rmax, cfg.split_m);
         item_count_kernel<<<nblk(nw, TPB), TPB, 0, st>>>(nw, (const int *)S.w_ni.p, P.meta, cfg.jsplit, (int *)S.w_nitems.p);
         CK(cub::DeviceScan::ExclusiveSum(S.cub_temp.p, tb2, (const int *)S.w_nitems.p, (int *)S.w_ioff.p, nw, st));
         item_total_kernel<<<1, 1, 0, st>>>(nw, (const int *)S.w_nitems.p, (const int *)S.w_ioff.p, P.meta);
@@ -894,19 +984,29 @@ int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *la
         // work items, longest first (stable: equal costs keep walk order, as the host list does)
         const int nit = S.h_meta->n_items;
         CK(S.item_key_a.reserve((size_t)nit * 8 + 16)); CK(S.item_key_b.reserve((size_t)nit * 8 + 16));
-        CK(S.item_a.reserve((size_t)nit * sizeof(WorkItem) + 16));
+        CK(S.item_a.reserve((size_t)nit * sizeof(BaseItem) + 16)); CK(S.item_b.reserve((size_t)nit * sizeof(BaseItem) + 16));
         item_emit_kernel<<<nblk(nw, TPB), TPB, 0, st>>>(nw, (const int *)S.w_ni.p, (const int *)S.w_ne.p, (const int *)S.w_ns.p,
                                                         (const int *)S.w_ioff.p, (const Meta *)S.meta.p, cfg.jsplit,
-                                                        (WorkItem *)S.item_a.p, (uint64_t *)S.item_key_a.p);
+                                                        (BaseItem *)S.item_a.p, (uint64_t *)S.item_key_a.p);
         CK(cudaGetLastError());
         ++*launches;
         if (nit > 0) {
             size_t tb = 0;
             CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, (const uint64_t *)S.item_key_a.p, (uint64_t *)S.item_key_b.p,
-                                                         (const int4 *)S.item_a.p, (int4 *)out.items, nit, 0, 64, st));
+                                                         (const int4 *)S.item_a.p, (int4 *)S.item_b.p, nit, 0, 64, st));
             CK(S.cub_temp.reserve(tb));
             CK(cub::DeviceRadixSort::SortPairsDescending(S.cub_temp.p, tb, (const uint64_t *)S.item_key_a.p, (uint64_t *)S.item_key_b.p,
-                                                         (const int4 *)S.item_a.p, (int4 *)out.items, nit, 0, 64, st));
+                                                         (const int4 *)S.item_a.p, (int4 *)S.item_b.p, nit, 0, 64, st));
+            if (out.n_items_out > nit) {      // the caller sized `items` for a segmented list (items.h: split_items_bound)
+                CK(S.item_cum.reserve((size_t)nit * 8 + 16)); CK(S.item_seg.reserve((size_t)out.n_items_out * 4 + 16));
+                item_split_kernel<<<1, SPLIT_TPB, 0, st>>>(nit, (const BaseItem *)S.item_b.p, (const uint64_t *)S.item_key_b.p,
+                                                           (const int *)S.w_ne.p, (const int *)S.w_ns.p, cfg.warp_slots,
+                                                           (long long *)S.item_cum.p, (int *)S.item_seg.p,
+                                                           (WorkItem *)out.items, out.n_items_out, out.seg_off);
+            } else
+                item_widen_kernel<<<nblk(nit, TPB), TPB, 0, st>>>(nit, (const BaseItem *)S.item_b.p, (WorkItem *)out.items);
+            CK(cudaGetLastError());
+            ++*launches;
         }
     }
     if (S.n_cells > 0) {

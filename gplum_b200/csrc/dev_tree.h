@@ -13,7 +13,7 @@ struct TreeCfg {
     int n_leaf, n_group;
     int quad;                    // SPJ layout: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B)
     // work-list policy (items.h)
-    long long warp_slots; int tile_cap, jsplit, rmax;
+    long long warp_slots; int tile_cap, jsplit, rmax, split_m;
 };
 
 // totals of a build, valid on the host after phase1 returned
@@ -27,7 +27,10 @@ struct TreeOut {                 // destination buffers of phase 2 (sizes from T
     int *epi_off, *ni, *n_epj, *n_spj;           // n_walk (ni may be NULL)
     long long *epj_disp, *spj_disp;              // n_walk
     int *adr_epj, *adr_spj;                      // n_adr_epj, n_adr_spj
-    void *items;                                 // n_items x WorkItem (16 B)
+    void *items;                                 // n_items_out x WorkItem (32 B)
+    int n_items_out;                             // = TreeCounts::n_items (one work item per tile), or tree_items_bound() of a
+                                                 //   pass that splits its tiles along j (trailing entries are empty items)
+    int *seg_off;                                // warp_slots + 1 entries, written when the pass is laid out in segments
     void *spj_aos;                               // n_cells x (80 | 32) B
 };
 

@@ -82,13 +82,15 @@ struct PinBuf {
 // One set of walks resident on the device (a dispatch, a flat pass, or a per-call functor call)
 struct WalkSet {
     DevBuf epi, epi_off, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, items, force;
+    DevBuf scratch, arrive;      // partial sums and arrival counters of j-split tiles (items.h)
+    DevBuf seg_off;              // segments of a one-wave pass: warp s runs items [seg_off[s], seg_off[s+1]) (items.h)
+    int n_seg = 0;               // 0: one item per warp
     PinBuf h_force, h_stage;     // pinned: results, flattened inputs of dispatch()
     int n_walk = 0, n_items = 0;
     long long n_epi = 0, n_adr_epj = 0, n_adr_spj = 0;
     long long n_int_epep = 0, n_int_epsp = 0;
     std::vector<int> ni_host;                    // for retrieve()
     std::vector<long long> epi_off_host;
-    bool has_split = false;                      // the work list holds EP/SP-split tiles: launches start from a zeroed ForceGrav
     bool pending = false;
     cudaEvent_t done = nullptr;                  // recorded after the D2H of a dispatch: retrieve(tag) waits on it only
     // dispatch() pipeline: the walks of one dispatch are cut into sub-batches; sub-batch b's lists go up on the
@@ -104,7 +106,7 @@ struct WalkSet {
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
-        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force,
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &seg_off,
                           &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp, &corr_compact})
             b->release();
         h_force.release(); h_stage.release();
@@ -133,6 +135,7 @@ struct Peer {
     void *slab[2] = {nullptr, nullptr};               // this rank's own slabs (cudaMalloc)
     void *mapped[2][MAX_PEERS] = {};                    // every rank's slabs in this process' address space
     DevBuf table[2];                                    // device copies of mapped[b][0..world)
+    DevBuf done;                                        // block counter of peer_pack_kernel
 };
 
 struct Ctx {
@@ -154,8 +157,8 @@ struct Ctx {
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
-    int epsp_split = -1;        // EP/SP split of full-width tiles: -1 = passes with less than one wave of items, 0 = never,
-                                // 1 = always (GPLUM_B200_EPSP_SPLIT)
+    int split_m = 2;            // j-split of full-width tiles in passes with less than two waves of items: pieces per warp
+                                // slot (items.h); 0 = never (GPLUM_B200_SPLIT_M)
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
     long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
     DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
@@ -175,61 +178,117 @@ int ensure_init()
     return gplum_b200_init(env ? atoi(env) : 0, 0, 0);
 }
 
-// ---- work list: split every walk into i-tiles, choose a tile shape, longest first (items.h) ----
-// returns true when the list contains EP/SP-split tiles (their ForceGrav range must be zeroed before the launch)
-bool build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, std::vector<WorkItem> &items, int walk_base = 0,
-                 bool allow_split = true)
+// ---- work list: split every walk into i-tiles, choose a tile shape, longest first; a pass with few items also
+// cuts its full-width tiles along j (items.h).  n_slots / n_groups receive the scratch slots and arrival counters
+// the split tiles of this list need (numbered from slot_base / group_base).  peer_walk (optional, per walk): the
+// walk reads other ranks' particles -> its items wait for the peers' flags.
+struct ItemList {
+    std::vector<WorkItem> items;
+    std::vector<int> seg_off;          // empty: one item per warp; else warp s runs items [seg_off[s], seg_off[s+1])
+    int n_slots = 0, n_groups = 0;
+};
+void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, ItemList &out, int walk_base = 0,
+                 bool allow_split = true, int slot_base = 0, int group_base = 0, const unsigned char *peer_walk = nullptr)
 {
-    items.clear();
-    std::vector<std::pair<double, WorkItem>> tmp;
+    out.items.clear(); out.seg_off.clear(); out.n_slots = 0; out.n_groups = 0;
+    std::vector<std::pair<double, BaseItem>> tmp;
     tmp.reserve((size_t)n_walk * 2);
     const bool split = g.jsplit != 0;
     long long n_items_at[5] = {0, 0, 0, 0, 0};
     for (int w = 0; w < n_walk; w++)
         for (int k = 0; k < 5; k++) n_items_at[k] += (ni[w] + (64 >> k) - 1) / (64 >> k);
-    const int cap = tile_cap_choose(n_items_at, g.warp_slots, g.tile_cap, split, g.rmax);
+    int cap = tile_cap_choose(n_items_at, g.warp_slots, g.tile_cap, split, g.rmax);
+    // a pass that may be laid out in segments keeps the most efficient tile shape: the segments fill the GPU
+    if (allow_split && g.split_m > 0 && g.rmax == 2 && g.tile_cap == 0) cap = 64;
     for (int w = 0; w < n_walk; w++) {
         int rem = ni[w], i0 = 0;
         while (rem > 0) {
             if (g.rmax >= 3 && rem > 64) {                   // RMAX = 4 build: up to 128 i-particles per warp
                 const int n = std::min(rem, 128);
                 const int cfg = (n + 31) / 32 - 1;
-                tmp.push_back({tile_cost(n_epj[w], n_spj[w], 32 * (cfg + 1)), WorkItem{w, i0, n, cfg}});
+                tmp.push_back({tile_cost(n_epj[w], n_spj[w], 32 * (cfg + 1)), BaseItem{w, i0, n, cfg}});
                 rem -= n; i0 += n;
                 continue;
             }
             int n, shape;
             tile_next(rem, cap, split, n, shape);
-            tmp.push_back({tile_cost(n_epj[w], n_spj[w], shape), WorkItem{w, i0, n, tile_cfg_of(shape)}});
+            tmp.push_back({tile_cost(n_epj[w], n_spj[w], shape), BaseItem{w, i0, n, tile_cfg_of(shape)}});
             rem -= n; i0 += n;
         }
     }
-    // a pass with less than one wave of items: issue every full-width tile twice, EP tiles and SP tiles apart
-    // (twice the warps on the issue ports, half the serial chain per item; kernels.cuh, `part`)
-    bool has_split = false;
-    if (allow_split && g.rmax <= 2 && g.epsp_split != 0 && (g.epsp_split > 0 || (long long)tmp.size() < g.warp_slots)) {
-        const size_t n0 = tmp.size();
-        for (size_t k = 0; k < n0; k++) {
-            WorkItem it = tmp[k].second;
-            const int w = it.walk;
-            if (it.cfg > 1 || n_epj[w] == 0 || n_spj[w] == 0) continue;
-            const int shape = it.cfg == 1 ? 64 : 32;
-            tmp[k] = {tile_cost_ep(n_epj[w], shape), WorkItem{w, it.i0, it.ni, it.cfg | TILE_EP_ONLY}};
-            tmp.push_back({tile_cost_sp(n_spj[w], shape), WorkItem{w, it.i0, it.ni, it.cfg | TILE_SP_ONLY}});
-            has_split = true;
-        }
-    }
     std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
-    items.reserve(tmp.size());
-    for (auto &t : tmp) { t.second.walk += walk_base; items.push_back(t.second); }
-    return has_split;
+    const bool do_split = allow_split && g.rmax <= 2 && split_active((long long)tmp.size(), g.warp_slots, g.split_m);
+    if (!do_split) {
+        out.items.reserve(tmp.size());
+        for (auto &t : tmp) {
+            const BaseItem &b = t.second;
+            const int wait = (peer_walk && peer_walk[b.walk]) ? ITEM_PEER_WAIT : 0;
+            out.items.push_back(WorkItem{b.walk + walk_base, b.i0, b.ni, b.cfg | wait, 0, -1, 0, 0});
+        }
+        return;
+    }
+    // one wave of equal segments (items.h): cut the line of costs at every n_seg-th of its length, at j-tile boundaries
+    long long W = 0;
+    for (auto &t : tmp) W += item_cost_units(t.first);
+    const long long n_seg = g.warp_slots;
+    out.items.reserve(tmp.size() + (size_t)n_seg);
+    out.seg_off.assign((size_t)n_seg + 1, 0);
+    std::vector<int> seg_of_item;
+    seg_of_item.reserve(tmp.size() + (size_t)n_seg);
+    long long C = 0;
+    for (auto &t : tmp) {
+        const BaseItem &b = t.second;
+        const int w = b.walk;
+        const int wait = (peer_walk && peer_walk[w]) ? ITEM_PEER_WAIT : 0;
+        const long long c = item_cost_units(t.first);
+        struct Part { int t0, t1; long long seg; };
+        Part parts[SPLIT_K_MAX + 1];
+        int K = 0;
+        SegCut q;
+        seg_cut_begin(q, W, n_seg, C, c, b.cfg, n_epj[w], n_spj[w]);
+        for (int t0, t1; K <= SPLIT_K_MAX; K++) {
+            long long sg;
+            if (!seg_cut_next(q, t0, t1, sg)) break;
+            parts[K] = Part{t0, t1, sg};
+        }
+        for (int k = 0; k < K; k++) {
+            const bool whole = K == 1;
+            out.items.push_back(WorkItem{w + walk_base, b.i0, b.ni, b.cfg | wait | (whole ? 0 : (K << 8) | (k << 16)),
+                                         whole ? 0 : parts[k].t0, whole ? -1 : parts[k].t1,
+                                         whole ? 0 : slot_base + out.n_slots, whole ? 0 : group_base + out.n_groups});
+            seg_of_item.push_back((int)parts[k].seg);
+        }
+        if (K > 1) { out.n_slots += K; out.n_groups += 1; }
+        C += c;
+    }
+    // seg_off[s] = first item of segment s (segments are non-decreasing along the list)
+    {
+        size_t k = 0;
+        for (long long sgm = 0; sgm <= n_seg; sgm++) {
+            while (k < seg_of_item.size() && seg_of_item[k] < sgm) k++;
+            out.seg_off[(size_t)sgm] = (int)k;
+        }
+        out.seg_off[(size_t)n_seg] = (int)seg_of_item.size();
+    }
+}
+
+// scratch records and arrival counters of a walk set's split tiles (grow-only; counters start at zero and every
+// pass leaves them at zero)
+int reserve_split(WalkSet &ws, int n_slots, int n_groups, cudaStream_t st)
+{
+    if (int r = ws.scratch.reserve((size_t)std::max(n_slots, 1) * 64 * sizeof(ForceAos))) return r;
+    const size_t cap0 = ws.arrive.cap;
+    if (int r = ws.arrive.reserve((size_t)std::max(n_groups, 1) * 4)) return r;
+    if (ws.arrive.cap != cap0) CU(cudaMemsetAsync(ws.arrive.p, 0, ws.arrive.cap, st));
+    return 0;
 }
 
 // Launches the force kernel on items [item0, item0 + n_items) of the set (default: all).  `first` resets the
 // candidate capture and counts the pass's interactions; sub-batch launches of one pass pass first = false.
 int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_items = -1, bool first = true,
-                long long zero_e0 = -1, long long zero_e1 = -1)
+                int seg0 = 0, int n_seg = -1)
 {
+    if (n_seg < 0) n_seg = ws.n_seg;
     if (n_items < 0) n_items = ws.n_items;
     // the bookkeeping of a pass's first launch happens even when that launch is empty (a dispatch whose first
     // sub-batch holds no i-particles): later sub-batches append to THIS pass's capture, not to the previous one's
@@ -247,16 +306,11 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
             CU(cudaMemsetAsync(ws.corr_meta.p, 0, 16, st));
             // i-particles no walk covers keep number = 0 (and trip the "not in its own EP list" status) instead of
             // feeding uninitialised counts into the correction's scan
-            if (!ws.has_split && zero_e0 < 0)
-                CU(cudaMemsetAsync(ws.force.p, 0, (size_t)ws.n_epi * sizeof(ForceAos), st));
+            CU(cudaMemsetAsync(ws.force.p, 0, (size_t)ws.n_epi * sizeof(ForceAos), st));
             ws.captured = true;
         }
     }
     if (n_items == 0) return 0;
-    // split tiles add their halves into ForceGrav (kernels.cuh, `part`): start from zero.  Default: the whole set
-    // when its list holds split tiles; dispatch() passes the i-range of a sub-batch instead.
-    if (zero_e0 < 0 && ws.has_split) { zero_e0 = 0; zero_e1 = ws.n_epi; }
-    if (zero_e1 > zero_e0) CU(cudaMemsetAsync((ForceAos *)ws.force.p + zero_e0, 0, (size_t)(zero_e1 - zero_e0) * sizeof(ForceAos), st));
     PassParams p;
     p.epi = (const EpiAos *)ws.epi.p;
     p.epi_off = (const int *)ws.epi_off.p;
@@ -270,14 +324,22 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
+    p.scratch = (ForceAos *)ws.scratch.p; p.arrive = (int *)ws.arrive.p;
+    p.seg_off = n_seg > 0 ? (const int *)ws.seg_off.p + seg0 : nullptr; p.n_seg = n_seg;
+    p.peer_flags = nullptr; p.peer_world = 0; p.peer_epoch = 0;
+    if (g.peer.on) {
+        p.peer_flags = reinterpret_cast<const int *>(static_cast<const char *>(g.peer.slab[0]) + ((size_t)1 << g.peer.shift) * sizeof(EpjPacked));
+        p.peer_world = g.peer.world; p.peer_epoch = g.peer.epoch;
+    }
     if (g.corr_on && ws.captured) {
         p.self_adr = (int *)ws.self_adr.p;
         p.pairs = (int2 *)ws.pairs.p;
         p.pair_count = (unsigned int *)ws.corr_meta.p;
         p.pair_cap = ws.pair_cap;
     }
-    if (g.rmax <= 2) force_pass_kernel<2><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
-    else force_pass_kernel<4><<<(n_items + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
+    const int n_warps = n_seg > 0 ? n_seg : n_items;
+    if (g.rmax <= 2) force_pass_kernel<2><<<(n_warps + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
+    else force_pass_kernel<4><<<(n_warps + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
     CU(cudaGetLastError());
     g.launches++;
     return 0;
@@ -332,9 +394,33 @@ int upload_walks(WalkSet &ws, int n_walk, const void *epi_all, const int *epi_of
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es;
     g.tree_built = false;
-    std::vector<WorkItem> items;
-    ws.has_split = build_items(n_walk, ni, n_epj, n_spj, items);
+    // multi-GPU peer mode: a walk whose EP list names a particle of another rank (index = owner << shift | local index)
+    // must not start before that rank has packed: its items wait for the peers' flags inside the kernel, and one empty
+    // barrier item ends the pass only after every peer has packed (a slab is reused two epochs later; kernels.cuh)
+    std::vector<unsigned char> peer_walk;
+    if (g.peer.on) {
+        peer_walk.assign((size_t)n_walk, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int w = 0; w < n_walk; w++) {
+            const int *a = adr_epj + epj_disp[w];
+            for (int j = 0; j < n_epj[w]; j++)
+                if ((a[j] >> g.peer.shift) != g.peer.rank) { peer_walk[w] = 1; break; }
+        }
+    }
+    ItemList il;
+    build_items(n_walk, ni, n_epj, n_spj, il, 0, true, 0, 0, g.peer.on ? peer_walk.data() : nullptr);
+    if (g.peer.on) {
+        il.items.push_back(WorkItem{0, 0, 0, ITEM_PEER_WAIT, 0, 0, 0, 0});
+        if (!il.seg_off.empty()) il.seg_off.back() = (int)il.items.size();        // the last segment's warp also holds the barrier
+    }
+    std::vector<WorkItem> &items = il.items;
     ws.n_items = (int)items.size();
+    ws.n_seg = il.seg_off.empty() ? 0 : (int)il.seg_off.size() - 1;
+    if (ws.n_seg > 0) {
+        if (int r = ws.seg_off.reserve(il.seg_off.size() * 4)) return r;
+        CU(cudaMemcpyAsync(ws.seg_off.p, il.seg_off.data(), il.seg_off.size() * 4, cudaMemcpyHostToDevice, st));   // pageable: staged on return
+    }
+    if (int r = reserve_split(ws, il.n_slots, il.n_groups, st)) return r;
     if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
     if (int r = ws.epi_off.reserve((size_t)n_walk * 4)) return r;
@@ -442,10 +528,11 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
         CU(cudaGetLastError());
     }
     // meta: [epi_off(int) | n_epj | n_spj | pad | epj_disp(ll) | spj_disp(ll) | items...]
-    std::vector<WorkItem> items;
+    ItemList il;
     const int zero = 0;
     const int ne = which == 0 ? nj : 0, ns = which == 1 ? nj : 0;
-    build_items(1, &ni, &ne, &ns, items, 0, false);
+    build_items(1, &ni, &ne, &ns, il, 0, false);
+    std::vector<WorkItem> &items = il.items;
     struct Meta { int epi_off, n_epj, n_spj, pad; long long epj_disp, spj_disp; } meta = {zero, ne, ns, 0, 0, 0};
     const size_t meta_bytes = sizeof(Meta) + items.size() * sizeof(WorkItem);
     if (int r = s.meta.reserve(meta_bytes)) return r;
@@ -480,6 +567,8 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.eps2 = eps2;
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
+    p.scratch = nullptr; p.arrive = nullptr; p.peer_flags = nullptr; p.peer_world = 0; p.peer_epoch = 0;
+    p.seg_off = nullptr; p.n_seg = 0;
     if (g.rmax <= 2) force_pass_kernel<2><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else force_pass_kernel<4><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     CU(cudaGetLastError());
@@ -520,7 +609,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_RMAX")) g.rmax = atoi(e) >= 3 ? 4 : (atoi(e) <= 1 ? 1 : 2);
     if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
-    if (const char *e = getenv("GPLUM_B200_EPSP_SPLIT")) g.epsp_split = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_SPLIT_M")) g.split_m = std::max(0, atoi(e));
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
@@ -739,7 +828,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         if (ni[w] < 0 || n_epj[w] < 0 || n_spj[w] < 0) return fail(GPLUM_B200_ERR_ARG, "negative count in walk %d", w);
         n_epi += ni[w]; n_ae += n_epj[w]; n_as += n_spj[w];
         i_ee += (long long)ni[w] * n_epj[w]; i_es += (long long)ni[w] * n_spj[w];
-        n_it_max += 2 * ((ni[w] + 3) / 4 + 1);    // smallest tile holds 4 i-particles; x2: EP/SP split
+        n_it_max += (long long)SPLIT_K_MAX * ((ni[w] + 31) / 32) + (ni[w] + 3) / 4 + 1;    // j-split parts of full-width tiles + short tails
     }
     const size_t b_epi = ((size_t)n_epi * sizeof(EpiAos) + 15) & ~(size_t)15, b_ae = (size_t)n_ae * 4, b_as = (size_t)n_as * 4;
     const size_t b_meta = (size_t)n_walk * (4 * 3 + 8 * 2);
@@ -763,7 +852,6 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
     }
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es; ws.n_items = 0;
-    ws.has_split = false;                        // per sub-batch below
     g.tree_built = false;
     if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
@@ -802,8 +890,17 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         CU(cudaMemcpyAsync(ws.epj_disp.p, h_edisp, (size_t)n_walk * 8, H2D, ci));
         CU(cudaMemcpyAsync(ws.spj_disp.p, h_sdisp, (size_t)n_walk * 8, H2D, ci));
     }
-    std::vector<WorkItem> items;
-    int item0 = 0;
+    ItemList il;
+    std::vector<WorkItem> &items = il.items;
+    int item0 = 0, slot0 = 0, group0 = 0, seg0 = 0;
+    ws.n_seg = 0;
+    if (int r = ws.seg_off.reserve((size_t)std::max(nsb, 1) * (size_t)(g.warp_slots + 1) * 4)) return r;
+    {   // scratch for the j-split tiles of small sub-batches: at most SPLIT_K_MAX parts per 32 i-particles
+        long long tiles = 0;
+        for (int w = 0; w < n_walk; w++) tiles += (ni[w] + 31) / 32;
+        const bool may_split = g.split_m > 0 && tiles < 2 * g.warp_slots * (long long)std::max(nsb, 1);
+        if (int r = reserve_split(ws, may_split ? (int)std::min<long long>(tiles * SPLIT_K_MAX, 1 << 22) : 1, may_split ? (int)tiles : 1, ci)) return r;
+    }
     for (int b = 0; b < nsb; b++) {
         const int w0 = ws.sub_w0[b], w1 = ws.sub_w0[b + 1];
 #pragma omp parallel for schedule(static)
@@ -812,7 +909,10 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
             memcpy(h_ae + h_edisp[w], adr_epj[w], (size_t)n_epj[w] * 4);
             memcpy(h_as + h_sdisp[w], adr_spj[w], (size_t)n_spj[w] * 4);
         }
-        const bool split_b = build_items(w1 - w0, ni + w0, n_epj + w0, n_spj + w0, items, w0);
+        build_items(w1 - w0, ni + w0, n_epj + w0, n_spj + w0, il, w0, true, slot0, group0);
+        slot0 += il.n_slots; group0 += il.n_groups;
+        if ((size_t)slot0 * 64 * sizeof(ForceAos) > ws.scratch.cap || (size_t)group0 * 4 > ws.arrive.cap)
+            return fail(GPLUM_B200_ERR_STATE, "split-tile scratch estimate too small");
         const int n_it = (int)items.size();
         if (item0 + n_it > n_it_max) return fail(GPLUM_B200_ERR_STATE, "work-item estimate too small");
         if (n_it) memcpy(h_items + item0, items.data(), (size_t)n_it * sizeof(WorkItem));
@@ -823,10 +923,13 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
         if (a1 > a0) CU(cudaMemcpyAsync((int *)ws.adr_epj.p + a0, h_ae + a0, (size_t)(a1 - a0) * 4, H2D, ci));
         if (s1 > s0) CU(cudaMemcpyAsync((int *)ws.adr_spj.p + s0, h_as + s0, (size_t)(s1 - s0) * 4, H2D, ci));
         if (n_it) CU(cudaMemcpyAsync((WorkItem *)ws.items.p + item0, h_items + item0, (size_t)n_it * sizeof(WorkItem), H2D, ci));
+        ws.n_items = item0 + n_it;
+        const int n_seg_b = il.seg_off.empty() ? 0 : (int)il.seg_off.size() - 1;
+        if (n_seg_b > 0) CU(cudaMemcpyAsync((int *)ws.seg_off.p + seg0, il.seg_off.data(), il.seg_off.size() * 4, H2D, ci));   // pageable: staged on return
         CU(cudaEventRecord(ws.ev_in[b], ci));
         CU(cudaStreamWaitEvent(st, ws.ev_in[b], 0));
-        ws.n_items = item0 + n_it;
-        if (int r = launch_pass(ws, st, g.eps2, item0, n_it, b == 0, split_b ? e0 : 0, split_b ? e1 : 0)) return r;
+        if (int r = launch_pass(ws, st, g.eps2, item0, n_it, b == 0, seg0, n_seg_b)) return r;
+        seg0 += n_seg_b > 0 ? n_seg_b + 1 : 0;
         CU(cudaEventRecord(ws.ev_k[b], st));
         CU(cudaStreamWaitEvent(co, ws.ev_k[b], 0));
         if (e1 > e0) CU(cudaMemcpyAsync((ForceAos *)ws.h_force.p + e0, (const ForceAos *)ws.force.p + e0, (size_t)(e1 - e0) * sizeof(ForceAos), cudaMemcpyDeviceToHost, co));
@@ -1009,6 +1112,8 @@ int gplum_b200_peer_open(const void *all_handles)
         if (int r = pe.table[b].reserve(sizeof(void *) * MAX_PEERS)) return r;
         CU(cudaMemcpy(pe.table[b].p, pe.mapped[b], sizeof(void *) * pe.world, cudaMemcpyHostToDevice));
     }
+    if (int r = pe.done.reserve(16)) return r;
+    CU(cudaMemset(pe.done.p, 0, 16));
     pe.on = true;
     return 0;
 }
@@ -1021,13 +1126,17 @@ int gplum_b200_peer_pack(const void *epj_aos_dev, int n)
     if (n < 0 || n > (1 << pe.shift)) return fail(GPLUM_B200_ERR_ARG, "peer_pack n=%d exceeds the slab (%d)", n, 1 << pe.shift);
     CU(cudaSetDevice(g.device));
     pe.parity ^= 1;                  // peers may still be reading the slab of the previous step
-    if (n > 0) {
-        pack_epj_kernel<<<(n + 255) / 256, 256, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)pe.slab[pe.parity]);
-        CU(cudaGetLastError());
-        g.launches++;
-    }
     pe.epoch++;
-    peer_signal_kernel<<<1, 32, 0, g.stream>>>((void *const *)pe.table[0].p, ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
+    // one launch: this rank's EPJ into its slab, its superparticles (the current j-set's, unless they are external),
+    // and the flag stores that tell every rank "packed" (kernels.cuh: peer_pack_kernel)
+    JSet &j = g.jset;
+    const int n_spj = (j.n_spj > 0 && !j.ext_spj) ? j.n_spj : 0;
+    const int nb_e = std::max(1, (n + PACK_BLOCK - 1) / PACK_BLOCK), nb_s = (n_spj + PACK_BLOCK - 1) / PACK_BLOCK;
+    peer_pack_kernel<<<nb_e + nb_s, PACK_BLOCK, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)pe.slab[pe.parity],
+                                                                j.spj_aos.p, n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
+                                                                (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2, nb_e,
+                                                                (unsigned int *)pe.done.p, (void *const *)pe.table[0].p,
+                                                                ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
     CU(cudaGetLastError());
     g.launches++;
     return 0;
@@ -1057,6 +1166,7 @@ int gplum_b200_peer_close(void)
             if (pe.on && q != pe.rank && pe.mapped[b][q]) cudaIpcCloseMemHandle(pe.mapped[b][q]);
         pe.table[b].release();
     }
+    pe.done.release();
     // the slabs themselves are freed by the caller's barrier-then-free protocol: peers must have
     // closed their mappings first (see gplum_b200/multigpu.py)
     pe.on = false;
@@ -1293,7 +1403,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     if (int r = j.epj_packed.reserve((size_t)n * sizeof(EpjPacked))) return r;
     gbt::TreeCfg cfg;
     cfg.n = n; cfg.theta = theta; cfg.n_leaf = n_leaf_limit; cfg.n_group = n_group_limit; cfg.quad = g.quad;
-    cfg.warp_slots = g.warp_slots; cfg.tile_cap = g.tile_cap; cfg.jsplit = g.jsplit; cfg.rmax = g.rmax;
+    cfg.warp_slots = g.warp_slots; cfg.tile_cap = g.tile_cap; cfg.jsplit = g.jsplit; cfg.rmax = g.rmax; cfg.split_m = g.split_m;
     gbt::TreeCounts c;
     memset(&c, 0, sizeof(c));
     int launches = 0;
@@ -1310,23 +1420,29 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     if (int r = ws.spj_disp.reserve(nw * 8)) return r;
     if (int r = ws.adr_epj.reserve((size_t)c.n_adr_epj * 4)) return r;
     if (int r = ws.adr_spj.reserve((size_t)c.n_adr_spj * 4)) return r;
-    if (int r = ws.items.reserve((size_t)c.n_items * sizeof(WorkItem))) return r;
+    // a pass with few items cuts its tiles along j on the device too (dev_tree.cu: item_split_kernel); the list is
+    // then sized by its upper bound and padded with empty items, so that no further host sync is needed
+    const bool dev_split = split_active(c.n_items, g.warp_slots, g.split_m);
+    const int n_items_out = dev_split ? (int)split_items_bound(c.n_items, g.warp_slots) : c.n_items;
+    if (int r = ws.items.reserve((size_t)n_items_out * sizeof(WorkItem))) return r;
+    if (int r = reserve_split(ws, dev_split ? n_items_out : 1, dev_split ? c.n_items : 1, st)) return r;
+    if (int r = ws.seg_off.reserve((size_t)(g.warp_slots + 1) * 4)) return r;
+    ws.n_seg = dev_split ? (int)g.warp_slots : 0;
     if (int r = j.spj_aos.reserve((size_t)c.n_cells * ssz)) return r;
     if (int r = j.spj_packed.reserve((size_t)c.n_cells * sizeof(SpjPacked))) return r;
     gbt::TreeOut o;
     o.epi_off = (int *)ws.epi_off.p; o.ni = nullptr; o.n_epj = (int *)ws.n_epj.p; o.n_spj = (int *)ws.n_spj.p;
     o.epj_disp = (long long *)ws.epj_disp.p; o.spj_disp = (long long *)ws.spj_disp.p;
     o.adr_epj = (int *)ws.adr_epj.p; o.adr_spj = (int *)ws.adr_spj.p;
-    o.items = ws.items.p; o.spj_aos = j.spj_aos.p;
+    o.items = ws.items.p; o.n_items_out = n_items_out; o.seg_off = (int *)ws.seg_off.p; o.spj_aos = j.spj_aos.p;
     launches = 0;
     e = gbt::tree_phase2(cfg, o, st, &launches);
     g.launches += launches;
     if (e) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 2: %s", cudaGetErrorString((cudaError_t)e));
-    ws.n_walk = c.n_walk; ws.n_items = c.n_items; ws.n_epi = n;
+    ws.n_walk = c.n_walk; ws.n_items = n_items_out; ws.n_epi = n;
     ws.n_adr_epj = c.n_adr_epj; ws.n_adr_spj = c.n_adr_spj;
     ws.n_int_epep = c.n_int_epep; ws.n_int_epsp = c.n_int_epsp;
     ws.ni_host.clear(); ws.epi_off_host.clear();
-    ws.has_split = false;                        // the device work-list builder issues whole tiles only
     ws.pending = false; ws.captured = false; ws.corrected = false;
     j.ext_epj = j.ext_spj = nullptr;
     j.n_epj = n; j.n_spj = c.n_cells;
@@ -1571,20 +1687,28 @@ int gplum_b200_state_push(const void *rec, const int *idx, int n_rec)
 
 // ---- host work-list builder, exposed for tests (no device needed) ----
 extern "C" int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj,
-                                            long long warp_slots, int tile_cap, int jsplit, int epsp_split,
-                                            int *items_out, int cap_items, int *n_items_out, int *has_split_out)
+                                            long long warp_slots, int tile_cap, int jsplit, int split_m,
+                                            int *items_out, int cap_items, int *n_items_out, int *n_slots_out, int *n_groups_out,
+                                            int *seg_off_out, int cap_seg, int *n_seg_out)
 {
     if (n_walk < 0 || !ni || !n_epj || !n_spj || !n_items_out) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: bad argument");
-    const long long ws0 = g.warp_slots; const int tc0 = g.tile_cap, js0 = g.jsplit, es0 = g.epsp_split;
-    g.warp_slots = warp_slots; g.tile_cap = tile_cap; g.jsplit = jsplit; g.epsp_split = epsp_split;
-    std::vector<WorkItem> items;
-    const bool hs = build_items(n_walk, ni, n_epj, n_spj, items);
-    g.warp_slots = ws0; g.tile_cap = tc0; g.jsplit = js0; g.epsp_split = es0;
-    *n_items_out = (int)items.size();
-    if (has_split_out) *has_split_out = hs ? 1 : 0;
+    const long long ws0 = g.warp_slots; const int tc0 = g.tile_cap, js0 = g.jsplit, sm0 = g.split_m;
+    g.warp_slots = warp_slots; g.tile_cap = tile_cap; g.jsplit = jsplit; g.split_m = split_m;
+    ItemList il;
+    build_items(n_walk, ni, n_epj, n_spj, il);
+    g.warp_slots = ws0; g.tile_cap = tc0; g.jsplit = js0; g.split_m = sm0;
+    *n_items_out = (int)il.items.size();
+    if (n_slots_out) *n_slots_out = il.n_slots;
+    if (n_groups_out) *n_groups_out = il.n_groups;
+    const int n_seg = il.seg_off.empty() ? 0 : (int)il.seg_off.size() - 1;
+    if (n_seg_out) *n_seg_out = n_seg;
     if (items_out) {
-        if ((int)items.size() > cap_items) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: %zu items, room for %d", items.size(), cap_items);
-        memcpy(items_out, items.data(), items.size() * sizeof(WorkItem));
+        if ((int)il.items.size() > cap_items) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: %zu items, room for %d", il.items.size(), cap_items);
+        memcpy(items_out, il.items.data(), il.items.size() * sizeof(WorkItem));
+    }
+    if (seg_off_out && n_seg > 0) {
+        if (n_seg + 1 > cap_seg) return fail(GPLUM_B200_ERR_ARG, "debug_build_items: %d segments, room for %d", n_seg, cap_seg - 1);
+        memcpy(seg_off_out, il.seg_off.data(), il.seg_off.size() * sizeof(int));
     }
     return 0;
 }

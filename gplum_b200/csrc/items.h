@@ -1,6 +1,6 @@
 // items.h -- how one walk (i-group) is cut into i-tiles ("work items") of the force pass.
 // Shared by the host work-list builder (gplum_b200.cu: build_items) and the device one
-// (dev_tree.cu: emit_items_kernel) so both produce the same items and the same cost keys.
+// (dev_tree.cu: emit_items_kernel / split_items_kernel) so both produce the same items and the same cost keys.
 #pragma once
 
 #if defined(__CUDACC__)
@@ -28,17 +28,95 @@ GB_HD void tile_next(int rem, int cap, bool split, int &n, int &shape)
 }
 
 // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
+constexpr double COST_EP = 18.5, COST_SP = 37.0, COST_TILE = 90.0, COST_ITEM = 200.0;
 GB_HD double tile_cost(int n_epj, int n_spj, int shape)
 {
-    const double cost_j = 18.5 * n_epj + 37.0 * n_spj;
-    const double cost_tiles = 90.0 * ((n_epj + 63) / 64 + (n_spj + 63) / 64) + 200.0;
+    const double cost_j = COST_EP * n_epj + COST_SP * n_spj;
+    const double cost_tiles = COST_TILE * ((n_epj + 63) / 64 + (n_spj + 63) / 64) + COST_ITEM;
     return cost_j * shape / 32.0 + cost_tiles;
 }
 
-// EP/SP split of full-width tiles (kernels.cuh: warp_force, `part`): cfg bits
-constexpr int TILE_EP_ONLY = 16, TILE_SP_ONLY = 32;
-GB_HD double tile_cost_ep(int n_epj, int shape) { return 18.5 * n_epj * shape / 32.0 + 90.0 * ((n_epj + 63) / 64) + 200.0; }
-GB_HD double tile_cost_sp(int n_spj, int shape) { return 37.0 * n_spj * shape / 32.0 + 90.0 * ((n_spj + 63) / 64) + 200.0; }
+// ---- j-split of full-width tiles: a pass with few items (a rank's share of a multi-GPU run, a small dispatch)
+// cannot fill the GPU with whole tiles -- 2300 items on 3552 warp slots leave a third of the issue slots empty and
+// the pass ends when the longest serial chains do.  Such a pass cuts every full-width tile (64 or 32 i-particles)
+// into K parts along its j-tile sequence (EP tiles first, then SP tiles); every part is its own work item on its
+// own warp, writes its partial sums to a scratch record, and the part that finishes LAST adds the K partial sums
+// in part order (kernels.cuh, warp_force) -- a fixed order, so the result does not depend on which warp finishes
+// when.  Cfg word of a final item: bits 0-3 tile shape, bit 6 waits for the peers' flags (multi-GPU peer mode),
+// bits 8-15 K, bits 16-23 part index.
+constexpr int ITEM_PEER_WAIT = 64;
+constexpr int SPLIT_K_MAX = 250;       // parts of one tile (the cfg word holds 8 bits of it)
+GB_HD int item_parts(int cfg) { return (cfg >> 8) & 0xff; }           // 0 or 1: unsplit
+GB_HD int item_part_index(int cfg) { return (cfg >> 16) & 0xff; }
+
+// number of j-tiles of a walk and the cost of the first t of them for a tile shape (EP tiles, then SP tiles)
+GB_HD int walk_tiles(int n_epj, int n_spj) { return (n_epj + 63) / 64 + (n_spj + 63) / 64; }
+GB_HD double tiles_cost(int n_epj, int n_spj, int shape, int t)
+{
+    const int nt_ep = (n_epj + 63) / 64;
+    const int te = t < nt_ep ? t : nt_ep, ts = t - te;
+    const int je = te * 64 < n_epj ? te * 64 : n_epj, js = ts * 64 < n_spj ? ts * 64 : n_spj;
+    return (COST_EP * je + COST_SP * js) * shape / 32.0 + COST_TILE * t;
+}
+
+// Segments: a pass with less than two waves of base items is laid out as ONE WAVE of warps with equal work.  The
+// base items in list order form a line of cost (integer units of the cost model); the line is cut into n_seg equal
+// segments, one per resident warp slot, at j-tile boundaries: a segment is a run of consecutive work items (the tail
+// part of one tile, whole tiles, the head part of another) that one warp executes back to back.  All warps start
+// together and finish together -- no scheduling tail, every issue port has its full set of warps to the end.
+// (Equal PARTS of every tile were measured first: 2-4 parts per tile did not beat whole tiles on a 1/8 shard,
+// because the pass still ended on a tail of single warps; profiles/r2_split_probe.txt.)
+GB_HD bool split_active(long long n_base, long long warp_slots, int split_m) { return split_m > 0 && n_base > 0 && n_base < 2 * warp_slots; }
+GB_HD long long item_cost_units(double cost) { return (long long)(cost + 0.5); }
+// segment of cost position x on a line of total cost W cut into n_seg pieces; boundary b sits at ceil(b W / n_seg)
+GB_HD long long seg_of(long long x, long long W, long long n_seg) { const long long s = (x * n_seg) / W; return s < n_seg ? s : n_seg - 1; }   // W n_seg < 2^63: passes that split are small
+GB_HD long long seg_boundary(long long b, long long W, long long n_seg) { return (b * W + n_seg - 1) / n_seg; }
+// j-tile boundary nearest to the point where a tile of shape `shape` has spent `offset` cost units
+GB_HD int split_tile_at(int n_epj, int n_spj, int shape, long long offset)
+{
+    const int nt = walk_tiles(n_epj, n_spj);
+    int lo = 0, hi = nt;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tiles_cost(n_epj, n_spj, shape, mid) + COST_ITEM < (double)offset) lo = mid + 1; else hi = mid; }
+    // the nearer of the two tile boundaries around the cut
+    if (lo > 0 && (double)offset - (tiles_cost(n_epj, n_spj, shape, lo - 1) + COST_ITEM) < (tiles_cost(n_epj, n_spj, shape, lo) + COST_ITEM) - (double)offset) lo--;
+    return lo;
+}
+// The parts of one base item on the segmented line, generated one after the other (host and device builders run
+// the same code): C = cost units before the item, c = its own.  Lane-split tails, one-tile walks and tiles that lie
+// inside one segment stay whole; every tile shape of the RMAX = 2 build can be cut, lane-split tails included.
+struct SegCut {
+    long long W, n_seg, C, s1, sb;
+    int n_epj, n_spj, shape, nt, t_prev, emitted;
+    bool whole, done;
+};
+GB_HD void seg_cut_begin(SegCut &q, long long W, long long n_seg, long long C, long long c, int cfg, int n_epj, int n_spj)
+{
+    q.W = W; q.n_seg = n_seg; q.C = C; q.n_epj = n_epj; q.n_spj = n_spj;
+    const int kc = cfg & 15;
+    q.shape = kc == 1 ? 64 : kc == 0 ? 32 : kc == 9 ? 16 : kc == 10 ? 8 : 4;
+    q.nt = walk_tiles(n_epj, n_spj);
+    const long long s0 = seg_of(C, W, n_seg);
+    q.s1 = c > 0 ? seg_of(C + c - 1, W, n_seg) : s0;
+    q.sb = s0 + 1; q.t_prev = 0; q.emitted = 0; q.done = false;
+    q.whole = (kc > 1 && kc < 9) || q.s1 == s0 || q.nt <= 1;      // RMAX = 4 shapes are not cut
+}
+// next part [t0, t1) and its segment; false when the item is exhausted.  A whole item reports t0 = 0, t1 = nt.
+GB_HD bool seg_cut_next(SegCut &q, int &t0, int &t1, long long &seg)
+{
+    if (q.done) return false;
+    if (q.whole) { t0 = 0; t1 = q.nt; seg = seg_of(q.C, q.W, q.n_seg); q.done = true; q.emitted = 1; return true; }
+    while (q.sb <= q.s1 && q.emitted < SPLIT_K_MAX - 1) {
+        const long long sb = q.sb++;
+        int t_cut = split_tile_at(q.n_epj, q.n_spj, q.shape, seg_boundary(sb, q.W, q.n_seg) - q.C);
+        if (t_cut > q.nt) t_cut = q.nt;
+        if (t_cut > q.t_prev) { t0 = q.t_prev; t1 = t_cut; seg = sb - 1; q.t_prev = t_cut; q.emitted++; return true; }
+    }
+    q.done = true;
+    if (q.nt > q.t_prev || q.emitted == 0) { t0 = q.t_prev; t1 = q.nt; seg = q.s1; q.emitted++; return true; }
+    return false;
+}
+// upper bound of the split list's length: every base item once, plus one extra part per segment boundary
+GB_HD long long split_items_bound(long long n_base, long long n_seg) { return n_base + n_seg + 8; }
 
 // Tile capacity of a pass: 64 i-particles per warp is the most efficient shape (staging is amortised
 // over the most pairs), and measured on 1/4- and 1/8-size shards it stays the fastest even at 0.6 waves.

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include "records.h"
+#include "items.h"
 
 namespace gb {
 
@@ -67,7 +68,34 @@ struct PassParams {
     // All three are nullptr unless capture is enabled.
     int *self_adr;
     int2 *pairs; unsigned int *pair_count; unsigned int pair_cap;
+    // j-split tiles (items.h): the K parts of a tile leave their partial sums in scratch[(slot0 + part) * 64 + i]
+    // and count their arrival in arrive[group]; the last one adds the partial sums in part order and writes ForceGrav
+    ForceAos *scratch; int *arrive;
+    // one-wave passes (items.h, segments): warp s executes items [seg_off[s], seg_off[s + 1]); nullptr: item s
+    const int *seg_off; int n_seg;
+    // multi-GPU peer mode: items flagged ITEM_PEER_WAIT start once every rank's flag word has reached the epoch,
+    // i.e. once all slabs of this step are packed (gplum_b200.cu: peer_pack)
+    const int *peer_flags; int peer_world, peer_epoch;
 };
+
+// spins until flags[0 .. world) >= epoch (the peers store their epoch over NVLink after packing, st.release.sys)
+__device__ __forceinline__ void peer_flags_wait(const int *flags, int world, int epoch)
+{
+    const int q = threadIdx.x & 31;
+    if (q < world) {
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + q) : "memory");
+            if (v - epoch >= 0) break;
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t - t0 > 10000000000ull) __trap();           // 10 s: a peer died; fail loudly instead of hanging
+        }
+    }
+    __syncwarp();
+}
 
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
@@ -108,10 +136,10 @@ __device__ __forceinline__ float4 ldg_f4(const void *p)
 // each thread then picks its fields from shared memory.  `in` must be 16 B aligned.
 constexpr int PACK_BLOCK = 256;
 template <int REC>
-__device__ __forceinline__ void stage_records(const void *__restrict__ in, int n, unsigned char *sm)
+__device__ __forceinline__ void stage_records(const void *__restrict__ in, int n, unsigned char *sm, int blk)
 {
     static_assert(REC % 16 == 0, "record size");
-    const int first = blockIdx.x * PACK_BLOCK;
+    const int first = blk * PACK_BLOCK;
     const int cnt = min(PACK_BLOCK, n - first);
     const int n16 = cnt * (REC / 16);
     const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const unsigned char *>(in) + (size_t)first * REC);
@@ -119,11 +147,11 @@ __device__ __forceinline__ void stage_records(const void *__restrict__ in, int n
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PACK_BLOCK) pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
+// one block's 256 EPJGrav records -> packed records (sm: PACK_BLOCK * 112 B)
+__device__ __forceinline__ void pack_epj_block(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out, int blk, unsigned char *sm)
 {
-    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(EpjAos)];
-    stage_records<sizeof(EpjAos)>(in, n, sm);
-    const int i = blockIdx.x * PACK_BLOCK + threadIdx.x;
+    stage_records<sizeof(EpjAos)>(in, n, sm, blk);
+    const int i = blk * PACK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const EpjAos &a = reinterpret_cast<const EpjAos *>(sm)[threadIdx.x];
     EpjPacked o;
@@ -134,6 +162,12 @@ __global__ void __launch_bounds__(PACK_BLOCK) pack_epj_kernel(const EpjAos *__re
     o.rs2 = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
     o.id = a.id_local; o.rank = a.myrank; o.pad = 0;
     out[i] = o;
+}
+
+__global__ void __launch_bounds__(PACK_BLOCK) pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
+{
+    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(EpjAos)];
+    pack_epj_block(in, n, out, blockIdx.x, sm);
 }
 
 // Halo send staging of the multi-GPU step: dst[k] = src[idx[k]] for 48 B packed EP records,
@@ -147,14 +181,13 @@ __global__ void gather_epj_packed_kernel(const uint4 *__restrict__ src, const in
 }
 
 // quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
-// src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).
-__global__ void __launch_bounds__(PACK_BLOCK) pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
-                                int quad, int trace_as_shipped, float eps2)
+// src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).  sm: PACK_BLOCK * 80 B.
+__device__ __forceinline__ void pack_spj_block(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
+                                               int quad, int trace_as_shipped, float eps2, int blk, unsigned char *sm)
 {
-    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(SpjQuadAos)];
-    if (quad) stage_records<sizeof(SpjQuadAos)>(in, n, sm);
-    else stage_records<sizeof(SpjMonoAos)>(in, n, sm);
-    const int i = blockIdx.x * PACK_BLOCK + threadIdx.x;
+    if (quad) stage_records<sizeof(SpjQuadAos)>(in, n, sm, blk);
+    else stage_records<sizeof(SpjMonoAos)>(in, n, sm, blk);
+    const int i = blk * PACK_BLOCK + threadIdx.x;
     if (i >= n) return;
     SpjPacked o;
     if (quad) {
@@ -176,6 +209,42 @@ __global__ void __launch_bounds__(PACK_BLOCK) pack_spj_kernel(const void *__rest
     }
     o.pad0 = o.pad1 = 0.0f;
     out[i] = o;
+}
+
+__global__ void __launch_bounds__(PACK_BLOCK) pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
+                                int quad, int trace_as_shipped, float eps2)
+{
+    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(SpjQuadAos)];
+    pack_spj_block(in, n, out, quad, trace_as_shipped, eps2, blockIdx.x, sm);
+}
+
+// Multi-GPU peer mode, one launch per step: blocks [0, nb_e) pack this rank's EPJ into its slab, the others pack its
+// SPJ.  The EPJ block that finishes last stores the new epoch into this rank's entry of EVERY rank's flag array
+// (the others' over NVLink): "my slab of this step is complete" (gplum_b200.cu: peer mode).
+__global__ void __launch_bounds__(PACK_BLOCK) peer_pack_kernel(const EpjAos *__restrict__ epj_in, int n_epj, EpjPacked *__restrict__ slab,
+                                                               const void *__restrict__ spj_in, int n_spj, SpjPacked *__restrict__ spj_out,
+                                                               int quad, int trace_as_shipped, float eps2, int nb_e,
+                                                               unsigned int *done, void *const *slab0_of, size_t flag_off,
+                                                               int rank, int world, int epoch)
+{
+    __shared__ __align__(16) unsigned char sm[PACK_BLOCK * sizeof(EpjAos)];
+    __shared__ int s_last;
+    if ((int)blockIdx.x >= nb_e) {
+        pack_spj_block(spj_in, n_spj, spj_out, quad, trace_as_shipped, eps2, blockIdx.x - nb_e, sm);
+        return;
+    }
+    if (n_epj > 0) pack_epj_block(epj_in, n_epj, slab, blockIdx.x, sm);
+    __threadfence_system();                             // the records are read by other GPUs
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == (unsigned int)(nb_e - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *done = 0;                    // ready for the next step
+    if ((int)threadIdx.x < world) {
+        int *f = reinterpret_cast<int *>(static_cast<char *>(slab0_of[threadIdx.x]) + flag_off) + rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -230,13 +299,10 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
     const int *adr_sp = p.adr_spj + p.spj_disp[w];
     const int nt_ep = (nj_ep + JW - 1) / JW, nt_sp = (nj_sp + JW - 1) / JW;
     const int nt = nt_ep + nt_sp;
-    // EP/SP split (cfg bits 4, 5): in a pass with less than one wave of items every full-width tile is issued
-    // twice, once for the walk's EP tiles and once for its SP tiles, so that twice as many warps share the
-    // issue ports and the serial chain of an item halves.  The two halves add into a zeroed ForceGrav with
-    // one atomic each: 0 + x + y has one rounding whichever comes first, so the result is deterministic.
-    const int part = (it.cfg >> 4) & 3;             // 0 = whole list, 1 = EP tiles only, 2 = SP tiles only
-    const int t_begin = part == 2 ? nt_ep : 0;
-    const int t_end = part == 1 ? nt_ep : nt;
+    // this item's share of the walk's tile sequence (items.h: a split tile's parts cover [0, nt) between them)
+    const int t_begin = it.t0;
+    const int t_end = it.t1 < 0 ? nt : min(it.t1, nt);
+    if (it.cfg & ITEM_PEER_WAIT) peer_flags_wait(p.peer_flags, p.peer_world, p.peer_epoch);
 
     // list index of slot (lane + 32k) of tile t, or -1 for padding
     auto slot_index = [&](int t, int k) -> int {
@@ -457,6 +523,7 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
 
     // ---- write-back: ForceGrav::clear + this pass's sums (a4 + a7 fused) ----
     __syncwarp();
+    float4 fo[R]; int4 no[R]; bool ok[R];           // this warp's result per i-slot (lane + 32 r), unscaled
     if (G > 1) {
         // combine the lane groups' partial results (same i in lanes l, l+W, l+2W, ...)
         int nn = s.nb_number[lane], nr = s.nb_rank[lane], nmax = s.nb_idmax[lane], nmin = s.nb_idmin[lane];
@@ -467,27 +534,68 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
             nn += __shfl_xor_sync(0xffffffffu, nn, o); nr += __shfl_xor_sync(0xffffffffu, nr, o);
             nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
         }
-        if (lane < W && lane < it.ni) {
-            float4 *out = reinterpret_cast<float4 *>(p.force + ibase + lane);
-            out[0] = make_float4(0.125f * ax[0], 0.125f * ay[0], 0.125f * az[0], 0.5f * ph[0]);   // undo the exact scales
-            reinterpret_cast<int4 *>(out)[1] = make_int4(nn, nr, nmax, nmin);
-        }
+        ok[0] = lane < W && lane < it.ni;
+        fo[0] = make_float4(0.125f * ax[0], 0.125f * ay[0], 0.125f * az[0], 0.5f * ph[0]);   // undo the exact scales
+        no[0] = make_int4(nn, nr, nmax, nmin);
     } else {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int i = lane + 32 * r;
-            if (i < it.ni) {
-                float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
-                if (part == 0) {
-                    out[0] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);   // undo the exact scales
-                } else {                       // half of a split tile: the pass zeroed ForceGrav before the launch
-                    float *f = reinterpret_cast<float *>(out);
-                    atomicAdd(f + 0, 0.125f * ax[r]); atomicAdd(f + 1, 0.125f * ay[r]);
-                    atomicAdd(f + 2, 0.125f * az[r]); atomicAdd(f + 3, 0.5f * ph[r]);
-                }
-                if (part != 2)
-                    reinterpret_cast<int4 *>(out)[1] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+            ok[r] = i < it.ni;
+            fo[r] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);
+            no[r] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
+        }
+    }
+    const int K = item_parts(it.cfg);
+    if (K <= 1) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (ok[r]) {
+                float4 *out = reinterpret_cast<float4 *>(p.force + ibase + lane + 32 * r);
+                out[0] = fo[r];
+                reinterpret_cast<int4 *>(out)[1] = no[r];
             }
+        }
+    } else {
+        // one of K parts of a tile: leave the partial sums in this part's scratch slot, count the arrival, and if
+        // this warp is the last of the K, add the partial sums in part order (a fixed order: the result does not
+        // depend on which warp finishes when) and write ForceGrav
+        ForceAos *slot = p.scratch + (size_t)(it.slot0 + item_part_index(it.cfg)) * 64;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (ok[r]) {
+                float4 *out = reinterpret_cast<float4 *>(slot + lane + 32 * r);
+                __stcg(out, fo[r]);
+                __stcg(reinterpret_cast<int4 *>(out) + 1, no[r]);
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.arrive + it.group, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == K - 1) {
+            __threadfence();
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (ok[r]) {
+                    const int i = lane + 32 * r;
+                    const ForceAos *q = p.scratch + (size_t)it.slot0 * 64 + i;
+                    float4 f = __ldcg(reinterpret_cast<const float4 *>(q));
+                    int4 nb = __ldcg(reinterpret_cast<const int4 *>(q) + 1);
+                    for (int k = 1; k < K; k++) {
+                        q += 64;
+                        const float4 g = __ldcg(reinterpret_cast<const float4 *>(q));
+                        const int4 mb = __ldcg(reinterpret_cast<const int4 *>(q) + 1);
+                        f.x += g.x; f.y += g.y; f.z += g.z; f.w += g.w;
+                        nb.x += mb.x; nb.y += mb.y; nb.z = max(nb.z, mb.z); nb.w = min(nb.w, mb.w);
+                    }
+                    float4 *out = reinterpret_cast<float4 *>(p.force + ibase + i);
+                    out[0] = f;
+                    reinterpret_cast<int4 *>(out)[1] = nb;
+                }
+            }
+            if (lane == 0) p.arrive[it.group] = 0;          // ready for the next pass over this work list
         }
     }
 }
@@ -505,30 +613,39 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
     const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     using Smem = WarpSmem<32 * RMAX>;
     Smem &s = reinterpret_cast<Smem *>(smem_raw)[wid];
-    const int item = blockIdx.x * WPB + wid;
-    if (item >= n_items) return;
-    const WorkItem it = p.items[item];
-    // cfg & 15: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = j-split tile, G = 2^k lane groups;
-    // cfg bits 4 / 5 (full-width tiles only): EP tiles only / SP tiles only (items.h: TILE_EP_ONLY, TILE_SP_ONLY)
-    const int kcfg = it.cfg & 15;
-    if (kcfg >= 8) {
-        switch (kcfg) {
-            case 9: warp_force<1, 2>(p, it, s); break;
-            case 10: warp_force<1, 4>(p, it, s); break;
-            default: warp_force<1, 8>(p, it, s); break;
-        }
-        return;
+    const int slot = blockIdx.x * WPB + wid;
+    int item = slot, item_end = min(slot + 1, n_items);
+    if (p.seg_off) {
+        if (slot >= p.n_seg) return;
+        item = p.seg_off[slot]; item_end = p.seg_off[slot + 1];
     }
-    if (RMAX <= 2) {
-        if (kcfg == 0) warp_force<1, 1>(p, it, s);
-        else warp_force<2, 1>(p, it, s);
-    } else {
-        switch (kcfg) {
-            case 0: warp_force<1, 1>(p, it, s); break;
-            case 1: warp_force<2, 1>(p, it, s); break;
-            case 2: warp_force<3, 1>(p, it, s); break;
-            default: warp_force<4, 1>(p, it, s); break;
+    for (; item < item_end; item++) {
+        const WorkItem it = p.items[item];
+        if (it.ni == 0) {           // barrier item of the multi-GPU peer mode: the pass ends after every peer has packed
+            if (it.cfg & ITEM_PEER_WAIT) peer_flags_wait(p.peer_flags, p.peer_world, p.peer_epoch);
+            continue;
         }
+        // cfg & 15: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = lane-split tile, G = 2^k lane groups;
+        // bit 6, bits 8-23: items.h (peer wait, j-split part k of K)
+        const int kcfg = it.cfg & 15;
+        if (kcfg >= 8) {
+            switch (kcfg) {
+                case 9: warp_force<1, 2>(p, it, s); break;
+                case 10: warp_force<1, 4>(p, it, s); break;
+                default: warp_force<1, 8>(p, it, s); break;
+            }
+        } else if (RMAX <= 2) {
+            if (kcfg == 0) warp_force<1, 1>(p, it, s);
+            else warp_force<2, 1>(p, it, s);
+        } else {
+            switch (kcfg) {
+                case 0: warp_force<1, 1>(p, it, s); break;
+                case 1: warp_force<2, 1>(p, it, s); break;
+                case 2: warp_force<3, 1>(p, it, s); break;
+                default: warp_force<4, 1>(p, it, s); break;
+            }
+        }
+        __syncwarp();               // the next item reuses this warp's shared-memory arrays
     }
 }
 

@@ -14,6 +14,12 @@ struct __align__(16) ForceAos { float acc[3]; float phi; int number, rank, id_ma
 static_assert(sizeof(EpiAos) == 48 && sizeof(EpjAos) == 112 && sizeof(SpjQuadAos) == 80 &&
               sizeof(SpjMonoAos) == 32 && sizeof(ForceAos) == 32, "reference layout");
 
-struct WorkItem { int walk, i0, ni, cfg; };
+// base item = one i-tile of one walk against its whole lists (what the cost sort orders); work item = the part of
+// a base item one warp executes: j-tiles [t0, t1) of the walk's tile sequence (EP tiles, then SP tiles; t1 < 0 = all).
+// Parts of a split tile share `group` (arrival counter) and write their partial sums to scratch slot slot0 + part
+// index (items.h: cfg bits).
+struct BaseItem { int walk, i0, ni, cfg; };
+struct __align__(16) WorkItem { int walk, i0, ni, cfg; int t0, t1, slot0, group; };
+static_assert(sizeof(BaseItem) == 16 && sizeof(WorkItem) == 32, "item layout");
 
 }  // namespace gb

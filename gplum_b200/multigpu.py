@@ -31,10 +31,11 @@ class MultiGpuPass:
     "peer"      no data moves ahead of time and no collective runs per step: every rank packs into
                 its own slab, the slabs are mapped into every process with CUDA IPC and boundary
                 walks gather the records they need straight from the owner's HBM over NVLink, tile
-                by tile, inside the force kernel.  "All slabs packed" is signalled through flag
-                words the ranks store into each other's memory over NVLink after packing; a
-                one-warp kernel on the boundary stream waits for them (slabs are double-buffered,
-                so this one barrier per step also covers the write-after-read hazard);
+                by tile, inside the force kernel.  A step is TWO launches: the pack kernel (EPJ slab,
+                superparticles, and "packed" flag words stored into every rank's memory over NVLink)
+                and one force launch over all walks, whose boundary items spin on those flags inside
+                the kernel while the interior items already run (slabs are double-buffered, so this
+                one barrier per step also covers the write-after-read hazard);
     "halo"      one all-to-all of only the records other ranks' boundary walks read;
     "allgather" in-place all-gather of every rank's packed slab."""
 
@@ -51,16 +52,34 @@ class MultiGpuPass:
         self.d_epj_raw = torch.from_numpy(lw.epj_all.view(np.uint8).copy()).cuda()
         wi, wb = sh.walks_interior, sh.walks_boundary
         self.n_interior, self.n_boundary = wi.n_walk, wb.n_walk
-        # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
-        F.walks_select(0)
-        F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
-                                wi.spj_disp, wi.n_spj, np.zeros(0, S.EPJ), lw.spj_all))
-        F.walks_select(1)
-        # the boundary set is small, but it co-runs with the interior kernel on a busy GPU: throughput,
-        # not one item's latency, is what counts -> full-width tiles instead of the per-pass choice
-        check(L.gplum_b200_set_tile_cap(boundary_cap))
-        F.walks_upload(wb, with_j=False)
-        check(L.gplum_b200_set_tile_cap(0))
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        if peer:
+            # the handles first: a walk set uploaded while peer mode is open flags the walks that read other ranks
+            h = (C.c_char * 128)()
+            check(L.gplum_b200_peer_setup(world, rank, sh.shift, h))
+            mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).cuda()
+            every = torch.zeros(world * 128, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(every, mine)
+            self._handles = every.cpu().numpy().tobytes()
+            check(L.gplum_b200_peer_open(self._handles))
+            self.exchange_bytes = 4 * world
+            # ONE walk set (interior and boundary walks in one work list, one launch per step) + the superparticles,
+            # which every rank holds itself
+            F.walks_select(0)
+            F.walks_upload(type(lw)(lw.epi, lw.epi_off, lw.ni, lw.adr_epj, lw.epj_disp, lw.n_epj, lw.adr_spj,
+                                    lw.spj_disp, lw.n_spj, np.zeros(0, S.EPJ), lw.spj_all))
+            dist.barrier()
+        else:
+            # slot 0: interior walks (+ the superparticles, which every rank holds itself); slot 1: boundary
+            F.walks_select(0)
+            F.walks_upload(type(lw)(wi.epi, wi.epi_off, wi.ni, wi.adr_epj, wi.epj_disp, wi.n_epj, wi.adr_spj,
+                                    wi.spj_disp, wi.n_spj, np.zeros(0, S.EPJ), lw.spj_all))
+            F.walks_select(1)
+            # the boundary set is small, but it co-runs with the interior kernel on a busy GPU: throughput,
+            # not one item's latency, is what counts -> full-width tiles instead of the per-pass choice
+            check(L.gplum_b200_set_tile_cap(boundary_cap))
+            F.walks_upload(wb, with_j=False)
+            check(L.gplum_b200_set_tile_cap(0))
         vp = lambda t: C.c_void_p(t.data_ptr())
         if halo:
             # local j-array = [own | halo]: own particles are packed in place, the halo region is the
@@ -74,15 +93,7 @@ class MultiGpuPass:
             check(L.gplum_b200_walks_set_packed_dev(vp(self.jbuf), n_own + n_halo, None, 0))
             self.exchange_bytes = (n_send + n_halo) * EB
         elif peer:
-            h = (C.c_char * 128)()
-            check(L.gplum_b200_peer_setup(world, rank, sh.shift, h))
-            mine = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).cuda()
-            every = torch.zeros(world * 128, dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(every, mine)
-            self._handles = every.cpu().numpy().tobytes()
-            check(L.gplum_b200_peer_open(self._handles))
-            self.exchange_bytes = 4 * world
-            dist.barrier()
+            pass
         else:
             # the gather buffer: every rank's packed slab; this rank packs straight into its own slab
             self.jbuf = torch.zeros(world * sh.epj_cap * EB, dtype=torch.uint8, device="cuda")
@@ -114,6 +125,22 @@ class MultiGpuPass:
     def step(self, trace=None):
         """One force pass of this rank.  trace: optional dict that receives timing events."""
         stream, side = self.stream, self.side
+        if self.exchange_kind == "peer":
+            # pack (EPJ slab + superparticles + flags to the peers, one launch) and ONE force launch: interior items
+            # start at once, boundary items wait for the peers' flags inside the kernel
+            if trace is not None:
+                ev = {k: torch.cuda.Event(enable_timing=True) for k in ("start", "packed", "int_end", "side_ready", "bnd_end")}
+                ev["start"].record(stream)
+            self.exchange()
+            if trace is not None:
+                ev["packed"].record(stream)
+            F.walks_select(0)
+            F.walks_run(repack=False)
+            if trace is not None:
+                for k in ("int_end", "side_ready", "bnd_end"):
+                    ev[k].record(stream)
+                trace["events"] = ev
+            return
         if trace is not None:
             ev = {k: torch.cuda.Event(enable_timing=True) for k in ("start", "packed", "int_end", "side_ready", "bnd_end")}
             ev["start"].record(stream)
@@ -129,7 +156,7 @@ class MultiGpuPass:
         with torch.cuda.stream(side):
             side.wait_event(self.ev_pack)  # the side stream waits for the packed SPJ ...
             self._use(side)
-            work.wait()                    # ... and for the exchange (NCCL work, or the peers' flags)
+            work.wait()                    # ... and for the exchange (NCCL work)
             if trace is not None:
                 ev["side_ready"].record(side)
             F.walks_select(1)
@@ -152,6 +179,9 @@ class MultiGpuPass:
         """This rank's forces (host, ForceGrav[ len(local.epi) ]) after step()."""
         torch.cuda.synchronize()
         n = len(self.lw.epi)
+        if self.exchange_kind == "peer":
+            F.walks_select(0)
+            return F.walks_download(n)
         out = S.cleared_force(n)
         for slot, ws in ((0, self.sh.walks_interior), (1, self.sh.walks_boundary)):
             if ws.n_walk == 0:

@@ -128,14 +128,17 @@ void gplum_b200_packed_sizes(int *epj_packed_bytes, int *spj_packed_bytes);
  * Every rank owns two slabs (double buffer) of 2^shift packed records; EP list indices are
  * (owner_rank << shift) | index_in_owner_slab.  peer_setup allocates the slabs and writes this
  * rank's two CUDA IPC handles (2 x 64 bytes) to handles_out; the caller all-gathers the handles
- * (rank-major) and passes them to peer_open.  peer_pack flips the buffer, packs n AoS records
- * (device pointer) into this rank's slab on the library stream and then stores the new epoch into
- * this rank's entry of EVERY rank's flag array (kept behind slab 0; remote ones over NVLink).
- * peer_wait enqueues, on the library stream, a one-warp kernel that spins until every rank's entry
- * of the local flag array has reached the epoch of the last peer_pack: walks launched after it may
- * read the other ranks' slabs.  No collective library call is on the path.  Because a rank only
- * packs epoch e+1 after its own walks of epoch e, having seen all flags at e+1 also means every
- * peer is done reading this rank's slab of epoch e -- the double buffer needs no second barrier.
+ * (rank-major) and passes them to peer_open.  peer_pack flips the buffer and, in ONE launch on the library
+ * stream, packs n AoS records (device pointer) into this rank's slab, packs the current j-set's
+ * superparticles, and stores the new epoch into this rank's entry of EVERY rank's flag array (kept
+ * behind slab 0; remote ones over NVLink).  Walk sets uploaded while peer mode is open know which of
+ * their walks name another rank's particles: those walks' work items spin INSIDE the force kernel until
+ * every rank's flag has reached the epoch of the last peer_pack, the others start at once, and one empty
+ * barrier item keeps the pass from ending before that -- pack + one force launch is a whole step, with
+ * no collective library call and no second stream on the path.  Because a rank only packs epoch e+1
+ * after its own pass of epoch e, having seen all flags at e+1 also means every peer is done reading this
+ * rank's slab of epoch e -- the double buffer needs no second barrier.  peer_wait enqueues the same wait
+ * as a one-warp kernel (for callers that launch their own kernels on peer data).
  * Every rank must call peer_pack the same number of times.  Replaces the EPJ part of FDPS's LET
  * exchange (FDPS/src/tree_for_force_impl_exlet.hpp:343-403) without moving data ahead of time.
  * peer_close unmaps, peer_free (after a barrier) releases the slabs. */
@@ -248,12 +251,18 @@ int gplum_b200_state_drift(const gplum_b200_iso_params *prm, double t0, double t
 int gplum_b200_state_pull_unhandled(void *rec_out, int *idx_out, int cap, int *n_out);
 int gplum_b200_state_push(const void *rec, const int *idx, int n_rec);
 
-/* The host work-list builder of the force pass, for tests (needs no device): cuts every walk into i-tiles
- * {walk, i0, ni, cfg} (4 ints each; cfg & 15: 0 = 32 i, 1 = 64 i, 9/10/11 = 16/8/4 i with the j-list split over
- * 2/4/8 lane groups; cfg & 16 / & 32: EP tiles only / SP tiles only), longest first. */
+/* The host work-list builder of the force pass, for tests (needs no device): cuts every walk into i-tiles and, in
+ * a pass with less than two waves of them (warp_slots), lays the tiles out as ONE wave of warp_slots equal-cost
+ * segments, cutting full-width tiles along j where a segment boundary falls.  One item = 8 ints
+ * {walk, i0, ni, cfg, t0, t1, slot0, group}: cfg & 15: 0 = 32 i, 1 = 64 i, 9/10/11 = 16/8/4 i with the j-list split
+ * over 2/4/8 lane groups; cfg bits 8-15 = K parts of this tile (0: whole tile), bits 16-23 = part index; [t0, t1) =
+ * the part's j-tiles of the walk's sequence (EP tiles of 64, then SP tiles; t1 < 0: all); slot0 + part index = its
+ * scratch record, group = its tile's arrival counter.  Longest base tile first.  seg_off_out (n_seg + 1 entries, n_seg
+ * = 0 when the pass is not segmented): warp s executes items [seg_off[s], seg_off[s+1]).  split_m = 0: never segment. */
 int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj,
-                                 long long warp_slots, int tile_cap, int jsplit, int epsp_split,
-                                 int *items_out, int cap_items, int *n_items_out, int *has_split_out);
+                                 long long warp_slots, int tile_cap, int jsplit, int split_m,
+                                 int *items_out, int cap_items, int *n_items_out, int *n_slots_out, int *n_groups_out,
+                                 int *seg_off_out, int cap_seg, int *n_seg_out);
 
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */

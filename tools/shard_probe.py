@@ -1,6 +1,6 @@
 """Per-rank pass of an N-way sharded run, emulated on one GPU: the first 1/k of the walks of the N=1e6
 workload (Morton-contiguous, like gplum_b200/shard.py's interior set), timed alone.  Usage:
-  GPLUM_B200_EPSP_SPLIT={0,-1,1} python tools/shard_probe.py [k ...]"""
+  GPLUM_B200_SPLIT_M={0,1,2,3,4} python tools/shard_probe.py [k ...]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,5 +22,5 @@ for k in [int(a) for a in sys.argv[1:]] or [1, 4, 8]:
     ms = F.walks_time(30, repack=False)
     if k == 1:
         full = ms
-    print("split=%s 1/%d of the walks: %d walks, %.4f ms per pass%s" % (
-        os.environ.get("GPLUM_B200_EPSP_SPLIT", "-1"), k, m, ms, "" if full is None else "  (x%d = %.3f of the full pass)" % (k, ms * k / full)))
+    print("split_m=%s 1/%d of the walks: %d walks, %.4f ms per pass%s" % (
+        os.environ.get("GPLUM_B200_SPLIT_M", "2"), k, m, ms, "" if full is None else "  (x%d = %.3f of the full pass)" % (k, ms * k / full)))
