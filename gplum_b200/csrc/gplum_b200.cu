@@ -83,6 +83,7 @@ struct PinBuf {
 struct WalkSet {
     DevBuf epi, epi_off, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, items, force;
     DevBuf scratch, arrive;      // partial sums and arrival counters of j-split tiles (items.h)
+    DevBuf force_org;            // forces in the caller's particle order (tree_download_original)
     DevBuf seg_off;              // segments of a one-wave pass: warp s runs items [seg_off[s], seg_off[s+1]) (items.h)
     int n_seg = 0;               // 0: one item per warp
     PinBuf h_force, h_stage;     // pinned: results, flattened inputs of dispatch()
@@ -106,7 +107,7 @@ struct WalkSet {
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
-        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &seg_off,
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &seg_off, &force_org,
                           &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp, &corr_compact})
             b->release();
         h_force.release(); h_stage.release();
@@ -157,6 +158,7 @@ struct Ctx {
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
+    int snake = 1;              // boustrophedon CTA order in passes of less than one wave (GPLUM_B200_SNAKE=0 disables)
     int split_m = 2;            // j-split of full-width tiles in passes with less than two waves of items: pieces per warp
                                 // slot (items.h); 0 = never (GPLUM_B200_SPLIT_M)
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
@@ -220,6 +222,18 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     const bool do_split = allow_split && g.rmax <= 2 && split_active((long long)tmp.size(), g.warp_slots, g.split_m);
     if (!do_split) {
         out.items.reserve(tmp.size());
+        // A pass whose CTAs are all resident at once (less than one wave) gets no dynamic balancing: CTA c lands on
+        // SM c mod n_sm, so with the plain longest-first order one SM collects the longest CTA of every round and
+        // another the shortest (measured: SMs active 82 % of the pass on a 1/8 shard).  Boustrophedon order -- every
+        // second round of n_sm CTAs reversed -- evens the per-SM sums out.
+        const long long n_full = (long long)tmp.size() / WPB, n_sm = g.warp_slots / 24;     // whole CTAs; a partial last one stays last
+        if (g.snake && allow_split && n_full > n_sm && (long long)tmp.size() <= g.warp_slots) {
+            for (long long r0 = n_sm; r0 < n_full; r0 += 2 * n_sm) {                          // every second round of n_sm CTAs
+                const long long r1 = std::min(r0 + n_sm, n_full);
+                for (long long a = r0, b = r1 - 1; a < b; a++, b--)
+                    for (int k = 0; k < WPB; k++) std::swap(tmp[(size_t)(a * WPB + k)], tmp[(size_t)(b * WPB + k)]);
+            }
+        }
         for (auto &t : tmp) {
             const BaseItem &b = t.second;
             const int wait = (peer_walk && peer_walk[b.walk]) ? ITEM_PEER_WAIT : 0;
@@ -498,6 +512,14 @@ __global__ void peer_wait_kernel(const int *flags, int world, int epoch)
     }
 }
 
+// out[idx[k]] = in[k] for 32 B ForceGrav records (two 16 B halves per record)
+__global__ void unsort_force_kernel(int n, const uint4 *__restrict__ in, const int *__restrict__ idx, uint4 *__restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n) return;
+    out[2 * (size_t)idx[t >> 1] + (t & 1)] = in[t];
+}
+
 __global__ void iota_kernel(int *p, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,6 +632,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
     if (const char *e = getenv("GPLUM_B200_SPLIT_M")) g.split_m = std::max(0, atoi(e));
+    if (const char *e = getenv("GPLUM_B200_SNAKE")) g.snake = atoi(e);
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
     CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
@@ -1522,6 +1545,24 @@ int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, lon
     }
     if (adr_epj && ws.n_adr_epj) CU(cudaMemcpy(adr_epj, ws.adr_epj.p, (size_t)ws.n_adr_epj * 4, D2H));
     if (adr_spj && ws.n_adr_spj) CU(cudaMemcpy(adr_spj, ws.adr_spj.p, (size_t)ws.n_adr_spj * 4, D2H));
+    return 0;
+}
+
+// forces of the GPU-built tree's pass in the order of the particles as they were handed in (FDPS's
+// copyForceOriginalOrder + writeBack, FDPS/src/tree_for_force_impl.hpp:873-883): scattered on the device, one D2H
+int gplum_b200_tree_download_original(void *force_out)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_download_original: no GPU-built tree in the selected slot");
+    if (!force_out) return fail(GPLUM_B200_ERR_ARG, "tree_download_original: NULL");
+    CU(cudaSetDevice(g.device));
+    WalkSet &ws = g.slots[g.cur];
+    const int n = (int)ws.n_epi;
+    if (int r = ws.force_org.reserve((size_t)n * sizeof(ForceAos))) return r;
+    unsort_force_kernel<<<(2 * n + 255) / 256, 256, 0, g.stream>>>(n, (const uint4 *)ws.force.p, gbt::tree_sorted_to_original(), (uint4 *)ws.force_org.p);
+    CU(cudaGetLastError());
+    g.launches++;
+    CU(cudaMemcpyAsync(force_out, ws.force_org.p, (size_t)n * sizeof(ForceAos), cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
     return 0;
 }
 

@@ -28,7 +28,13 @@ GB_HD void tile_next(int rem, int cap, bool split, int &n, int &shape)
 }
 
 // cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
-constexpr double COST_EP = 18.5, COST_SP = 37.0, COST_TILE = 90.0, COST_ITEM = 200.0;
+constexpr double COST_EP = 18.5, COST_SP = 37.0, COST_TILE = 90.0;
+#ifndef GB_COST_ITEM
+#define GB_COST_ITEM 4000.0
+#endif
+// per item: its prologue is a chain of dependent global loads (item -> walk record -> index list -> particles),
+// several microseconds in which the warp issues nothing; 4000 slots measured best for the segmented layout
+constexpr double COST_ITEM = GB_COST_ITEM;
 GB_HD double tile_cost(int n_epj, int n_spj, int shape)
 {
     const double cost_j = COST_EP * n_epj + COST_SP * n_spj;
@@ -66,7 +72,10 @@ GB_HD double tiles_cost(int n_epj, int n_spj, int shape, int t)
 // together and finish together -- no scheduling tail, every issue port has its full set of warps to the end.
 // (Equal PARTS of every tile were measured first: 2-4 parts per tile did not beat whole tiles on a 1/8 shard,
 // because the pass still ended on a tail of single warps; profiles/r2_split_probe.txt.)
-GB_HD bool split_active(long long n_base, long long warp_slots, int split_m) { return split_m > 0 && n_base > 0 && n_base < 2 * warp_slots; }
+// Measured on 1/4, 1/8 and 1/16 shards of the N = 1e6 disk (profiles/r2_split_probe.txt): with 0.3 waves of tiles or
+// more, whole tiles under the hardware's dynamic CTA scheduling are faster (short items' warps leave early and the
+// rest speed up); below that one wave of segments wins (0.081 against 0.095 ms at 1/16).  split_m scales the limit.
+GB_HD bool split_active(long long n_base, long long warp_slots, int split_m) { return split_m > 0 && n_base > 0 && n_base * 8 < warp_slots * split_m; }
 GB_HD long long item_cost_units(double cost) { return (long long)(cost + 0.5); }
 // segment of cost position x on a line of total cost W cut into n_seg pieces; boundary b sits at ceil(b W / n_seg)
 GB_HD long long seg_of(long long x, long long W, long long n_seg) { const long long s = (x * n_seg) / W; return s < n_seg ? s : n_seg - 1; }   // W n_seg < 2^63: passes that split are small

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(PACK_BLOCK) peer_pack_kernel(const EpjAos *__r
         return;
     }
     if (n_epj > 0) pack_epj_block(epj_in, n_epj, slab, blockIdx.x, sm);
-    __threadfence_system();                             // the records are read by other GPUs
+    __threadfence();                                    // records visible in this GPU's L2, where the peers' loads arrive
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == (unsigned int)(nb_e - 1));
     __syncthreads();

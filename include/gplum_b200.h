@@ -221,6 +221,10 @@ int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, lon
                              int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
                              int *sorted_to_original);
 int gplum_b200_tree_gpu_times(float *ms6);
+/* ForceGrav[n] of the last pass over the GPU-built tree, in the order the particles were handed to
+ * tree_build_gpu / tree_build_gpu_epj (FDPS's copyForceOriginalOrder + writeBack,
+ * FDPS/src/tree_for_force_impl.hpp:873-883, tree_for_force.hpp:148-153); host pointer, synchronises. */
+int gplum_b200_tree_download_original(void *force_out);
 /* diagnostics: %globaltimer (ns) at the level boundaries inside the cells+moments kernel of the last build;
  * returns the number of stamps written (<= cap) */
 int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap);
