@@ -3,23 +3,29 @@
 
 A "step" is one force pass (TreeForForce::calcForce: j-pack + every walk's EP-EP + EP-SP +
 neighbour-candidate detection + force write) over the interaction lists of a synthetic
-Kokubo-Ida disk.  Workload at any N: configs[2], N=1e6 planetesimals in a 0.9-1.1 AU annulus,
-sample/parameter.dat tree parameters, n_group_limit per --group.
+Kokubo-Ida disk.  Default workload: BASELINE configs[2], N=1e6 planetesimals in a 0.9-1.1 AU annulus,
+sample/parameter.dat tree parameters, n_group_limit per --group (--n / --a-in / --a-out: configs[1], [4]).
+The lists are FDPS's own, list for list (tests/test_tree.py pins the host builder to the compiled reference).
 
   value     interactions/s with raw particles + lists resident in HBM (CUDA events, max over ranks)
-  e2e       same metric through the reference-facing C ABI (gplum_b200_dispatch/retrieve, the
-            FDPS multi-walk-index functors) with pinned HOST buffers: H2D of j-particles, walks
-            and lists, kernels, D2H of forces, all inside the timed region; at N>1 every rank ships
-            what its rank of an MPI-FDPS run holds (own walks, local + LET particles, its SPJ)
+  e2e       N=1: the whole soft-force evaluation a caller of calcForceAllAndWriteBack sees, through the C ABI with
+            HOST buffers: raw particles (48 B each) up, tree + groups + lists built on the GPU, force pass, forces
+            back in particle order (32 B each) -- gplum_b200_tree_build_gpu + walks_run + tree_download_original.
+            N>1: every rank ships what its rank of an MPI-FDPS run holds through gplum_b200_dispatch/retrieve.
+  e2e_multiwalk (N=1) the FDPS multi-walk-index functors (dispatch/retrieve) with host-built lists shipped every pass
+  parity_check   after the timed region: this run's forces of every 50th walk against the oracle
+            (acc/phi 1e-4 with the conditioning floor of tests/synth.py, neighbour ints exact); non-zero exit on failure
   roofline  dominant kernel (force_pass_kernel): algorithmic flop (30/EP-EP pair, 59/EP-SP pair,
             SURVEY 8d) / its CUDA-event time, against the FP32 FFMA peak measured in the same run
-  cpu_baseline  the reference's own functors (oracle/_ref, AVX2+OpenMP build) on a bounded sample
+  cpu_baseline  the reference's own functors (oracle/_ref, AVX2+OpenMP build) on a bounded sample;
+  cpu_baseline_stage  the reference's whole stage (FDPS tree + walk + functors + correctForceLong) once
 
-`--impl reference` times only the reference CPU path (all host threads) on the same config.
-N>1 (torchrun): walks are sharded by Morton-contiguous domains; per step every rank packs its own
-j-particles and one NCCL all-to-all moves only the records other ranks' boundary walks need (the
-reference's LET exchange; `--exchange allgather` moves everything instead).  The exchange overlaps
-the interior walks; boundary walks run on a second stream when it lands (gplum_b200/shard.py).
+`--impl reference` times only the reference CPU path (all host threads) on the same config, with the lists the
+reference's own FDPS tree records (oracle/_ref; nothing of the product library is loaded).
+N>1 (torchrun): walks are sharded by Morton-contiguous domains; per step every rank packs its own j-particles and
+signals its peers in one launch, and one force launch evaluates all its walks -- the walks that read other ranks'
+particles gather them from the owners' HBM over NVLink inside the kernel, after an in-kernel wait for the peers'
+flags (gplum_b200/multigpu.py; `--exchange halo|allgather` use NCCL collectives instead).
 Fixed total work => strong scaling.
 """
 import argparse
@@ -34,6 +40,13 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the OpenMP build of FDPS (the CPU arms) keeps per-level arrays on the stack: 8 MB overflows at N >= 2e5
+try:
+    import resource
+    _h = resource.getrlimit(resource.RLIMIT_STACK)[1]
+    resource.setrlimit(resource.RLIMIT_STACK, (_h if _h != resource.RLIM_INFINITY and _h < (1 << 30) else (1 << 30), _h))
+except Exception:
+    pass
 # torchrun defaults OMP_NUM_THREADS to 1 per rank; the plugin's host side (list flattening, force accumulation in
 # dispatch/retrieve) is OpenMP code like the reference's: give every rank its share of the host cores
 if os.environ.get("LOCAL_WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
@@ -44,7 +57,8 @@ if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 FLOP_EPEP, FLOP_EPSP = 30.0, 59.0
-METRIC = "soft-force interactions/s (EP-EP+EP-SP), N=1e6 disk"
+def metric_name(n):
+    return "soft-force interactions/s (EP-EP+EP-SP), N=%s disk" % ("1e%d" % round(np.log10(n)) if 10 ** round(np.log10(n)) == n else str(n))
 
 
 def make_workload(n, group, seed=0, a_in=0.9, a_out=1.1):
@@ -121,6 +135,21 @@ def cpu_reference_run(w, eps2, budget_s, threads):
     return kind, s, O, lib, reps
 
 
+def reference_lists(args):
+    """The lists of the reference arm come from the reference itself: its FDPS tree records what it hands to the
+    dispatch functor (oracle/ref_shim.cpp: ref_tree_build).  Same lists as make_workload's, bit for bit
+    (tests/test_tree.py); falls back to the host builder where oracle/_ref does not exist."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    from gplum_b200 import disk
+    if not O.have_ref("scalar"):
+        return make_workload(args.n, args.group, a_in=args.a_in, a_out=args.a_out)[0]
+    d = disk.make_disk(args.n, a_in=args.a_in, a_out=args.a_out, seed=0)
+    r_out, r_search = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    return O.ref_tree_walks(d["pos"], d["mass"], r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=args.group,
+                            n_walk_limit=512, vel=d["vel"])
+
+
 def run_reference(args, w):
     threads = os.cpu_count()
     kind, s, O, lib, reps = cpu_reference_run(w, 0.0, args.cpu_seconds / max(1, args.steps + args.warmup), threads)
@@ -136,7 +165,7 @@ def run_reference(args, w):
     val = n_int / dt
     sample_desc = "%d of %d walks (every %d-th) of the same lists, %d pass(es) per step, %.3g interactions/step" % (
         s.n_walk, w.n_walk, max(1, w.n_walk // max(1, s.n_walk)), reps, n_int / args.steps)
-    return {"metric": METRIC, "value": val, "unit": "interactions/s", "impl": "reference", "n_gpus": args.gpus,
+    return {"metric": metric_name(args.n), "value": val, "unit": "interactions/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, w),
@@ -146,12 +175,72 @@ def run_reference(args, w):
 
 def workload_config(args, w):
     ee, es = w.n_interactions()
-    return {"workload": "Kokubo-Ida disk N=%d a=[0.9,1.1]AU (BASELINE configs[2]); theta=0.5 n_leaf_limit=8 "
-                        "n_group_limit=%d; individual cutoff, quadrupole SPJ" % (args.n, args.group),
+    cfg = {(1000000, 0.9, 1.1): "configs[2]", (100000, 0.9, 1.1): "configs[1]", (10000000, 0.5, 10.0): "configs[4]"}.get(
+        (args.n, args.a_in, args.a_out), "custom")
+    return {"workload": "Kokubo-Ida disk N=%d a=[%g,%g]AU (BASELINE %s); theta=0.5 n_leaf_limit=8 "
+                        "n_group_limit=%d; individual cutoff, quadrupole SPJ" % (args.n, args.a_in, args.a_out, cfg, args.group),
             "n_particles": args.n, "n_group_limit": args.group, "n_walks": int(w.n_walk),
             "interactions_epep": ee, "interactions_epsp": es,
-            "l2": "per-step inputs (lists+particles) exceed L2 at N=1e6; no flush",
+            "l2": getattr(args, "l2_note", "n/a"),
             "parallelism": "i-groups sharded over %d GPU(s), EPJ exchange: %s" % (args.gpus, getattr(args, "exchange", "halo"))}
+
+
+def parity_check(w, walk_range, force_local, e0, stride=50):
+    """Forces this run produced (force_local[k] belongs to i-particle e0 + k of the global walk set w) against the
+    oracle on every stride-th walk of [walk_range): acc/phi within 1e-4 (tests/synth.py: with the conditioning floor
+    the large-N tests use), neighbour ints exact.  Returns a dict; "ok" False on any violation."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    import synth
+    idx = np.arange(walk_range[0], walk_range[1], stride)
+    if len(idx) == 0:
+        return {"walks": 0, "particles": 0, "max_rel": 0.0, "ok": True}
+    s = O.Walks(w.epi, w.epi_off[idx], w.ni[idx], w.adr_epj, w.epj_disp[idx], w.n_epj[idx], w.adr_spj, w.spj_disp[idx],
+                w.n_spj[idx], w.epj_all, w.spj_all)
+    want, _ = O.calc_walks(s, 0.0, n_threads=0)
+    sa, sp = O.calc_walks_abs(s, 0.0)
+    sel = np.concatenate([np.arange(w.epi_off[k], w.epi_off[k] + w.ni[k]) for k in idx])
+    got = force_local[sel - e0]
+    an = np.linalg.norm(want["acc"][sel].astype(np.float64), axis=1)
+    rel = np.linalg.norm(got["acc"].astype(np.float64) - want["acc"][sel], axis=1) / np.maximum(an, 1e-300)
+    ok, msg = True, ""
+    try:
+        synth.assert_force_close(got, want[sel], 1e-4, "bench parity", cond=(sa[sel], sp[sel]))
+    except AssertionError as e:
+        ok, msg = False, str(e)[:200]
+    out = {"walks": int(len(idx)), "particles": int(len(sel)), "max_rel": float(rel.max()),
+           "above_1e-4": int((rel > 1e-4).sum()), "neighbour_ints_exact": bool(ok or "acc" in msg or "phi" in msg), "ok": ok}
+    if msg:
+        out["error"] = msg
+    return out
+
+
+def stage_baseline(args, w):
+    """The reference's whole stage on the host cores: tree_grav.calcForceAllAndWriteBack(...) + correctForceLong(...)
+    exactly as src/main_p3t.cpp:583-593 calls them, all OpenMP threads, AVX2 build (oracle/ref_shim.cpp: ref_stage_time)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    from gplum_b200 import structs as S
+    if not O.have_ref("simd"):
+        return None
+    raw = w.raw
+    t_force, t_corr, n_ngb = O.ref_stage_time(raw["pos"], w.raw_vel, raw["mass"], raw["r_out"], raw["r_search"], S.corr_params(),
+                                              theta=0.5, n_leaf_limit=8, n_group_limit=args.group, reps=2, kind="simd")
+    dt = t_force + t_corr
+    return {"ms_per_step": dt * 1e3, "calc_force_all_ms": t_force * 1e3, "correct_force_long_ms": t_corr * 1e3,
+            "interactions_per_s": sum(w.n_interactions()) / dt, "neighbours": n_ngb, "cores": os.cpu_count(), "kind": "reference",
+            "sample": "best of 2 evaluations of calcForceAllAndWriteBack + correctForceLong (src/main_p3t.cpp:583-593), "
+                      "n_group_limit=%d" % args.group}
+
+
+def captured_traffic(args, world):
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r2_force_pass_traffic.json")))
+        if world == 1 and (args.n, args.group, args.a_in, args.a_out) == (j["n"], j["group"], j["a_in"], j["a_out"]):
+            return int(j["dram_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 def pinned_like(a):
@@ -232,6 +321,55 @@ def soft_step_leg(args, w, F, S, L, check):
                    "correct_long_download_compact, pinned host buffers"}
 
 
+def tree_e2e_leg(args, w, F, S, L, check, reps):
+    """e2e at N = 1: one soft-force evaluation as the caller of calcForceAllAndWriteBack sees it
+    (FDPS/src/tree_for_force.hpp:1239-1253), through the C ABI with host buffers.  Inside the timed region, every
+    step: raw particles (pinned host SoA, 48 B each) -> device, Morton sort + tree + moments + i-groups + lists on
+    the GPU, force pass, forces scattered back to particle order and copied to pinned host memory (32 B each).
+    Also timed with PAGEABLE caller buffers (FDPS's arrays are pageable)."""
+    import ctypes as C
+    import torch
+    n = args.n
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    sz = np.zeros(8, dtype=np.int64)
+
+    def run(raw, out):
+        def one():
+            check(L.gplum_b200_tree_build_gpu(n, vp(raw["pos"]), vp(raw["mass"]), vp(raw["r_out"]), vp(raw["r_search"]),
+                                              0.5, 8, args.group, 0, vp(sz)))
+            F.walks_run(repack=False)
+            check(L.gplum_b200_tree_download_original(vp(out)))
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    raw_pin = {k: pin(np.ascontiguousarray(v, dtype=np.float64)) for k, v in w.raw.items()}
+    out_pin = pin(np.zeros(n, dtype=S.FORCE))
+    dt = run(raw_pin, out_pin)
+    # the forces that came back are the pass's forces, in particle order
+    order = w.epi["id_local"]
+    F.walks_upload(w); F.walks_run(repack=True)
+    ref = F.walks_download(n)
+    same = bool(np.array_equal(out_pin["number"][order], ref["number"]) and
+                np.allclose(out_pin["acc"][order], ref["acc"], rtol=1e-4, atol=0))
+    raw_page = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in w.raw.items()}
+    dt_page = run(raw_page, np.zeros(n, dtype=S.FORCE))
+    n_int = int(sz[6] + sz[7])
+    assert (int(sz[6]), int(sz[7])) == w.n_interactions(), "GPU-built lists differ from FDPS's"
+    return {"value": n_int / dt, "unit": "interactions/s", "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int(32 * n),
+            "ms_per_step": dt * 1e3, "ms_per_step_pageable_buffers": dt_page * 1e3, "forces_match_resident_pass": same,
+            "api": "gplum_b200_tree_build_gpu + gplum_b200_walks_run + gplum_b200_tree_download_original, pinned host buffers "
+                   "(include/gravity_tree_b200.hpp binds these behind calcForceAllAndWriteBack)"}
+
+
 def resident_step_leg(args, w, F, S, L, check):
     """SURVEY 8f-3 on top of f1 + f2: the particles stay in HBM across steps.  One step, all inside the timed
     region: velKick, Kepler drift of the isolated particles, the particles that need the host's hard part
@@ -298,7 +436,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=1000000)
     ap.add_argument("--group", type=int, default=512)
+    ap.add_argument("--a-in", type=float, default=0.9)
+    ap.add_argument("--a-out", type=float, default=1.1)
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-stage-baseline", action="store_true", help="skip the one evaluation of the reference's whole stage")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--boundary-cap", type=int, default=32, help="N>1: i-particles per work item of the boundary walks")
     ap.add_argument("--exchange", default="peer", choices=["peer", "halo", "allgather"],
@@ -313,8 +454,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        w, _ = make_workload(args.n, args.group)
-        print(json.dumps(run_reference(args, w)))
+        print(json.dumps(run_reference(args, reference_lists(args))))
         return
 
     import torch
@@ -327,7 +467,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    w, t_build = make_workload(args.n, args.group)
+    w, t_build = make_workload(args.n, args.group, a_in=args.a_in, a_out=args.a_out)
     ee, es = w.n_interactions()
     F.init(local_rank)
     F.set_params(0.0, True, 0)
@@ -357,18 +497,40 @@ def main():
         my_int = sum(lw.n_interactions())
         step, exchange, exch_bytes = mg.step, mg.exchange, mg.exchange_bytes
 
+    # bytes one step of this rank reads: when they fit the 126 MB L2 a step would find the previous step's data there,
+    # so a buffer larger than L2 is written between the timed steps (each step timed by its own pair of events)
+    mine = w if world == 1 else lw
+    step_bytes = (48 + 32) * len(mine.epi) + 4 * (len(mine.adr_epj) + len(mine.adr_spj)) + 160 * len(mine.epj_all) + 144 * len(mine.spj_all)
+    l2_flush = step_bytes < 2 * 126e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if l2_flush else None
     for _ in range(args.warmup):
         step()
     barrier()
     F.counters(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    if l2_flush:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evs:
+            flush_buf.zero_()
+            a.record(stream)
+            step()
+            b.record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
     launches, c_ee, c_es = F.counters()
+    args.l2_note = ("this rank's per-step inputs (%.0f MB) fit the 126 MB L2: a 256 MB buffer is written between timed "
+                    "steps, each step timed by its own CUDA events" % (step_bytes / 1e6)) if l2_flush else (
+                    "per-step inputs (%.0f MB of lists + particles) exceed the 126 MB L2; no flush" % (step_bytes / 1e6))
+    # ---- parity of THIS run's forces (every 50th walk of this rank) against the oracle
+    parity = parity_check(w, (0, w.n_walk) if world == 1 else sh.walk_range,
+                          F.walks_download(len(w.epi)) if world == 1 else mg.forces(), 0 if world == 1 else sh.epi_range[0])
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     n_int = torch.tensor([float(my_int)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -439,13 +601,15 @@ def main():
         4 * ((len(w.adr_epj) + len(w.adr_spj)) if world == 1 else (len(sh.local.adr_epj) + len(sh.local.adr_spj)))
     roofline = {"bound": "fp32", "kernel": "force_pass_kernel", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
-                # (profiles/r1_force_pass_v5_ncu_summary.txt: 235.96 MB read + 32.71 MB written); other
-                # workloads have no capture
-                "traffic": 268674560 if (world == 1 and args.n == 1000000 and args.group == 512) else None,
+                # DRAM bytes of one launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+                # `ncu --set full` capture of this workload by the same kernel source (profiles/r2_force_pass_traffic.json,
+                # written by tools/ncu_traffic.py); null for workloads without a capture
+                "traffic": captured_traffic(args, world),
                 "traffic_unit": "bytes/launch",
+                "peak_nominal": 74.4,
                 "peak_source": "FFMA microbenchmark in this run (MEASURED_PEAKS.json has no CUDA-core figure); "
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
+                "frac_of_nominal": achieved / 74.4,
                 "kernel_ms": k_ms, "flop_per_launch": flop,
                 "interactions_per_s_kernel_only": (my_ee + my_es) / (k_ms * 1e-3),
                 "gflops_38flop_convention": 38.0 * (my_ee + my_es) / (k_ms * 1e-3) / 1e9,
@@ -503,6 +667,13 @@ def main():
            "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e.item() * 1e3,
            "api": "gplum_b200_dispatch(send_all) + gplum_b200_dispatch(walks) + gplum_b200_retrieve, pinned host buffers"}
     F.set_params(0.0, True, 0)
+    e2e_multiwalk = None
+    if world == 1:
+        # the headline e2e at N = 1 is the whole evaluation a caller of calcForceAllAndWriteBack sees: raw particles in
+        # host memory -> tree, groups and lists built on the GPU -> force pass -> forces back in particle order.
+        # (the multi-walk-index functors above ship host-built lists every pass: reported as e2e_multiwalk)
+        e2e_multiwalk = e2e
+        e2e = tree_e2e_leg(args, w, F, S, L, check, n_e2e)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -512,16 +683,29 @@ def main():
         dist.all_gather_object(all_phases, {k: (round(v, 4) if isinstance(v, float) else v) for k, v in phases.items()
                                             if k in ("rank", "step_ms", "host_enqueue_ms", "timeline_ms", "exchange_ms", "interior_kernel_ms", "boundary_kernel_ms",
                                                      "interior_walks", "boundary_walks")})
+    par_all = [parity]
+    if world > 1:
+        par_all = [None] * world
+        dist.all_gather_object(par_all, parity)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
-
-    out = {"metric": METRIC, "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
+        sys.exit(0 if parity["ok"] else 3)
+    parity_out = {"walks": sum(p["walks"] for p in par_all), "particles": sum(p["particles"] for p in par_all),
+                  "max_rel": max(p["max_rel"] for p in par_all), "above_1e-4": sum(p["above_1e-4"] for p in par_all),
+                  "ok": all(p["ok"] for p in par_all), "ranks_checked": len(par_all),
+                  "what": "forces of the timed run, every 50th walk of every rank, against the oracle (acc/phi 1e-4 "
+                          "with the conditioning floor of tests/synth.py; number/id_max/id_min/rank==0 exact)"}
+    errs = [p["error"] for p in par_all if "error" in p]
+    if errs:
+        parity_out["errors"] = errs
+    out = {"metric": metric_name(args.n), "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, w),
            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-           "list_build_s_host": t_build}
+           "parity_check": parity_out, "list_build_s_host": t_build}
+    if e2e_multiwalk is not None:
+        out["e2e_multiwalk"] = e2e_multiwalk
     if soft_corr is not None:
         out["soft_corr"] = soft_corr
     if soft_step is not None:
@@ -540,9 +724,15 @@ def main():
         out["cpu_baseline"] = {"value": n / dt, "unit": "interactions/s", "cores": threads, "kind": kind,
                                "sample": "%d of %d walks of the same lists x %d passes (%.3g interactions, %.1f s)" % (
                                    s.n_walk, w.n_walk, reps, n, dt)}
+    if world == 1 and not args.no_cpu_baseline and not args.no_stage_baseline:
+        st = stage_baseline(args, w)
+        if st is not None:
+            out["cpu_baseline_stage"] = st
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if not parity_out["ok"]:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -334,6 +334,66 @@ long long ref_correct_long(int n, const double *pos, const double *vel, const do
     return off;
 }
 
+// ---- the reference's whole soft-force stage, timed (bench.py: cpu_baseline_stage) ----
+// Exactly the calls of src/main_p3t.cpp:583-593: tree_grav.calcForceAllAndWriteBack(calcForceEPEPWithSearch(),
+// calcForceEPSP(), system_grav, dinfo, true, MAKE_LIST, false) and correctForceLong(...), on one rank with all
+// OpenMP threads.  seconds_out[0] = force stage (tree build + walks + functors + write-back), [1] = correctForceLong,
+// both the minimum over `reps` repetitions; returns the number of neighbours found (>= 0).
+long long ref_stage_time(int n, const double *pos, const double *vel, const double *mass, const double *r_out,
+                         const double *r_search, double theta, int n_leaf_limit, int n_group_limit, double eps2,
+                         double dt_tree, double gamma, double R_search2, double R_search3, int reps, double *seconds_out)
+{
+    if (!g_ps_initialized) {
+        int argc = 1;
+        char arg0[] = "ref_shim";
+        char *argv_[] = {arg0, nullptr};
+        char **argv = argv_;
+        PS::Initialize(argc, argv);
+        g_ps_initialized = true;
+    }
+    FP_t::eps2 = eps2;
+    FP_t::dt_tree = dt_tree;
+    FP_t::R_search2 = R_search2;
+    FP_t::R_search3 = R_search3;
+    FP_t::setGamma(gamma);
+    PS::ParticleSystem<FP_t> psys;
+    psys.initialize();
+    psys.setNumberOfParticleLocal(n);
+    for (int i = 0; i < n; i++) {
+        psys[i].id = i;
+        psys[i].pos = PS::F64vec(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+        psys[i].vel = PS::F64vec(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        psys[i].acc_d = 0.0;
+        psys[i].mass = mass[i];
+        psys[i].r_out = r_out[i];
+        psys[i].r_out_inv = 1. / r_out[i];
+        psys[i].r_search = r_search[i];
+    }
+    NeighborList NList;
+    setIDLocalAndMyrank(psys, NList);
+    PS::DomainInfo dinfo;
+    dinfo.initialize(0.3);
+    dinfo.setNumberOfDomainMultiDimension(1, 1, 1);
+    dinfo.setBoundaryCondition(PS::BOUNDARY_CONDITION_OPEN);
+    dinfo.collectSampleParticle(psys, true);
+    dinfo.decomposeDomain();
+    Tree_t tree;
+    tree.initialize(n, theta, n_leaf_limit, n_group_limit);
+    PS::S32 n_ngb_tot = 0, n_with_ngb = 0;
+    double best_f = 1e300, best_c = 1e300;
+    for (int r = 0; r < reps; r++) {
+        const double t0 = PS::GetWtime();
+        tree.calcForceAllAndWriteBack(calcForceEPEPWithSearch(), calcForceEPSP(), psys, dinfo, true, PS::MAKE_LIST, false);
+        const double t1 = PS::GetWtime();
+        correctForceLong(psys, tree, NList, n_ngb_tot, n_with_ngb);
+        const double t2 = PS::GetWtime();
+        best_f = std::min(best_f, t1 - t0);
+        best_c = std::min(best_c, t2 - t1);
+    }
+    seconds_out[0] = best_f; seconds_out[1] = best_c;
+    return n_ngb_tot;
+}
+
 // ---- snapshot wire format: layout of the raw records the reference dumps ----
 // snap_tmp.dat = FileHeader (src/energy.h:70-127, fwrite of the struct) + n_body x FPGrav (src/particle.h:860-876).
 // out[] = sizeof(FileHeader), sizeof(Energy), offsetof(FileHeader: n_body, id_next, time, e_init, e_now),

@@ -221,6 +221,23 @@ def ref_correct_long(pos, vel, acc_d, mass, r_out, r_search, ids, prm, theta=0.5
     return w, force, res, lists
 
 
+def ref_stage_time(pos, vel, mass, r_out, r_search, prm, theta=0.5, n_leaf_limit=8, n_group_limit=64, reps=1, kind="simd"):
+    """Seconds of the reference's own soft-force stage on this host (oracle/ref_shim.cpp: ref_stage_time):
+    (calcForceAllAndWriteBack, correctForceLong, neighbours found).  The OpenMP build of FDPS keeps per-level
+    arrays on the stack: the caller must have raised RLIMIT_STACK (bench.py does) for N >= 2e5."""
+    lib = ref(kind)
+    lib.ref_stage_time.restype = C.c_longlong
+    lib.ref_stage_time.argtypes = [_i] + [_vp] * 5 + [C.c_double, _i, _i] + [C.c_double] * 5 + [_i, _vp]
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pos, vel, mass, r_out, r_search = map(f64, (pos, vel, mass, r_out, r_search))
+    sec = np.zeros(2)
+    p = prm[0]
+    n_ngb = lib.ref_stage_time(len(pos), _ptr(pos), _ptr(vel), _ptr(mass), _ptr(r_out), _ptr(r_search), theta, n_leaf_limit,
+                               n_group_limit, float(p["eps2"]), float(p["dt_tree"]), float(p["gamma"]), float(p["R_search2"]),
+                               float(p["R_search3"]), int(reps), _ptr(sec))
+    return float(sec[0]), float(sec[1]), int(n_ngb)
+
+
 # ------------------------------------------------------------------ isolated-particle step (SURVEY 8 f3)
 ISO_PARAMS = np.dtype([("m_sun", "<f8"), ("dt_tree", "<f8"), ("eta_0", "<f8"), ("eta_sun0", "<f8"),
                        ("alpha2", "<f8"), ("dt_min", "<f8"), ("eps2_sun", "<f8")])
