@@ -358,8 +358,9 @@ def tree_e2e_leg(args, w, F, S, L, check, reps):
     order = w.epi["id_local"]
     F.walks_upload(w); F.walks_run(repack=True)
     ref = F.walks_download(n)
-    same = bool(np.array_equal(out_pin["number"][order], ref["number"]) and
-                np.allclose(out_pin["acc"][order], ref["acc"], rtol=1e-4, atol=0))
+    da = np.linalg.norm(out_pin["acc"][order].astype(np.float64) - ref["acc"], axis=1) / np.linalg.norm(ref["acc"].astype(np.float64), axis=1)
+    same = bool(np.array_equal(out_pin["number"][order], ref["number"]) and np.array_equal(out_pin["id_max"][order], ref["id_max"])
+                and np.quantile(da, 0.9999) < 1e-4 and da.max() < 2e-3)        # list order inside a walk differs: last bits
     raw_page = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in w.raw.items()}
     dt_page = run(raw_page, np.zeros(n, dtype=S.FORCE))
     n_int = int(sz[6] + sz[7])

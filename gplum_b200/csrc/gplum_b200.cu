@@ -164,7 +164,9 @@ struct Ctx {
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
     long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
     DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
-    PinBuf tree_pin;            // pinned staging of pageable SoA inputs
+    PinBuf tree_pin;            // pinned staging of pageable host inputs (upload_host)
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    bool stage_used[2] = {false, false};
     bool tree_built = false;    // the selected slot + j-set hold a GPU-built tree
     // device-resident particle state (iso_step.cu): EPJGrav[n] with particle k at slot k, + time, dt, acc0, flags
     DevBuf st_epj, st_time, st_dt, st_acc0, st_iso, st_star, st_handled, st_rec, st_idx, st_cnt;
@@ -1413,6 +1415,81 @@ int gplum_b200_fp32_peak(int iters, float *tflops, float *ms_out)
 
 // ---- interaction lists built on the GPU (dev_tree.cu) ----
 namespace {
+// Host -> device copy of a caller's array that may be PAGEABLE (FDPS's ReallocatableArrays, std::vectors): a plain
+// cudaMemcpyAsync from pageable memory is staged by the driver at a fraction of the PCIe rate.  Here the array is cut
+// into chunks that OpenMP threads copy into two pinned staging buffers while the previous chunk is on the wire.
+// Pinned arrays go straight through.  The copy is complete on the stream, not on return.
+constexpr size_t STAGE_CHUNK = 8u << 20;
+int upload_host(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return 0;
+    cudaPointerAttributes at;
+    const cudaError_t pe = cudaPointerGetAttributes(&at, src);
+    if (pe != cudaSuccess) cudaGetLastError();
+    if (pe == cudaSuccess && at.type != cudaMemoryTypeUnregistered) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    if (int r = g.tree_pin.reserve(2 * STAGE_CHUNK)) return r;
+    if (!g.ev_stage[0]) for (auto &e : g.ev_stage) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    char *pin[2] = {(char *)g.tree_pin.p, (char *)g.tree_pin.p + STAGE_CHUNK};
+    int k = 0;
+    for (size_t off = 0; off < bytes; off += STAGE_CHUNK, k ^= 1) {
+        const size_t nb = std::min(STAGE_CHUNK, bytes - off);
+        if (g.stage_used[k]) CU(cudaEventSynchronize(g.ev_stage[k]));          // the copy that last used this buffer is done
+        const char *s0 = (const char *)src + off;
+        const long long n_part = (long long)((nb + (1u << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static)
+        for (long long q = 0; q < n_part; q++) {
+            const size_t a = (size_t)q << 20, b = std::min(nb, a + (1u << 20));
+            memcpy(pin[k] + a, s0 + a, b - a);
+        }
+        CU(cudaMemcpyAsync((char *)dst + off, pin[k], nb, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(g.ev_stage[k], st));
+        g.stage_used[k] = true;
+    }
+    return 0;
+}
+
+// Device -> host copy into a caller's array that may be pageable: chunks land in the pinned staging buffers and
+// OpenMP threads copy chunk k out while chunk k+1 is on the wire.  Complete on return.
+int download_host(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return 0;
+    cudaPointerAttributes at;
+    const cudaError_t pe = cudaPointerGetAttributes(&at, dst);
+    if (pe != cudaSuccess) cudaGetLastError();
+    if (pe == cudaSuccess && at.type != cudaMemoryTypeUnregistered) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return 0;
+    }
+    if (int r = g.tree_pin.reserve(2 * STAGE_CHUNK)) return r;
+    if (!g.ev_stage[0]) for (auto &e : g.ev_stage) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) if (g.stage_used[k]) { CU(cudaEventSynchronize(g.ev_stage[k])); g.stage_used[k] = false; }
+    char *pin[2] = {(char *)g.tree_pin.p, (char *)g.tree_pin.p + STAGE_CHUNK};
+    const size_t n_chunk = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    for (size_t c = 0; c <= n_chunk; c++) {
+        if (c < n_chunk) {
+            const size_t off = c * STAGE_CHUNK, nb = std::min(STAGE_CHUNK, bytes - off);
+            CU(cudaMemcpyAsync(pin[c & 1], (const char *)src + off, nb, cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(g.ev_stage[c & 1], st));
+        }
+        if (c > 0) {
+            const size_t off = (c - 1) * STAGE_CHUNK, nb = std::min(STAGE_CHUNK, bytes - off);
+            CU(cudaEventSynchronize(g.ev_stage[(c - 1) & 1]));
+            const long long n_part = (long long)((nb + (1u << 20) - 1) >> 20);
+            const char *p0 = pin[(c - 1) & 1];
+#pragma omp parallel for schedule(static)
+            for (long long q = 0; q < n_part; q++) {
+                const size_t a = (size_t)q << 20, b = std::min(nb, a + (1u << 20));
+                memcpy((char *)dst + off + a, p0 + a, b - a);
+            }
+        }
+    }
+    return 0;
+}
+
 int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_leaf_limit, int n_group_limit, long long *sizes)
 {
     if (g.rmax > 2) return fail(GPLUM_B200_ERR_STATE, "the GPU list builder needs the RMAX <= 2 kernel");
@@ -1493,11 +1570,10 @@ int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, cons
     if (int r = g.tree_in.reserve(N * 48)) return r;
     if (int r = g.tree_raw.reserve(N * sizeof(EpjAos))) return r;
     double *d = (double *)g.tree_in.p;
-    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
-    CU(cudaMemcpyAsync(d, pos, N * 24, H2D, st));
-    CU(cudaMemcpyAsync(d + 3 * N, mass, N * 8, H2D, st));
-    CU(cudaMemcpyAsync(d + 4 * N, r_out, N * 8, H2D, st));
-    CU(cudaMemcpyAsync(d + 5 * N, r_search, N * 8, H2D, st));
+    if (int r = upload_host(d, pos, N * 24, st)) return r;
+    if (int r = upload_host(d + 3 * N, mass, N * 8, st)) return r;
+    if (int r = upload_host(d + 4 * N, r_out, N * 8, st)) return r;
+    if (int r = upload_host(d + 5 * N, r_search, N * 8, st)) return r;
     int launches = 0;
     if (int e = gbt::tree_soa_to_epj(n, d, d + 3 * N, d + 4 * N, d + 5 * N, rank, g.tree_raw.p, st, &launches))
         return fail(GPLUM_B200_ERR_CUDA, "soa_to_epj: %s", cudaGetErrorString((cudaError_t)e));
@@ -1514,7 +1590,7 @@ int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double 
     const void *src = epj;
     if (!on_device) {
         if (int r = g.tree_raw.reserve((size_t)n * sizeof(EpjAos))) return r;
-        CU(cudaMemcpyAsync(g.tree_raw.p, epj, (size_t)n * sizeof(EpjAos), cudaMemcpyHostToDevice, g.stream));
+        if (int r = upload_host(g.tree_raw.p, epj, (size_t)n * sizeof(EpjAos), g.stream)) return r;
         src = g.tree_raw.p;
     }
     return tree_build_common(n, src, theta, n_leaf_limit, n_group_limit, sizes);
@@ -1561,9 +1637,7 @@ int gplum_b200_tree_download_original(void *force_out)
     unsort_force_kernel<<<(2 * n + 255) / 256, 256, 0, g.stream>>>(n, (const uint4 *)ws.force.p, gbt::tree_sorted_to_original(), (uint4 *)ws.force_org.p);
     CU(cudaGetLastError());
     g.launches++;
-    CU(cudaMemcpyAsync(force_out, ws.force_org.p, (size_t)n * sizeof(ForceAos), cudaMemcpyDeviceToHost, g.stream));
-    CU(cudaStreamSynchronize(g.stream));
-    return 0;
+    return download_host(force_out, ws.force_org.p, (size_t)n * sizeof(ForceAos), g.stream);
 }
 
 int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap)
