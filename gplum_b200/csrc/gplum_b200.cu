@@ -158,6 +158,8 @@ struct Ctx {
     long long warp_slots = 148 * 24;   // resident warps of the force kernel on this device
     int tile_cap = 0;           // 0 = choose per pass (build_items), else the i-tile capacity to use
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
+    int bulk = 0;               // GPLUM_B200_BULK=1: EP tiles staged by bulk copies (cp.async.bulk + mbarrier) of index runs;
+                                // default per-record cp.async, measured 2 % faster (profiles/r2_bulk_copy_probe.txt)
     int snake = 1;              // boustrophedon CTA order in passes of less than one wave (GPLUM_B200_SNAKE=0 disables)
     int split_m = 2;            // j-split of full-width tiles in passes with less than two waves of items: pieces per warp
                                 // slot (items.h); 0 = never (GPLUM_B200_SPLIT_M)
@@ -354,8 +356,12 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
         p.pair_cap = ws.pair_cap;
     }
     const int n_warps = n_seg > 0 ? n_seg : n_items;
-    if (g.rmax <= 2) force_pass_kernel<2><<<(n_warps + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
-    else force_pass_kernel<4><<<(n_warps + WPB - 1) / WPB, WPB * 32, g.smem_bytes, st>>>(p, n_items);
+    // bulk-copy staging of the EP tiles (kernels.cuh) or per-record cp.async; peer slabs are always gathered by cp.async
+    const bool bulk = g.bulk && !g.peer.on;
+    const dim3 grid((n_warps + WPB - 1) / WPB), block(WPB * 32);
+    if (g.rmax > 2) force_pass_kernel<4, false><<<grid, block, g.smem_bytes, st>>>(p, n_items);
+    else if (bulk) force_pass_kernel<2, true><<<grid, block, g.smem_bytes, st>>>(p, n_items);
+    else force_pass_kernel<2, false><<<grid, block, g.smem_bytes, st>>>(p, n_items);
     CU(cudaGetLastError());
     g.launches++;
     return 0;
@@ -593,8 +599,9 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
     p.scratch = nullptr; p.arrive = nullptr; p.peer_flags = nullptr; p.peer_world = 0; p.peer_epoch = 0;
     p.seg_off = nullptr; p.n_seg = 0;
-    if (g.rmax <= 2) force_pass_kernel<2><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
-    else force_pass_kernel<4><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
+    if (g.rmax > 2) force_pass_kernel<4, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
+    else if (g.bulk) force_pass_kernel<2, true><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
+    else force_pass_kernel<2, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     CU(cudaGetLastError());
     g.launches++;
     if (which == 0) g.n_epep += (long long)ni * nj; else g.n_epsp += (long long)ni * nj;
@@ -635,9 +642,11 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
     if (const char *e = getenv("GPLUM_B200_SPLIT_M")) g.split_m = std::max(0, atoi(e));
     if (const char *e = getenv("GPLUM_B200_SNAKE")) g.snake = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_BULK")) g.bulk = atoi(e) ? 1 : 0;
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
-    CU(cudaFuncSetAttribute(force_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
-    CU(cudaFuncSetAttribute(force_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
+    CU(cudaFuncSetAttribute(force_pass_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
+    CU(cudaFuncSetAttribute(force_pass_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
+    CU(cudaFuncSetAttribute(force_pass_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<128>) * WPB));
     g.warp_slots = (long long)prop.multiProcessorCount * 24;      // 6 CTAs x 4 warps per SM (80 registers)
     g.device = device;
     if (max_i) {
