@@ -371,6 +371,73 @@ def tree_e2e_leg(args, w, F, S, L, check, reps):
                    "(include/gravity_tree_b200.hpp binds these behind calcForceAllAndWriteBack)"}
 
 
+def multi_soft_step_leg(args, w, F, S, L, check, world, rank, dist, torch):
+    """The soft-force evaluation of an N-GPU run without host-side lists (SURVEY 8e with 8f-1/2): every rank ships
+    ITS n / world particles (pinned host EPJGrav records) to its GPU, the ranks all-gather the records over NVLink
+    (NCCL), every GPU builds the same tree and evaluates its Morton-contiguous share of the walks -- forces, changeover
+    correction, neighbour lists --, and every rank copies back the forces of its share and the corrections of its
+    particles that have neighbours.  Wall clock per step, max over ranks."""
+    import ctypes as C
+    from gplum_b200 import state as ST
+    from gplum_b200.multigpu import MultiGpuSoftStep
+    n = args.n
+    if n % world:
+        return None
+    m = n // world
+    epj = ST.make_epj(w.raw["pos"][rank * m:(rank + 1) * m], w.raw_vel[rank * m:(rank + 1) * m], w.raw["mass"][rank * m:(rank + 1) * m],
+                      w.raw["r_out"][rank * m:(rank + 1) * m], w.raw["r_search"][rank * m:(rank + 1) * m],
+                      ids=np.arange(rank * m, (rank + 1) * m))
+    epj["id_local"] = np.arange(rank * m, (rank + 1) * m)
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    p_epj = pin(epj)
+    p_force = pin(np.zeros(n, dtype=S.FORCE))
+    ms = MultiGpuSoftStep(epj, n, world, rank, theta=0.5, n_leaf_limit=8, n_group_limit=args.group)
+    prm = S.corr_params()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    p_corr = pin(np.zeros(n, dtype=S.CORR))
+    ngb_cap = 4 * n + (1 << 20)
+    p_ngb = pin(np.zeros(ngb_cap, dtype=S.NGB))
+    n_slots, n_pairs, n_corr = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+
+    def one():
+        ms.upload_local(p_epj)
+        ms.step(prm)
+        ms.forces(out=p_force)
+        check(L.gplum_b200_correct_long_download_compact(0, vp(p_corr), n, C.byref(n_corr), vp(p_ngb), ngb_cap,
+                                                         C.byref(n_slots), C.byref(n_pairs)))
+
+    F.walks_select(0)
+    F.soft_corr_enable(True)
+    try:
+        for _ in range(3):
+            one()
+        torch.cuda.synchronize(); dist.barrier()
+        reps = max(3, args.steps // 2)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            one()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        phases = {}
+        from gplum_b200 import tree
+        phases = tree.gpu_build_times()
+    finally:
+        F.soft_corr_enable(False)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    w0, w1, e0, e1 = ms.share()
+    mine = torch.tensor([float(ms.sizes[6] + ms.sizes[7]), float(e1 - e0), float(n_corr.value)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    return {"ms_per_step": dt.item() * 1e3, "interactions_per_s": mine[0].item() / dt.item(),
+            "interactions": int(mine[0].item()), "particles_covered": int(mine[1].item()), "particles_with_neighbours": int(mine[2].item()),
+            "h2d_bytes_per_rank": int(112 * m), "allgather_bytes_per_rank": int(112 * n),
+            "rank0_share": {"walks": [w0, w1], "particles": [e0, e1]},
+            "rank0_list_build_gpu_phases_ms": {k: round(v, 4) for k, v in phases.items()},
+            "api": "all_gather_into_tensor (NCCL) + gplum_b200_tree_build_gpu_part + walks_run + correct_long_run + "
+                   "walks_download_range + correct_long_download_compact"}
+
+
 def resident_step_leg(args, w, F, S, L, check):
     """SURVEY 8f-3 on top of f1 + f2: the particles stay in HBM across steps.  One step, all inside the timed
     region: velKick, Kepler drift of the isolated particles, the particles that need the host's hard part
@@ -618,7 +685,10 @@ def main():
 
     # ------------------------------------------------------------------ end to end via the C ABI
     if world > 1:
-        mg.close()
+        mg.close()                               # peer mode off: the legs below use plain indices
+        soft_step = multi_soft_step_leg(args, w, F, S, L, check, world, rank, dist, torch)
+        if soft_step is not None and soft_step["interactions"] != ee + es:
+            soft_step["error"] = "the ranks' lists do not add up to the single-rank pass (%d vs %d)" % (soft_step["interactions"], ee + es)
     F.walks_select(0)
     if world == 1:
         lw = w

@@ -80,6 +80,7 @@ struct Meta {
     int fcount[N_LVL];                     // cells of level l that split
     int overflow;
     int n_walk;
+    int w0, w1, e0, e1;                    // this rank's share: walks [w0, w1) = particles [e0, e1) in tree order
     int cap, n_items;
     long long n_adr_epj, n_adr_spj, n_int_epep, n_int_epsp;
     unsigned long long stamp[96];          // globaltimer at the phase boundaries of tree_coop_kernel (block 0)
@@ -523,6 +524,26 @@ __global__ void __launch_bounds__(TPB, 3) tree_coop_kernel(KP P, int *fr_a, int 
     if (b == 0 && threadIdx.x == 0) meta->n_stamp = ns;
 }
 
+// ---- multi-GPU: this rank's share of the walks.  Every rank builds the same tree over all particles; rank r of W
+// evaluates the walks whose first particle (tree order) lies in [n r / W, n (r+1) / W) -- contiguous in Morton order,
+// i.e. a compact spatial domain, what dinfo.decomposeDomainAll gives an MPI rank of the reference. ----
+__global__ void walk_range_kernel(KP P, const int *__restrict__ walk_cell, int n_walk, int part_rank, int part_world)
+{
+    if (threadIdx.x != 0) return;
+    Meta *m = P.meta;
+    const long long p0 = (long long)P.n * part_rank / part_world, p1 = (long long)P.n * (part_rank + 1) / part_world;
+    int b[2];
+    for (int q = 0; q < 2; q++) {                   // number of walks whose first particle is below the bound
+        const long long bound = q ? p1 : p0;
+        int lo = 0, hi = n_walk;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((long long)P.c_meta[walk_cell[mid]].x < bound) lo = mid + 1; else hi = mid; }
+        b[q] = lo;
+    }
+    m->w0 = b[0]; m->w1 = b[1];
+    m->e0 = b[0] < n_walk ? P.c_meta[walk_cell[b[0]]].x : P.n;
+    m->e1 = b[1] < n_walk ? P.c_meta[walk_cell[b[1]]].x : P.n;
+}
+
 // ---- per-group walk: one warp per group, depth-first in steps of 4 cells x 8 children ----
 struct WalkP {
     KP P;
@@ -542,7 +563,11 @@ __global__ void __launch_bounds__(WALK_WPB * 32) walk_kernel(WalkP A)
     const double inv_theta2 = 1.0 / (P.theta * P.theta);
     const double len = P.meta->len;
     const unsigned lt = (1u << lane) - 1;
-    for (int g = blockIdx.x * WALK_WPB + wib; g < A.n_walk; g += gridDim.x * WALK_WPB) {
+    const int w0 = P.meta->w0, w1 = P.meta->w1;
+    if (!FILL)                                              // walks of other ranks: empty lists, no work items
+        for (int g = blockIdx.x * WALK_WPB * 32 + threadIdx.x; g < A.n_walk; g += gridDim.x * WALK_WPB * 32)
+            if (g < w0 || g >= w1) { const int4 gm = P.c_meta[A.walk_cell[g]]; A.epi_off[g] = gm.x; A.ni[g] = gm.y; A.n_epj[g] = 0; A.n_spj[g] = 0; }
+    for (int g = w0 + blockIdx.x * WALK_WPB + wib; g < w1; g += gridDim.x * WALK_WPB) {
         const int gc = A.walk_cell[g];
         const int4 gm = P.c_meta[gc];
         // group boxes: lanes 0..11 load one double each, everybody gets all 12
@@ -631,7 +656,7 @@ __global__ void __launch_bounds__(1024) totals_kernel(int n_walk, const int *__r
                                                       int tile_cap, int jsplit, int rmax, int split_m)
 {
     long long v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // adr_epj, adr_spj, int_ee, int_es, items at cap 64..4
-    for (int w = threadIdx.x; w < n_walk; w += 1024) {
+    for (int w = threadIdx.x + m->w0; w < m->w1; w += 1024) {
         const long long i = ni[w], e = ne[w], s = ns[w];
         v[0] += e; v[1] += s; v[2] += i * e; v[3] += i * s;
         for (int k = 0; k < 5; k++) v[4 + k] += (i + (64 >> k) - 1) / (64 >> k);
@@ -657,7 +682,7 @@ __global__ void __launch_bounds__(TPB) item_count_kernel(int n_walk, const int *
     const int w = blockIdx.x * TPB + threadIdx.x;
     if (w >= n_walk) return;
     const int cap = m->cap;
-    int rem = ni[w], cnt = 0;
+    int rem = (w >= m->w0 && w < m->w1) ? ni[w] : 0, cnt = 0;
     while (rem > 0) { int n, shape; gb::tile_next(rem, cap, jsplit != 0, n, shape); rem -= n; cnt++; }
     n_items[w] = cnt;
 }
@@ -677,7 +702,7 @@ __global__ void __launch_bounds__(TPB) item_emit_kernel(int n_walk, const int *_
     const int w = blockIdx.x * TPB + threadIdx.x;
     if (w >= n_walk) return;
     const int cap = m->cap;
-    int rem = ni[w], i0 = 0, k = ioff[w];
+    int rem = (w >= m->w0 && w < m->w1) ? ni[w] : 0, i0 = 0, k = ioff[w];
     while (rem > 0) {
         int n, shape;
         gb::tile_next(rem, cap, jsplit != 0, n, shape);
@@ -919,6 +944,9 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
     for (int l = 0; l <= N_LVL; l++) S.lvl_start[l] = S.h_meta->lvl_start[l];
     S.n_cells = S.lvl_start[N_LVL];
     S.n_walk = S.h_meta->n_walk;
+    walk_range_kernel<<<1, 32, 0, st>>>(P, (const int *)S.walk_cell.p, S.n_walk, cfg.part_rank, cfg.part_world > 0 ? cfg.part_world : 1);
+    CK(cudaGetLastError());
+    ++*launches;
     S.n_levels = 0;
     for (int l = 0; l < N_LVL; l++) if (S.lvl_start[l + 1] > S.lvl_start[l]) S.n_levels = l + 1;
     const int nw = S.n_walk;
@@ -952,6 +980,7 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
     CK(cudaStreamSynchronize(st));
     S.h_meta_stamps = S.h_meta;
     counts->n_cells = S.n_cells; counts->n_walk = nw; counts->n_levels = S.n_levels;
+    counts->w0 = S.h_meta->w0; counts->w1 = S.h_meta->w1; counts->e0 = S.h_meta->e0; counts->e1 = S.h_meta->e1;
     counts->overflow = S.h_meta->overflow;
     counts->n_items = nw > 0 ? S.h_meta->n_items : 0; counts->cap = nw > 0 ? S.h_meta->cap : 0;
     counts->n_adr_epj = nw > 0 ? S.h_meta->n_adr_epj : 0; counts->n_adr_spj = nw > 0 ? S.h_meta->n_adr_spj : 0;

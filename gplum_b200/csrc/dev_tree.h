@@ -14,6 +14,7 @@ struct TreeCfg {
     int quad;                    // SPJ layout: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B)
     // work-list policy (items.h)
     long long warp_slots; int tile_cap, jsplit, rmax, split_m;
+    int part_rank = 0, part_world = 1;   // multi-GPU: lists and work items only for this rank's share of the walks
 };
 
 // totals of a build, valid on the host after phase1 returned
@@ -21,6 +22,7 @@ struct TreeCounts {
     int n_cells, n_walk, n_items, cap;
     long long n_adr_epj, n_adr_spj, n_int_epep, n_int_epsp;
     int n_levels, overflow;      // overflow: 1 = cell capacity, 2 = walk stack
+    int w0, w1, e0, e1;          // this rank's walks [w0, w1) = particles [e0, e1) in tree order
 };
 
 struct TreeOut {                 // destination buffers of phase 2 (sizes from TreeCounts)

@@ -86,6 +86,7 @@ struct WalkSet {
     DevBuf force_org;            // forces in the caller's particle order (tree_download_original)
     DevBuf seg_off;              // segments of a one-wave pass: warp s runs items [seg_off[s], seg_off[s+1]) (items.h)
     int n_seg = 0;               // 0: one item per warp
+    int part_e0 = 0, part_e1 = 0;  // multi-GPU tree build: this rank's i-particles [e0, e1) of the set (0, 0: all)
     PinBuf h_force, h_stage;     // pinned: results, flattened inputs of dispatch()
     int n_walk = 0, n_items = 0;
     long long n_epi = 0, n_adr_epj = 0, n_adr_spj = 0;
@@ -415,6 +416,7 @@ int upload_walks(WalkSet &ws, int n_walk, const void *epi_all, const int *epi_of
     }
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es;
+    ws.part_e0 = ws.part_e1 = 0;
     g.tree_built = false;
     // multi-GPU peer mode: a walk whose EP list names a particle of another rank (index = owner << shift | local index)
     // must not start before that rank has packed: its items wait for the peers' flags inside the kernel, and one empty
@@ -886,6 +888,7 @@ int gplum_b200_dispatch(int tag, int n_walk, const void *const *epi, const int *
     }
     ws.n_walk = n_walk; ws.n_epi = n_epi; ws.n_adr_epj = n_ae; ws.n_adr_spj = n_as;
     ws.n_int_epep = i_ee; ws.n_int_epsp = i_es; ws.n_items = 0;
+    ws.part_e0 = ws.part_e1 = 0;
     g.tree_built = false;
     if (int r = ws.epi.reserve((size_t)n_epi * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n_epi * sizeof(ForceAos))) return r;
@@ -1284,7 +1287,7 @@ int gplum_b200_correct_long_run(int slot, const gplum_b200_corr_params *prm, int
     const size_t tb = soft_corr_scan_temp_bytes(n);
     if (int r = ws.scan_temp.reserve(tb)) return r;
     SoftCorrArgs a;
-    a.n_epi = n; a.epi = ws.epi.p; a.force = ws.force.p; a.epj_aos = g.jset.epj_aos.p;
+    a.n_epi = n; a.i0 = ws.part_e1 > ws.part_e0 ? ws.part_e0 : 0; a.i1 = ws.part_e1 > ws.part_e0 ? ws.part_e1 : n; a.epi = ws.epi.p; a.force = ws.force.p; a.epj_aos = g.jset.epj_aos.p;
     a.self_adr = (const int *)ws.self_adr.p;
     a.pairs = (const int2 *)ws.pairs.p; a.pair_count = (const unsigned int *)ws.corr_meta.p; a.pair_cap = ws.pair_cap;
     a.cnt = (int *)ws.cnt.p; a.off = (int *)ws.off.p; a.cursor = (int *)ws.cursor.p; a.csr = (int *)ws.csr.p;
@@ -1499,7 +1502,8 @@ int download_host(void *dst, const void *src, size_t bytes, cudaStream_t st)
     return 0;
 }
 
-int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_leaf_limit, int n_group_limit, long long *sizes)
+int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_leaf_limit, int n_group_limit, long long *sizes,
+                      int part_rank = 0, int part_world = 1)
 {
     if (g.rmax > 2) return fail(GPLUM_B200_ERR_STATE, "the GPU list builder needs the RMAX <= 2 kernel");
     cudaStream_t st = g.stream;
@@ -1513,6 +1517,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     gbt::TreeCfg cfg;
     cfg.n = n; cfg.theta = theta; cfg.n_leaf = n_leaf_limit; cfg.n_group = n_group_limit; cfg.quad = g.quad;
     cfg.warp_slots = g.warp_slots; cfg.tile_cap = g.tile_cap; cfg.jsplit = g.jsplit; cfg.rmax = g.rmax; cfg.split_m = g.split_m;
+    cfg.part_rank = part_rank; cfg.part_world = part_world;
     gbt::TreeCounts c;
     memset(&c, 0, sizeof(c));
     int launches = 0;
@@ -1549,6 +1554,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     g.launches += launches;
     if (e) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 2: %s", cudaGetErrorString((cudaError_t)e));
     ws.n_walk = c.n_walk; ws.n_items = n_items_out; ws.n_epi = n;
+    ws.part_e0 = part_world > 1 ? c.e0 : 0; ws.part_e1 = part_world > 1 ? c.e1 : 0;
     ws.n_adr_epj = c.n_adr_epj; ws.n_adr_spj = c.n_adr_spj;
     ws.n_int_epep = c.n_int_epep; ws.n_int_epsp = c.n_int_epsp;
     ws.ni_host.clear(); ws.epi_off_host.clear();
@@ -1560,6 +1566,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     if (sizes) {
         sizes[0] = c.n_walk; sizes[1] = n; sizes[2] = c.n_adr_epj; sizes[3] = c.n_adr_spj; sizes[4] = n;
         sizes[5] = c.n_cells; sizes[6] = c.n_int_epep; sizes[7] = c.n_int_epsp;
+        if (part_world > 1) { sizes[8] = c.w0; sizes[9] = c.w1; sizes[10] = c.e0; sizes[11] = c.e1; }
     }
     return 0;
 }
@@ -1603,6 +1610,32 @@ int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double 
         src = g.tree_raw.p;
     }
     return tree_build_common(n, src, theta, n_leaf_limit, n_group_limit, sizes);
+}
+
+// Multi-GPU form: every rank hands over the SAME n particles (device pointer: the all-gathered EPJGrav
+// records of all ranks) and builds the same tree, but walks, lists, work items -- and hence forces and corrections --
+// only for its share: the walks whose first particle in tree order lies in [n r / W, n (r+1) / W).
+// sizes[12]: [0..7] as tree_build_gpu (counts of THIS rank's lists), [8], [9] = its walks [w0, w1), [10], [11] = its
+// i-particles [e0, e1) in tree order.
+int gplum_b200_tree_build_gpu_part(int n, const void *epj_dev, double theta, int n_leaf_limit, int n_group_limit,
+                                   int part_rank, int part_world, long long *sizes)
+{
+    if (n <= 0 || !epj_dev || theta <= 0.0 || part_world < 1 || part_rank < 0 || part_rank >= part_world)
+        return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu_part: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    return tree_build_common(n, epj_dev, theta, n_leaf_limit, n_group_limit, sizes, part_rank, part_world);
+}
+
+// ForceGrav[count] of i-particles [first, first + count) of the selected walk set (tree order), host pointer
+int gplum_b200_walks_download_range(void *force_out, long long first, long long count)
+{
+    if (int r = ensure_init()) return r;
+    WalkSet &ws = g.slots[g.cur];
+    if (first < 0 || count < 0 || first + count > ws.n_epi || (count > 0 && !force_out)) return fail(GPLUM_B200_ERR_ARG, "walks_download_range: bad range");
+    CU(cudaSetDevice(g.device));
+    if (count == 0) { CU(cudaStreamSynchronize(g.stream)); return 0; }
+    return download_host(force_out, (const ForceAos *)ws.force.p + first, (size_t)count * sizeof(ForceAos), g.stream);
 }
 
 int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,

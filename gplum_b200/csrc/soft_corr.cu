@@ -71,10 +71,10 @@ struct EpiAos { int id_local, myrank; double pos[3]; double r_out, r_search; }; 
 struct ForceAos { float acc[3]; float phi; int number, rank, id_max, id_min; };                    // 32
 static_assert(sizeof(EpjAos) == 112 && sizeof(EpiAos) == 48 && sizeof(ForceAos) == 32, "reference layout");
 
-__global__ void corr_count_kernel(const ForceAos *__restrict__ force, int n, int *__restrict__ cnt, int *__restrict__ cursor)
+__global__ void corr_count_kernel(const ForceAos *__restrict__ force, int n, int i0, int i1, int *__restrict__ cnt, int *__restrict__ cursor)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i <= n) cnt[i] = (i < n) ? force[i].number : 0;
+    if (i <= n) cnt[i] = (i >= i0 && i < i1) ? force[i].number : 0;
     if (i < n) cursor[i] = 0;
 }
 
@@ -128,10 +128,11 @@ __global__ void __launch_bounds__(128) corr_apply_kernel(SoftCorrArgs a)
     SoftCorr out;
     out.id_local = ((const EpiAos *)a.epi)[i].id_local;
     out.ngb_off = overflow ? 0 : base;
-    const int sa = a.self_adr[i];
+    const bool mine = i >= a.i0 && i < a.i1;
+    const int sa = mine ? a.self_adr[i] : -1;
     if (sa < 0 || overflow) {   // sa < 0 cannot happen with FDPS lists (a group's own particles are in its EP list);
                                 // overflow: neutral record, nothing outside the buffers is touched (scatter kernel)
-        if (!overflow) atomicAdd(&a.status[1], 1u);
+        if (!overflow && mine) atomicAdd(&a.status[1], 1u);
         out.acc[0] = out.acc[1] = out.acc[2] = 0.; out.phi = 0.; out.acc0 = 0.;
         out.id_cluster = -1; out.number = 0; out.in_domain = 1;
         a.out[i] = out;
@@ -239,7 +240,7 @@ int soft_corr_launch(const SoftCorrArgs &a, void *scan_temp, size_t scan_temp_by
 {
     if (a.n_epi <= 0) return 0;
     const int n1 = a.n_epi + 1;
-    corr_count_kernel<<<(n1 + 255) / 256, 256, 0, st>>>((const ForceAos *)a.force, a.n_epi, a.cnt, a.cursor);
+    corr_count_kernel<<<(n1 + 255) / 256, 256, 0, st>>>((const ForceAos *)a.force, a.n_epi, a.i0, a.i1, a.cnt, a.cursor);
     cudaError_t e = cub::DeviceScan::ExclusiveSum(scan_temp, scan_temp_bytes, (const int *)a.cnt, a.off, n1, st);
     if (e != cudaSuccess) return (int)e;
     corr_scatter_kernel<<<148 * 4, 256, 0, st>>>(a.pairs, a.pair_count, a.pair_cap, a.off, a.cursor, a.csr, a.status);

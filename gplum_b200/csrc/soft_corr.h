@@ -15,6 +15,7 @@ static_assert(sizeof(SoftCorr) == 64 && sizeof(SoftCorrInit) == 64 && sizeof(Sof
 
 struct SoftCorrArgs {
     int n_epi;
+    int i0, i1;                 // only i-particles [i0, i1) are corrected (multi-GPU: this rank's share); the rest get neutral records
     const void *epi;            // EPIGrav[n_epi], walk-concatenated
     const void *force;          // ForceGrav[n_epi] of the pass (number = candidate count)
     const void *epj_aos;        // EPJGrav[] of the pass, as FDPS holds epj_sorted_

@@ -203,3 +203,50 @@ class MultiGpuPass:
             check(self.L.gplum_b200_peer_free())
         check(self.L.gplum_b200_walks_set_packed_dev(None, 0, None, 0))
         F.walks_select(0)
+
+
+class MultiGpuSoftStep:
+    """One soft-force evaluation of a multi-GPU run with NO host-side lists and no rank touching the global particle
+    set on the host (SURVEY 8e + 8f-1/2): every rank holds n / world particles in HBM; per step
+
+        NCCL all-gather of the raw EPJGrav records over NVLink   (FDPS's LET exchange, exlet.hpp:343-403: here every
+                                                                  rank gets every particle -- 112 MB at N = 1e6)
+        gplum_b200_tree_build_gpu_part                            the same tree on every GPU, lists for this rank's walks
+        walks_run + correct_long_run                              forces, changeover correction, neighbour lists: own share
+
+    The share of rank r is the Morton-contiguous range of walks whose first particle lies in [n r / W, n (r+1) / W) of
+    the tree order -- a compact spatial domain, like an FDPS domain."""
+
+    def __init__(self, epj_local, n_total, world, rank, theta=0.5, n_leaf_limit=8, n_group_limit=64):
+        assert n_total % world == 0 and len(epj_local) == n_total // world, "equal shares (all_gather_into_tensor)"
+        self.L = lib()
+        self.world, self.rank, self.n = world, rank, n_total
+        self.theta, self.leaf, self.group = theta, n_leaf_limit, n_group_limit
+        self.d_local = torch.from_numpy(np.ascontiguousarray(epj_local).view(np.uint8).copy()).cuda()
+        self.d_all = torch.empty(n_total * S.EPJ.itemsize, dtype=torch.uint8, device="cuda")
+        self.sizes = np.zeros(12, dtype=np.int64)
+
+    def upload_local(self, epj_local_pinned):
+        """host -> device of this rank's records (a step's H2D when the particles live on the host)"""
+        self.d_local.copy_(torch.from_numpy(epj_local_pinned.view(np.uint8)), non_blocking=True)
+
+    def step(self, prm=None):
+        dist.all_gather_into_tensor(self.d_all, self.d_local)
+        check(self.L.gplum_b200_tree_build_gpu_part(self.n, C.c_void_p(self.d_all.data_ptr()), float(self.theta), int(self.leaf),
+                                                    int(self.group), self.rank, self.world,
+                                                    self.sizes.ctypes.data_as(C.c_void_p)))
+        F.walks_run(repack=False)
+        if prm is not None:
+            F.correct_long_run(prm)
+        return self.sizes
+
+    def share(self):
+        """(w0, w1, e0, e1): this rank's walks and i-particles (tree order) of the last step"""
+        return tuple(int(x) for x in self.sizes[8:12])
+
+    def forces(self, out=None):
+        """ForceGrav[e1 - e0] of this rank's particles (tree order)."""
+        _, _, e0, e1 = self.share()
+        f = np.zeros(e1 - e0, dtype=S.FORCE) if out is None else out
+        check(self.L.gplum_b200_walks_download_range(f.ctypes.data_as(C.c_void_p), e0, e1 - e0))
+        return f[:e1 - e0]

@@ -217,6 +217,16 @@ int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, cons
                               int rank, long long *sizes);
 int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double theta, int n_leaf_limit,
                                   int n_group_limit, long long *sizes);
+/* Multi-GPU form: every rank passes the SAME n EPJGrav records (device pointer -- the all-gather of all
+ * ranks' particles, FDPS's LET exchange FDPS/src/tree_for_force_impl_exlet.hpp:343-403 turned into one NCCL
+ * all-gather over NVLink) and builds the same tree, but walks, lists and work items only for its share: the walks
+ * whose first particle in tree order lies in [n r / W, n (r+1) / W) -- a Morton-contiguous spatial domain.  Forces
+ * (walks_run) and corrections (correct_long_run) then exist for that share only.  sizes[12]: [0..7] as
+ * tree_build_gpu for THIS rank's lists, [8], [9] = its walks [w0, w1), [10], [11] = its i-particles [e0, e1). */
+int gplum_b200_tree_build_gpu_part(int n, const void *epj_dev, double theta, int n_leaf_limit, int n_group_limit,
+                                   int part_rank, int part_world, long long *sizes);
+/* ForceGrav[count] of i-particles [first, first + count) of the selected walk set (tree order); host pointer. */
+int gplum_b200_walks_download_range(void *force_out, long long first, long long count);
 int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,
                              int *adr_spj, long long *spj_disp, int *n_spj, void *epj_all, void *spj_all,
                              int *sorted_to_original);

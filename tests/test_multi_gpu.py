@@ -74,3 +74,89 @@ def test_two_ranks_match_single_rank_oracle(exchange, tmp_path):
         got[e0:e1] = f; covered += e1 - e0; n_bnd += nb
     assert covered == len(w.epi) and n_bnd > 0
     synth.assert_force_close(got, want, 1e-4, "2 ranks, " + exchange)
+
+
+def _soft_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from gplum_b200 import disk, functors as F, state as ST, structs as S, tree
+    from gplum_b200._lib import check, lib
+    from gplum_b200.multigpu import MultiGpuSoftStep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = 24000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=9)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    ro, rs = ro * 2.0, rs * 3.0                                 # neighbours across the rank boundary
+    epj = ST.make_epj(d["pos"], d["vel"], d["mass"], ro, rs)
+    F.init(rank)
+    F.set_params(0.0, True, 0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    check(lib().gplum_b200_set_stream(C.c_void_p(stream.cuda_stream)))
+    m = n // world
+    ms = MultiGpuSoftStep(epj[rank * m:(rank + 1) * m], n, world, rank, n_group_limit=128)
+    prm = S.corr_params()
+    F.soft_corr_enable(True)
+    try:
+        for _ in range(2):
+            sz = ms.step(prm)
+        f = ms.forces()
+        corr, ngb = F.correct_long_download_compact(n)
+        g, order = tree.copy_walks_gpu(sz[:8])
+    finally:
+        F.soft_corr_enable(False)
+    np.save(os.path.join(out_dir, "sf%d.npy" % rank), f)
+    np.save(os.path.join(out_dir, "sc%d.npy" % rank), corr)
+    np.save(os.path.join(out_dir, "sn%d.npy" % rank), ngb)
+    np.save(os.path.join(out_dir, "ss%d.npy" % rank), np.array(ms.share()))
+    np.save(os.path.join(out_dir, "so%d.npy" % rank), order)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_multi_rank_soft_step_without_host_lists(tmp_path):
+    """all-gather of raw particles over NCCL -> the same tree on every GPU -> every rank its share of walks, forces,
+    corrections and neighbour lists: the union equals the single-rank oracle (forces 1e-4, corrections 1e-12,
+    neighbour lists as sets), and the shares partition the particles."""
+    import torch.multiprocessing as mp
+    import oracle_api as O
+    import synth
+    from gplum_b200 import disk, structs as S, tree
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_soft_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n = 24000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=9)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    ro, rs = ro * 2.0, rs * 3.0
+    h, order = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=128)
+    h.epj_all["vel"] = d["vel"][order]
+    want, _ = O.calc_walks(h, 0.0)
+    prm = S.corr_params()
+    oc, _, on = O.correct_long(h, prm, force=want)
+    got = S.cleared_force(n); covered = 0; prev = 0
+    n_ngb = 0
+    for r in range(world):
+        f = np.load(tmp_path / ("sf%d.npy" % r)); w0, w1, e0, e1 = np.load(tmp_path / ("ss%d.npy" % r))
+        assert np.array_equal(np.load(tmp_path / ("so%d.npy" % r)), order)        # same tree on every rank
+        assert e0 == prev and len(f) == e1 - e0
+        got[e0:e1] = f; covered += e1 - e0; prev = e1
+        corr = np.load(tmp_path / ("sc%d.npy" % r)); ngb = np.load(tmp_path / ("sn%d.npy" % r))
+        # compact records = this rank's particles that have neighbours
+        sel = np.nonzero(oc["number"][e0:e1] > 0)[0] + e0
+        assert len(corr) == len(sel) and np.array_equal(corr["id_local"], oc["id_local"][sel])
+        assert np.array_equal(corr["number"], oc["number"][sel])
+        tot = np.linalg.norm(want["acc"][sel].astype(np.float64) + oc["acc"][sel], axis=1)[:, None]
+        assert (np.abs(corr["acc"] - oc["acc"][sel]) <= 1e-12 * tot).all()
+        for c, k in zip(corr, sel):
+            a = set(ngb["id"][c["ngb_off"]:c["ngb_off"] + c["number"]].tolist())
+            b = set(on["id"][oc["ngb_off"][k]:oc["ngb_off"][k] + oc["number"][k]].tolist())
+            assert a == b
+        n_ngb += int(corr["number"].sum())
+    assert covered == n and n_ngb == int(oc["number"].sum()) and n_ngb > 100
+    synth.assert_force_close(got, want, 1e-4, "multi-rank soft step")
