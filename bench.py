@@ -502,7 +502,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1000000, help="particles (under torchrun use --particles: its own parser claims --n)")
     ap.add_argument("--group", type=int, default=512)
     ap.add_argument("--a-in", type=float, default=0.9)
     ap.add_argument("--a-out", type=float, default=1.1)
@@ -679,6 +679,11 @@ def main():
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4",
                 "frac_of_nominal": achieved / 74.4,
                 "kernel_ms": k_ms, "flop_per_launch": flop,
+                # `achieved` counts the DSL's algorithm (30 / 59 flop per pair, its 5-flop Newton step
+                # included).  The shipped kernel takes MUFU.RSQ's 2^-22.9 as the refined value and does not run that
+                # step (kernels.cuh GB_NEWTON, profiles/r2_newton_step.txt): the flop it executes are 25 / 54 per pair
+                "executed_flop_per_launch": (FLOP_EPEP - 5.0) * my_ee + (FLOP_EPSP - 5.0) * my_es,
+                "executed_frac": ((FLOP_EPEP - 5.0) * my_ee + (FLOP_EPSP - 5.0) * my_es) / (k_ms * 1e-3) / 1e12 / peak_tf,
                 "interactions_per_s_kernel_only": (my_ee + my_es) / (k_ms * 1e-3),
                 "gflops_38flop_convention": 38.0 * (my_ee + my_es) / (k_ms * 1e-3) / 1e9,
                 "list_bytes_per_launch": alg_bytes}

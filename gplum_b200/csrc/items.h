@@ -27,8 +27,12 @@ GB_HD void tile_next(int rem, int cap, bool split, int &n, int &shape)
     shape = rem > 32 ? 64 : rem > 16 ? 32 : rem > 8 ? 16 : rem > 4 ? 8 : 4;
 }
 
-// cost model in issue slots per lane (EP-EP 18.5, EP-SP 37 per pair) + per-tile staging overhead
-constexpr double COST_EP = 18.5, COST_SP = 37.0, COST_TILE = 90.0;
+// cost model in issue slots per lane (EP-EP 15.5, EP-SP 34 per pair; 3 more each with the Newton step compiled in,
+// kernels.cuh: GB_NEWTON) + per-tile staging overhead
+#ifndef GB_NEWTON
+#define GB_NEWTON 0
+#endif
+constexpr double COST_EP = GB_NEWTON ? 18.5 : 15.5, COST_SP = GB_NEWTON ? 37.0 : 34.0, COST_TILE = 90.0;
 #ifndef GB_COST_ITEM
 #define GB_COST_ITEM 4000.0
 #endif

@@ -6,13 +6,13 @@
 // packed j-arrays resident in HBM.  Arithmetic follows src/gravity_kernel_epep.pikg:53-97 and
 // src/gravity_kernel_epsp.pikg:47-100: FP64 shift by the group's first i-particle, then FP32.
 //
-// Per pair, EP-EP (hot loop, 18.5 issue slots for the DSL's 30 flop + rsqrt):
+// Per pair, EP-EP (hot loop, 15.5 issue slots for the DSL's 30 flop + rsqrt):
 //   d = xj-xi (3 FADD); r2 = d.d+eps2 (3 FFMA); rmin = min3(rmin, r2[i0], r2[i1]) (FMNMX3 per 2 pairs);
 //   r2c = max3(r2, rout2_i, rout2_j) (FMNMX3; max(a,b)^2 == max(a^2,b^2) exactly in FP);
-//   y = MUFU.RSQ(r2c); Newton step of the DSL as a = y*(3 - r2c*y*y) = 2*y' (3; the DSL's *0.5 is
-//   a power of two and is carried exactly in the accumulators' scale: phi2 = 2*phi, acc8 = 8*acc,
-//   undone at the write -- bit-identical results); t = m*a; v = (a*a)*t (3);
-//   acc8 += v*d (3 FFMA); phi2 -= t (FADD).
+//   a = MUFU.RSQ(r2c) (GB_NEWTON below: the DSL's Newton step is what PIKG adds to a 12-bit estimate; MUFU.RSQ has
+//   the refined accuracy already.  With GB_NEWTON = 1 the step runs as a = y*(3 - r2c*y*y) = 2*y', 3 more slots, and
+//   its *0.5, a power of two, is carried exactly in the accumulators' scale and undone at the write);
+//   t = m*a; v = (a*a)*t (3); acc += v*d (3 FFMA); phi -= t (FADD).
 // Neighbour candidates: the hot loop only evaluates a conservative filter (min r2 < T with
 // T >= rsearch2 of every pair of the lane and tile, widened by 2^-16); j-groups that pass
 // (rare: self + true candidates) are re-tested in the reference's exact, non-fused evaluation
@@ -33,6 +33,17 @@ namespace gb {
 #define GB_MINB2 6
 #endif
 constexpr int UNROLL = GB_UNROLL;
+// Reciprocal square root.  The DSL writes rsqrt(r2) and PIKG expands it for the target: on AVX2 a 12-bit estimate
+// + one Newton step (rel. error ~2e-7), on AVX-512 a 14-bit one.  MUFU.RSQ (rsqrt.approx.f32) is specified to 2^-22.9
+// = 1.3e-7 over the whole range, i.e. it already has the accuracy the reference's estimate reaches AFTER its Newton
+// step, so the shipped build uses it as is (GB_NEWTON = 0).  GB_NEWTON = 1 compiles the step in (3 more issue slots per
+// pair, ~10 % of a pass); measured difference between the two on the N = 1e6 pass: profiles/r2_newton_step.txt.
+#ifndef GB_NEWTON
+#define GB_NEWTON 0
+#endif
+// rinv_scaled() returns RS * rsqrt(x); the power-of-two RS is carried exactly in the accumulators' scale
+constexpr float RS = GB_NEWTON ? 2.0f : 1.0f;
+constexpr float RS2_INV = 1.0f / (RS * RS), RS_INV = 1.0f / RS, RS3_INV = 1.0f / (RS * RS * RS);
 
 // ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
 struct __align__(16) EpjPacked {   // 48 B
@@ -40,8 +51,8 @@ struct __align__(16) EpjPacked {   // 48 B
     double z; float m, rout2;
     float rs2; int id; int rank; int pad;
 };
-struct __align__(16) SpjPacked {   // 64 B; Q = (3q - tr*I)/4, mtr = -(eps2*tr)/4 hoisted (j-only terms;
-                                   // the exact power-of-two scale pairs with a = 2*y' in the pair loop)
+struct __align__(16) SpjPacked {   // 64 B; Q = (3q - tr*I)/RS^2, mtr = -(eps2*tr)/RS^2 hoisted (j-only terms;
+                                   // the exact power-of-two scale pairs with a = RS*y in the pair loop)
     double x, y;
     double z; float m, qxx;
     float qyy, qzz, qxy, qyz;
@@ -102,6 +113,15 @@ __device__ __forceinline__ float rsqrt_approx(float x)
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+__device__ __forceinline__ float rinv_scaled(float x)
+{
+    const float y = rsqrt_approx(x);
+#if GB_NEWTON
+    return y * fmaf(-x, y * y, 3.0f);      // the DSL's y*(3 - x*y*y)*0.5 without the 0.5
+#else
+    return y;
+#endif
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c)
 {
@@ -197,11 +217,11 @@ __device__ __forceinline__ void pack_spj_block(const void *__restrict__ in, int 
         const float qxy = (float)a.quad[3], qzx = (float)a.quad[4], qyz = (float)a.quad[5];
         const float tr = trace_as_shipped ? (float)(a.quad[0] + a.quad[1] + a.quad[0])
                                           : __fadd_rn(__fadd_rn(qxx, qyy), qzz);
-        o.qxx = 0.25f * __fsub_rn(__fmul_rn(3.0f, qxx), tr);
-        o.qyy = 0.25f * __fsub_rn(__fmul_rn(3.0f, qyy), tr);
-        o.qzz = 0.25f * __fsub_rn(__fmul_rn(3.0f, qzz), tr);
-        o.qxy = 0.25f * __fmul_rn(3.0f, qxy); o.qyz = 0.25f * __fmul_rn(3.0f, qyz); o.qzx = 0.25f * __fmul_rn(3.0f, qzx);
-        o.mtr = -0.25f * __fmul_rn(eps2, tr);
+        o.qxx = RS2_INV * __fsub_rn(__fmul_rn(3.0f, qxx), tr);
+        o.qyy = RS2_INV * __fsub_rn(__fmul_rn(3.0f, qyy), tr);
+        o.qzz = RS2_INV * __fsub_rn(__fmul_rn(3.0f, qzz), tr);
+        o.qxy = RS2_INV * __fmul_rn(3.0f, qxy); o.qyz = RS2_INV * __fmul_rn(3.0f, qyz); o.qzx = RS2_INV * __fmul_rn(3.0f, qzx);
+        o.mtr = -RS2_INV * __fmul_rn(eps2, tr);
     } else {
         const SpjMonoAos &a = reinterpret_cast<const SpjMonoAos *>(sm)[threadIdx.x];
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
@@ -504,10 +524,9 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
                         r2[r] = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
                         const float r2c = fmax3(r2[r], ro2i[r], ro2);
-                        const float y = rsqrt_approx(r2c);
-                        const float a = y * fmaf(-r2c, y * y, 3.0f);      // 2*y'
-                        const float t = pj.w * a;                          // 2*m*y'
-                        const float v = (a * a) * t;                       // 8*m*y'^3
+                        const float a = rinv_scaled(r2c);                  // RS*y
+                        const float t = pj.w * a;                          // RS*m*y
+                        const float v = (a * a) * t;                       // RS^3*m*y^3
                         ax[r] = fmaf(v, dx, ax[r]);
                         ay[r] = fmaf(v, dy, ay[r]);
                         az[r] = fmaf(v, dz, az[r]);
@@ -578,16 +597,15 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
                     for (int r = 0; r < R; r++) {
                         const float dx = pj.x - xi[r], dy = pj.y - yi[r], dz = pj.z - zi[r];
                         const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
-                        const float y = rsqrt_approx(r2);
-                        const float a = y * fmaf(-r2, y * y, 3.0f);                    // 2*y'
-                        const float a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a2 * a3; // 4y'^2 8y'^3 16y'^4 32y'^5
+                        const float a = rinv_scaled(r2);                               // RS*y
+                        const float a2 = a * a, a3 = a2 * a, a4 = a2 * a2, a5 = a2 * a3;
                         const float qrx = fmaf(qb.y, dz, fmaf(qa.w, dy, qa.x * dx));   // (Qxx dx + Qxy dy + Qzx dz)/4
                         const float qry = fmaf(qa.w, dx, fmaf(qb.x, dz, qa.y * dy));   // (Qyy dy + Qyz dz + Qxy dx)/4
                         const float qrz = fmaf(qb.x, dy, fmaf(qb.y, dx, qa.z * dz));   // (Qzz dz + Qzx dx + Qyz dy)/4
                         const float rqr = fmaf(qrz, dz, fmaf(qry, dy, fmaf(qrx, dx, qb.z)));
-                        const float wq = rqr * a4;                                      // 4 * rqr*y'^4
-                        const float meff = fmaf(0.125f, wq, pj.w);                      // m + 0.5 rqr y'^4
-                        const float meff3 = fmaf(0.625f, wq, pj.w) * a3;                // 8 (m + 2.5 rqr y'^4) y'^3
+                        const float wq = rqr * a4;                                      // RS^2 * rqr*y^4
+                        const float meff = fmaf(0.5f * RS2_INV, wq, pj.w);              // m + 0.5 rqr y^4
+                        const float meff3 = fmaf(2.5f * RS2_INV, wq, pj.w) * a3;        // RS^3 (m + 2.5 rqr y^4) y^3
                         ph[r] = fmaf(-meff, a, ph[r]);
                         ax[r] = fmaf(meff3, dx, fmaf(-a5, qrx, ax[r]));
                         ay[r] = fmaf(meff3, dy, fmaf(-a5, qry, ay[r]));
@@ -618,14 +636,14 @@ __device__ __forceinline__ void warp_force(const PassParams &p, const WorkItem i
             nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o)); nmin = min(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
         }
         ok[0] = lane < W && lane < it.ni;
-        fo[0] = make_float4(0.125f * ax[0], 0.125f * ay[0], 0.125f * az[0], 0.5f * ph[0]);   // undo the exact scales
+        fo[0] = make_float4(RS3_INV * ax[0], RS3_INV * ay[0], RS3_INV * az[0], RS_INV * ph[0]);   // undo the exact scales
         no[0] = make_int4(nn, nr, nmax, nmin);
     } else {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int i = lane + 32 * r;
             ok[r] = i < it.ni;
-            fo[r] = make_float4(0.125f * ax[r], 0.125f * ay[r], 0.125f * az[r], 0.5f * ph[r]);
+            fo[r] = make_float4(RS3_INV * ax[r], RS3_INV * ay[r], RS3_INV * az[r], RS_INV * ph[r]);
             no[r] = make_int4(s.nb_number[i], s.nb_rank[i], s.nb_idmax[i], s.nb_idmin[i]);
         }
     }

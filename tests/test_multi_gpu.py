@@ -1,5 +1,6 @@
 """Multi-GPU force pass on real GPUs (needs >= 2 devices; skipped on a 1-GPU box -- run it with
-`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`).  Two NCCL ranks shard the walks
+`gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`, or at 8 ranks with GPLUM_TEST_WORLD=8 under
+`gpurun --gpus 8`; logs of both: profiles/r2_pytest_multi_w2.log, r2_pytest_multi_w8.log).  NCCL ranks shard the walks
 of one disk, exchange EPJ (halo all-to-all and full all-gather variants) and evaluate their share
 with the CUDA kernels; the union must match the single-rank oracle pass: acc/phi 1e-4, neighbour
 info bit-exact."""
@@ -10,6 +11,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+WORLD = int(os.environ.get("GPLUM_TEST_WORLD", "2"))          # gpurun --gpus 8: GPLUM_TEST_WORLD=8
 
 
 def _ngpu():
@@ -56,14 +58,14 @@ def _worker(rank, world, port, out_dir, exchange):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.skipif(_ngpu() < WORLD, reason="needs >= %d GPUs" % WORLD)
 @pytest.mark.parametrize("exchange", ["peer", "halo", "allgather"])
 def test_two_ranks_match_single_rank_oracle(exchange, tmp_path):
     import torch.multiprocessing as mp
     import oracle_api as O
     import synth
     from gplum_b200 import structs as S
-    world = 2
+    world = WORLD
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(world, port, str(tmp_path), exchange), nprocs=world, join=True)
     w = _workload()
@@ -73,7 +75,7 @@ def test_two_ranks_match_single_rank_oracle(exchange, tmp_path):
         f = np.load(tmp_path / ("f%d.npy" % r)); e0, e1, nb = np.load(tmp_path / ("r%d.npy" % r))
         got[e0:e1] = f; covered += e1 - e0; n_bnd += nb
     assert covered == len(w.epi) and n_bnd > 0
-    synth.assert_force_close(got, want, 1e-4, "2 ranks, " + exchange)
+    synth.assert_force_close(got, want, 1e-4, "%d ranks, " % world + exchange)
 
 
 def _soft_worker(rank, world, port, out_dir):
@@ -118,7 +120,7 @@ def _soft_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.skipif(_ngpu() < WORLD, reason="needs >= %d GPUs" % WORLD)
 def test_multi_rank_soft_step_without_host_lists(tmp_path):
     """all-gather of raw particles over NCCL -> the same tree on every GPU -> every rank its share of walks, forces,
     corrections and neighbour lists: the union equals the single-rank oracle (forces 1e-4, corrections 1e-12,
@@ -127,7 +129,7 @@ def test_multi_rank_soft_step_without_host_lists(tmp_path):
     import oracle_api as O
     import synth
     from gplum_b200 import disk, structs as S, tree
-    world = 2
+    world = WORLD
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_soft_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     n = 24000

@@ -67,7 +67,7 @@ def check_cover(items, ni, ne, ns, n_slots, n_groups):
 
 
 def item_costs(items, ne, ns):
-    """issue slots per lane of every work item (items.h cost model: 18.5 per EP pair, 37 per SP pair, 90 per j-tile)"""
+    """issue slots per lane of every work item (items.h cost model: 15.5 per EP pair, 34 per SP pair, 90 per j-tile)"""
     out = np.zeros(len(items))
     for k, (w, i0, n, cfg, t0, t1, _, _) in enumerate(items):
         shape = SHAPE[cfg & 15]
@@ -76,7 +76,7 @@ def item_costs(items, ne, ns):
         a, b = (0, nt) if t1 < 0 else (t0, t1)
         je = min(min(b, ep_t) * 64, ne[w]) - min(min(a, ep_t) * 64, ne[w])
         js = min(max(b - ep_t, 0) * 64, ns[w]) - min(max(a - ep_t, 0) * 64, ns[w])
-        out[k] = (18.5 * je + 37.0 * js) * shape / 32.0 + 90.0 * (b - a) + (4000.0 if a == 0 else 0.0)
+        out[k] = (15.5 * je + 34.0 * js) * shape / 32.0 + 90.0 * (b - a) + (4000.0 if a == 0 else 0.0)
     return out
 
 
