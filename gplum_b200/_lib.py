@@ -59,6 +59,7 @@ SYMBOLS = {
     "gplum_b200_state_drift": (_i, [_vp, C.c_double, C.c_double, _i, _vp, _vp]),
     "gplum_b200_state_pull_unhandled": (_i, [_vp, _vp, _i, C.POINTER(_i)]),
     "gplum_b200_state_push": (_i, [_vp, _vp, _i]),
+    "gplum_b200_debug_trace": (_i, [_i, _vp, _i, C.POINTER(_i)]),
     "gplum_b200_debug_build_items": (_i, [_i, _vp, _vp, _vp, _ll, _i, _i, _i, _vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _vp, _i, C.POINTER(_i)]),
     "gplum_b200_fp32_peak": (_i, [_i, C.POINTER(_f), C.POINTER(_f)]),
     "gplum_b200_soft_corr_enable": (_i, [_i, _ll]),

@@ -83,6 +83,7 @@ struct PinBuf {
 struct WalkSet {
     DevBuf epi, epi_off, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, items, force;
     DevBuf scratch, arrive;      // partial sums and arrival counters of j-split tiles (items.h)
+    DevBuf place;                // claim counters of placed passes (kernels.cuh: PassParams::place), zero between launches
     DevBuf force_org;            // forces in the caller's particle order (tree_download_original)
     DevBuf seg_off;              // segments of a one-wave pass: warp s runs items [seg_off[s], seg_off[s+1]) (items.h)
     int n_seg = 0;               // 0: one item per warp
@@ -108,7 +109,7 @@ struct WalkSet {
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
-        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &seg_off, &force_org,
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &place, &seg_off, &force_org,
                           &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp, &corr_compact})
             b->release();
         h_force.release(); h_stage.release();
@@ -161,7 +162,8 @@ struct Ctx {
     int jsplit = 1;             // short i-tiles split their j-lists over lane groups (GPLUM_B200_JSPLIT=0 disables)
     int bulk = 0;               // GPLUM_B200_BULK=1: EP tiles staged by bulk copies (cp.async.bulk + mbarrier) of index runs;
                                 // default per-record cp.async, measured 2 % faster (profiles/r2_bulk_copy_probe.txt)
-    int snake = 1;              // boustrophedon CTA order in passes of less than one wave (GPLUM_B200_SNAKE=0 disables)
+    int place = 1;              // passes of at most `place` waves of items are placed by SM and scheduler (items.h: place_item;
+                                // GPLUM_B200_PLACE=0: item s on warp s of the grid, wherever the hardware puts it)
     int split_m = 2;            // j-split of full-width tiles in passes with less than two waves of items: pieces per warp
                                 // slot (items.h); 0 = never (GPLUM_B200_SPLIT_M)
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
@@ -171,6 +173,8 @@ struct Ctx {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     bool stage_used[2] = {false, false};
     bool tree_built = false;    // the selected slot + j-set hold a GPU-built tree
+    bool trace_on = false;      // gplum_b200_debug_trace: the force kernel records where and when every item ran
+    DevBuf trace; int trace_items = 0;
     // device-resident particle state (iso_step.cu): EPJGrav[n] with particle k at slot k, + time, dt, acc0, flags
     DevBuf st_epj, st_time, st_dt, st_acc0, st_iso, st_star, st_handled, st_rec, st_idx, st_cnt;
     PinBuf st_pin;
@@ -227,18 +231,6 @@ void build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj, 
     const bool do_split = allow_split && g.rmax <= 2 && split_active((long long)tmp.size(), g.warp_slots, g.split_m);
     if (!do_split) {
         out.items.reserve(tmp.size());
-        // A pass whose CTAs are all resident at once (less than one wave) gets no dynamic balancing: CTA c lands on
-        // SM c mod n_sm, so with the plain longest-first order one SM collects the longest CTA of every round and
-        // another the shortest (measured: SMs active 82 % of the pass on a 1/8 shard).  Boustrophedon order -- every
-        // second round of n_sm CTAs reversed -- evens the per-SM sums out.
-        const long long n_full = (long long)tmp.size() / WPB, n_sm = g.warp_slots / 24;     // whole CTAs; a partial last one stays last
-        if (g.snake && allow_split && n_full > n_sm && (long long)tmp.size() <= g.warp_slots) {
-            for (long long r0 = n_sm; r0 < n_full; r0 += 2 * n_sm) {                          // every second round of n_sm CTAs
-                const long long r1 = std::min(r0 + n_sm, n_full);
-                for (long long a = r0, b = r1 - 1; a < b; a++, b--)
-                    for (int k = 0; k < WPB; k++) std::swap(tmp[(size_t)(a * WPB + k)], tmp[(size_t)(b * WPB + k)]);
-            }
-        }
         for (auto &t : tmp) {
             const BaseItem &b = t.second;
             const int wait = (peer_walk && peer_walk[b.walk]) ? ITEM_PEER_WAIT : 0;
@@ -350,13 +342,30 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
         p.peer_flags = reinterpret_cast<const int *>(static_cast<const char *>(g.peer.slab[0]) + ((size_t)1 << g.peer.shift) * sizeof(EpjPacked));
         p.peer_world = g.peer.world; p.peer_epoch = g.peer.epoch;
     }
+    p.trace = nullptr;
+    if (g.trace_on) {
+        if (int r = g.trace.reserve((size_t)(item0 + n_items) * 32)) return r;
+        if (item0 == 0) CU(cudaMemsetAsync(g.trace.p, 0, (size_t)n_items * 32, st));
+        p.trace = (unsigned long long *)g.trace.p + 4 * (size_t)item0;
+        g.trace_items = item0 + n_items;
+    }
     if (g.corr_on && ws.captured) {
         p.self_adr = (int *)ws.self_adr.p;
         p.pairs = (int2 *)ws.pairs.p;
         p.pair_count = (unsigned int *)ws.corr_meta.p;
         p.pair_cap = ws.pair_cap;
     }
-    const int n_warps = n_seg > 0 ? n_seg : n_items;
+    int n_warps = n_seg > 0 ? n_seg : n_items;
+    // a whole pass of at most one wave of items, more than one per scheduler: placed (items.h)
+    const int n_bins = (int)(g.warp_slots / 24) * 4;
+    p.place = nullptr; p.place_bins = 0; p.place_rounds = 0;
+    if (g.place && g.rmax <= 2 && n_seg == 0 && item0 == 0 && n_items == ws.n_items && n_items > n_bins && n_items <= g.warp_slots * g.place) {
+        const size_t cap0 = ws.place.cap;
+        if (int r = ws.place.reserve((size_t)(n_bins + 2) * 4)) return r;
+        if (ws.place.cap != cap0) CU(cudaMemsetAsync(ws.place.p, 0, ws.place.cap, st));
+        p.place = (int *)ws.place.p; p.place_bins = n_bins; p.place_rounds = place_rounds(n_items, n_bins);
+        n_warps = n_bins * std::min(p.place_rounds, (int)(g.warp_slots / n_bins));      // more rounds than fit: the resident warps loop
+    }
     // bulk-copy staging of the EP tiles (kernels.cuh) or per-record cp.async; peer slabs are always gathered by cp.async
     const bool bulk = g.bulk && !g.peer.on;
     const dim3 grid((n_warps + WPB - 1) / WPB), block(WPB * 32);
@@ -600,7 +609,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
     p.scratch = nullptr; p.arrive = nullptr; p.peer_flags = nullptr; p.peer_world = 0; p.peer_epoch = 0;
-    p.seg_off = nullptr; p.n_seg = 0;
+    p.seg_off = nullptr; p.n_seg = 0; p.trace = nullptr; p.place = nullptr; p.place_bins = 0; p.place_rounds = 0;
     if (g.rmax > 2) force_pass_kernel<4, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else if (g.bulk) force_pass_kernel<2, true><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else force_pass_kernel<2, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
@@ -643,7 +652,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_FLAGS")) g.flags = atoi(e);
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
     if (const char *e = getenv("GPLUM_B200_SPLIT_M")) g.split_m = std::max(0, atoi(e));
-    if (const char *e = getenv("GPLUM_B200_SNAKE")) g.snake = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_PLACE")) g.place = atoi(e);
     if (const char *e = getenv("GPLUM_B200_BULK")) g.bulk = atoi(e) ? 1 : 0;
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
@@ -1843,6 +1852,21 @@ int gplum_b200_state_push(const void *rec, const int *idx, int n_rec)
 }  // extern "C"
 
 // ---- host work-list builder, exposed for tests (no device needed) ----
+extern "C" int gplum_b200_debug_trace(int on, unsigned long long *out, int cap_items, int *n_items_out)
+{
+    if (int r = ensure_init()) return r;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (out) {
+        if (!n_items_out) return fail(GPLUM_B200_ERR_ARG, "debug_trace: n_items_out is null");
+        if (g.trace_items > cap_items) return fail(GPLUM_B200_ERR_ARG, "debug_trace: %d items, room for %d", g.trace_items, cap_items);
+        CU(cudaStreamSynchronize(g.stream));
+        if (g.trace_items > 0) CU(cudaMemcpy(out, g.trace.p, (size_t)g.trace_items * 32, cudaMemcpyDeviceToHost));
+        *n_items_out = g.trace_items;
+    }
+    g.trace_on = on != 0;
+    return 0;
+}
+
 extern "C" int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, const int *n_spj,
                                             long long warp_slots, int tile_cap, int jsplit, int split_m,
                                             int *items_out, int cap_items, int *n_items_out, int *n_slots_out, int *n_groups_out,

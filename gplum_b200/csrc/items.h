@@ -131,6 +131,16 @@ GB_HD bool seg_cut_next(SegCut &q, int &t0, int &t1, long long &seg)
 // upper bound of the split list's length: every base item once, plus one extra part per segment boundary
 GB_HD long long split_items_bound(long long n_base, long long n_seg) { return n_base + n_seg + 8; }
 
+// Placement of a pass whose warps are all resident at once (at most warp_slots items): the hardware puts CTA c on an
+// SM of its own choosing (measured on B200: neither c mod n_sm nor balanced -- profiles/r2_placement.txt) and nothing
+// rebalances afterwards, so the pass lasts as long as the scheduler with the largest sum of item costs (the model
+// cost predicts a scheduler's finishing time to 4 %).  A placed pass launches `rounds` CTAs per SM; every warp looks
+// up where it runs -- bin = SM x 4 + scheduler -- and is the k-th warp of its bin to ask: it takes entry (k, bin) of
+// the list, which is sorted longest first and dealt to the bins in boustrophedon order, round k left to right for
+// even k and right to left for odd k.  No table; host- and device-built lists need nothing but their order.
+GB_HD int place_item(int k, int bin, int n_bins) { return (k & 1) ? k * n_bins + (n_bins - 1 - bin) : k * n_bins + bin; }
+GB_HD int place_rounds(long long n_items, int n_bins) { return (int)((n_items + n_bins - 1) / n_bins); }
+
 // Tile capacity of a pass: 64 i-particles per warp is the most efficient shape (staging is amortised
 // over the most pairs), and measured on 1/4- and 1/8-size shards it stays the fastest even at 0.6 waves.
 // Only a pass that cannot give every fourth warp slot an item (per-call functor form, a small boundary

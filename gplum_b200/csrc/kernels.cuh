@@ -87,6 +87,14 @@ struct PassParams {
     // multi-GPU peer mode: items flagged ITEM_PEER_WAIT start once every rank's flag word has reached the epoch,
     // i.e. once all slabs of this step are packed (gplum_b200.cu: peer_pack)
     const int *peer_flags; int peer_world, peer_epoch;
+    // Placed passes (items.h: place_item): a pass whose warps are all resident at once has no dynamic balancing; its
+    // warps claim their item by WHERE they run -- bin = SM x scheduler, k = how many warps of that bin came before.
+    // place[0 .. place_bins) = the bins' claim counters, [place_bins] = items claimed so far, [place_bins + 1] = warps
+    // that have exited; all zero before and after a launch.  nullptr: warp s runs item s (or segment s).
+    int *place; int place_bins, place_rounds;
+    // placement trace (gplum_b200_debug_trace): per item {start, end (globaltimer ns), %smid | %warpid << 32, times run};
+    // nullptr = off
+    unsigned long long *trace;
 };
 
 // spins until flags[0 .. world) >= epoch (the peers store their epoch over NVLink after packing, st.release.sys)
@@ -715,15 +723,71 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
     using Smem = WarpSmem<32 * RMAX>;
     Smem &s = reinterpret_cast<Smem *>(smem_raw)[wid];
     const int slot = blockIdx.x * WPB + wid;
+    const int lane = threadIdx.x & 31;
     int item = slot, item_end = min(slot + 1, n_items);
     if (p.seg_off) {
         if (slot >= p.n_seg) return;
         item = p.seg_off[slot]; item_end = p.seg_off[slot + 1];
     }
-    for (; item < item_end; item++) {
+    // placed pass: this warp's bin, and where its search for unclaimed entries stands (-1: own bin not yet tried)
+    int my_bin = 0, scan = -1;
+    bool first_claim = true;
+    if (p.place) {
+        unsigned int smid, warpid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %warpid;" : "=r"(warpid));
+        my_bin = (int)((smid * 4u + (warpid & 3u)) % (unsigned int)p.place_bins);
+        item = 0; item_end = 0;
+    }
+    for (;;) {
+        if (p.place) {
+            // next unclaimed entry: first this warp's own bin, then -- only if items are still unclaimed once this warp
+            // has nothing left, i.e. the hardware did not spread the CTAs evenly -- any bin, 32 counters at a time
+            int found = -1;
+            if (scan < 0) {
+                scan = 0;
+                int k = 0;
+                if (lane == 0) k = atomicAdd(p.place + my_bin, 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k < p.place_rounds && place_item(k, my_bin, p.place_bins) < n_items) {
+                    found = place_item(k, my_bin, p.place_bins);
+                    scan = -1;                      // more rounds than resident warps: come back to this bin afterwards
+                } else if (first_claim) {
+                    __nanosleep(2000);              // no entry here: let the rightful owners claim theirs before looking around
+                }
+                first_claim = false;
+            }
+            while (found < 0) {
+                int claimed = 0;
+                if (lane == 0) claimed = *reinterpret_cast<volatile int *>(p.place + p.place_bins);
+                claimed = __shfl_sync(0xffffffffu, claimed, 0);
+                if (claimed >= n_items || scan >= p.place_bins) break;
+                const int b = (my_bin + 1 + scan + lane) % p.place_bins;
+                int k = p.place_rounds;
+                if (scan + lane < p.place_bins) k = *reinterpret_cast<volatile int *>(p.place + b);
+                const bool open = k < p.place_rounds && place_item(k, b, p.place_bins) < n_items;
+                const unsigned int m = __ballot_sync(0xffffffffu, open);
+                if (m == 0u) { scan += 32; continue; }
+                const int src = __ffs(m) - 1;
+                const int bb = __shfl_sync(0xffffffffu, b, src);
+                int kk = 0;
+                if (lane == 0) kk = atomicAdd(p.place + bb, 1);
+                kk = __shfl_sync(0xffffffffu, kk, 0);
+                if (kk < p.place_rounds && place_item(kk, bb, p.place_bins) < n_items) found = place_item(kk, bb, p.place_bins);
+                // else: someone else took it; look at the same 32 bins again
+            }
+            if (found < 0) break;
+            if (lane == 0) atomicAdd(p.place + p.place_bins, 1);
+            item = found;
+        } else {
+            if (item >= item_end) break;
+        }
         const WorkItem it = p.items[item];
+        unsigned long long tr0 = 0;
+        if (p.trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr0));
         if (it.ni == 0) {           // barrier item of the multi-GPU peer mode: the pass ends after every peer has packed
             if (it.cfg & ITEM_PEER_WAIT) peer_flags_wait(p.peer_flags, p.peer_world, p.peer_epoch);
+            item++;
             continue;
         }
         // cfg & 15: 0..3 = R-1 register slots per lane (full-width tiles); 8+k = lane-split tile, G = 2^k lane groups;
@@ -747,6 +811,27 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
             }
         }
         __syncwarp();               // the next item reuses this warp's shared-memory arrays
+        if (p.trace && (threadIdx.x & 31) == 0) {
+            unsigned long long tr1; unsigned int smid, warpid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr1));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            asm volatile("mov.u32 %0, %warpid;" : "=r"(warpid));
+            p.trace[4 * (size_t)item] = tr0; p.trace[4 * (size_t)item + 1] = tr1;
+            p.trace[4 * (size_t)item + 2] = (unsigned long long)smid | ((unsigned long long)warpid << 32);
+            atomicAdd(p.trace + 4 * (size_t)item + 3, 1ull);
+        }
+        item++;
+    }
+    if (p.place) {
+        // the last warp to leave zeroes the counters for the next launch (every other warp's last access is its
+        // arrival here)
+        int old = 0;
+        if (lane == 0) old = atomicAdd(p.place + p.place_bins + 1, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (int)(gridDim.x * WPB) - 1) {
+            __threadfence();
+            for (int k = lane; k < p.place_bins + 2; k += 32) p.place[k] = 0;
+        }
     }
 }
 

@@ -278,6 +278,12 @@ int gplum_b200_debug_build_items(int n_walk, const int *ni, const int *n_epj, co
                                  int *items_out, int cap_items, int *n_items_out, int *n_slots_out, int *n_groups_out,
                                  int *seg_off_out, int cap_seg, int *n_seg_out);
 
+/* Test / profiling support: with `on`, every following force pass records for each work item (in list order) when and
+ * where it ran: {start, end} in globaltimer nanoseconds, %smid | %warpid << 32, and how many times it was run (4 x 64 bit
+ * per item; barrier items of the peer mode leave zeros).  `out` != NULL first copies the last pass's records
+ * (cap_items = room in items). */
+int gplum_b200_debug_trace(int on, unsigned long long *out, int cap_items, int *n_items_out);
+
 /* FP32 FMA issue-rate microbenchmark (the roofline denominator measured in the same run):
  * returns achieved FFMA TFLOP/s (2 flop per FFMA) over `iters` launches. */
 int gplum_b200_fp32_peak(int iters, float *tflops, float *ms);
