@@ -253,10 +253,11 @@ def pinned_like(a):
 
 def soft_step_leg(args, w, F, S, L, check):
     """Next rows of the path (SURVEY 8f-1 + 8f-2): one whole soft-force evaluation without host-side
-    lists.  Per step, inside the timed region: raw particles (pinned host SoA, 48 B each) -> device,
-    tree + i-groups + interaction lists built on the GPU (dev_tree.cu), force pass with candidate
-    capture, changeover correction, forces + the corrections of the particles that have neighbours + neighbour
-    lists back to pinned host memory.
+    lists, driven the way include/gravity_tree_b200.hpp drives it.  Per step, inside the timed region: particle
+    columns (pinned host memory, 48 B each) -> device, tree + i-groups + interaction lists built on the GPU
+    (dev_tree.cu), force pass with candidate capture, {acc, phi} of every particle and the neighbour words of the
+    listed ones back; velocities of the listed particles up, changeover correction, the corrections of the
+    particles that have neighbours + neighbour lists back to pinned host memory.
     The reference: setParticleLocalTree .. calcForceAllAndWriteBack + correctForceLong
     (src/main_p3t.cpp:583-593)."""
     import ctypes as C
@@ -267,7 +268,10 @@ def soft_step_leg(args, w, F, S, L, check):
     def pin(a):
         b, t = pinned_like(a); keep.append(t); return b
     raw = {k: pin(np.ascontiguousarray(v, dtype=np.float64)) for k, v in w.raw.items()}
-    p_force = pin(np.zeros(n, dtype=S.FORCE))
+    p_acc = pin(np.zeros((n, 4), dtype=np.float32)); p_idx = pin(np.zeros(n, dtype=np.int32)); p_nb = pin(np.zeros((n, 4), dtype=np.int32))
+    p_vel = pin(np.zeros((n, 3), dtype=np.float64))
+    vel_all = np.ascontiguousarray(w.raw_vel, dtype=np.float64)
+    n_listed = C.c_int(0)
     p_corr = pin(np.zeros(n, dtype=S.CORR))
     ngb_cap = 4 * n + (1 << 20)
     p_ngb = pin(np.zeros(ngb_cap, dtype=S.NGB))
@@ -280,8 +284,11 @@ def soft_step_leg(args, w, F, S, L, check):
         sizes[0] = tree.build_walks_gpu(raw["pos"], raw["mass"], raw["r_out"], raw["r_search"], theta=0.5,
                                         n_leaf_limit=8, n_group_limit=args.group)
         F.walks_run(repack=False)
+        check(L.gplum_b200_tree_download_compact(vp(p_acc), vp(p_idx), vp(p_nb), n, C.byref(n_listed)))
+        m = n_listed.value
+        np.take(vel_all, p_idx[:m], axis=0, out=p_vel[:m])           # the caller's gather of the listed particles
+        check(L.gplum_b200_tree_set_motion_sparse(m, vp(p_idx), vp(p_vel), None))
         F.correct_long_run(prm)
-        check(L.gplum_b200_walks_download(vp(p_force)))
         check(L.gplum_b200_correct_long_download_compact(0, vp(p_corr), n, C.byref(n_corr), vp(p_ngb), ngb_cap,
                                                          C.byref(n_slots), C.byref(n_pairs)))
 
@@ -311,22 +318,25 @@ def soft_step_leg(args, w, F, S, L, check):
     n_int = int(sz[6] + sz[7])
     assert (int(sz[6]), int(sz[7])) == w.n_interactions(), "GPU-built lists differ from the host builder's"
     return {"ms_per_step": dt * 1e3, "interactions_per_s": n_int / dt,
-            "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int(32 * n + 64 * n_corr.value + 16 * n_slots.value),
-            "particles_with_neighbours": int(n_corr.value),
+            "h2d_bytes_per_step": int(48 * n + 28 * n_listed.value),
+            "d2h_bytes_per_step": int(16 * n + 20 * n_listed.value + 64 * n_corr.value + 16 * n_slots.value),
+            "particles_with_neighbours": int(n_corr.value), "particles_listed": int(n_listed.value),
             "list_build_ms_wall": dt_build * 1e3, "list_build_gpu_phases_ms": {k: round(v, 4) for k, v in phases.items()},
             "list_build_ms_host_builder": w.t_host_lists * 1e3,
             "force_pass_ms_on_gpu_lists": k_ms, "n_walks": int(sz[0]), "n_cells": int(sz[5]),
             "neighbour_pairs": int(n_pairs.value),
-            "api": "gplum_b200_tree_build_gpu + walks_run + correct_long_run + walks_download + "
-                   "correct_long_download_compact, pinned host buffers"}
+            "api": "gplum_b200_tree_build_gpu + walks_run + tree_download_compact + tree_set_motion_sparse + correct_long_run + "
+                   "correct_long_download_compact, pinned host buffers (include/gravity_tree_b200.hpp: "
+                   "calcForceAllAndWriteBack + correctForceLong)"}
 
 
 def tree_e2e_leg(args, w, F, S, L, check, reps):
     """e2e at N = 1: one soft-force evaluation as the caller of calcForceAllAndWriteBack sees it
     (FDPS/src/tree_for_force.hpp:1239-1253), through the C ABI with host buffers.  Inside the timed region, every
     step: raw particles (pinned host SoA, 48 B each) -> device, Morton sort + tree + moments + i-groups + lists on
-    the GPU, force pass, forces scattered back to particle order and copied to pinned host memory (32 B each).
-    Also timed with PAGEABLE caller buffers (FDPS's arrays are pageable)."""
+    the GPU, force pass, results scattered back to particle order and copied to pinned host memory: {acc, phi} of
+    every particle (16 B) + the neighbour words of the particles that have candidates (the others hold
+    ForceGrav::clear()'s values).  Also timed with PAGEABLE caller buffers (FDPS's arrays are pageable)."""
     import ctypes as C
     import torch
     n = args.n
@@ -336,12 +346,15 @@ def tree_e2e_leg(args, w, F, S, L, check, reps):
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     sz = np.zeros(8, dtype=np.int64)
 
+    n_nb = C.c_int(0)
+
     def run(raw, out):
+        acc4, idx, nbw = out
         def one():
             check(L.gplum_b200_tree_build_gpu(n, vp(raw["pos"]), vp(raw["mass"]), vp(raw["r_out"]), vp(raw["r_search"]),
                                               0.5, 8, args.group, 0, vp(sz)))
             F.walks_run(repack=False)
-            check(L.gplum_b200_tree_download_original(vp(out)))
+            check(L.gplum_b200_tree_download_compact(vp(acc4), vp(idx), vp(nbw), n, C.byref(n_nb)))
         for _ in range(2):
             one()
         torch.cuda.synchronize()
@@ -352,9 +365,14 @@ def tree_e2e_leg(args, w, F, S, L, check, reps):
         return (time.perf_counter() - t0) / reps
 
     raw_pin = {k: pin(np.ascontiguousarray(v, dtype=np.float64)) for k, v in w.raw.items()}
-    out_pin = pin(np.zeros(n, dtype=S.FORCE))
-    dt = run(raw_pin, out_pin)
+    outs = (pin(np.zeros((n, 4), dtype=np.float32)), pin(np.zeros(n, dtype=np.int32)), pin(np.zeros((n, 4), dtype=np.int32)))
+    dt = run(raw_pin, outs)
     # the forces that came back are the pass's forces, in particle order
+    out_pin = S.cleared_force(n)
+    out_pin["acc"] = outs[0][:, :3]; out_pin["phi"] = outs[0][:, 3]
+    kk = outs[1][:n_nb.value]
+    for c, name in enumerate(("number", "rank", "id_max", "id_min")):
+        out_pin[name][kk] = outs[2][:n_nb.value, c]
     order = w.epi["id_local"]
     F.walks_upload(w); F.walks_run(repack=True)
     ref = F.walks_download(n)
@@ -362,12 +380,13 @@ def tree_e2e_leg(args, w, F, S, L, check, reps):
     same = bool(np.array_equal(out_pin["number"][order], ref["number"]) and np.array_equal(out_pin["id_max"][order], ref["id_max"])
                 and np.quantile(da, 0.9999) < 1e-4 and da.max() < 2e-3)        # list order inside a walk differs: last bits
     raw_page = {k: np.ascontiguousarray(v, dtype=np.float64).copy() for k, v in w.raw.items()}
-    dt_page = run(raw_page, np.zeros(n, dtype=S.FORCE))
+    dt_page = run(raw_page, (np.zeros((n, 4), dtype=np.float32), np.zeros(n, dtype=np.int32), np.zeros((n, 4), dtype=np.int32)))
     n_int = int(sz[6] + sz[7])
     assert (int(sz[6]), int(sz[7])) == w.n_interactions(), "GPU-built lists differ from FDPS's"
-    return {"value": n_int / dt, "unit": "interactions/s", "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int(32 * n),
+    return {"value": n_int / dt, "unit": "interactions/s", "h2d_bytes_per_step": int(48 * n), "d2h_bytes_per_step": int(16 * n + 20 * n_nb.value + 4),
+            "particles_with_neighbour_candidates": int(n_nb.value),
             "ms_per_step": dt * 1e3, "ms_per_step_pageable_buffers": dt_page * 1e3, "forces_match_resident_pass": same,
-            "api": "gplum_b200_tree_build_gpu + gplum_b200_walks_run + gplum_b200_tree_download_original, pinned host buffers "
+            "api": "gplum_b200_tree_build_gpu + gplum_b200_walks_run + gplum_b200_tree_download_compact, pinned host buffers "
                    "(include/gravity_tree_b200.hpp binds these behind calcForceAllAndWriteBack)"}
 
 

@@ -45,6 +45,10 @@ SYMBOLS = {
     "gplum_b200_synchronize": (_i, []),
     "gplum_b200_counters": (None, [C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), _i]),
     "gplum_b200_tree_build_gpu": (_i, [_i, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _vp]),
+    "gplum_b200_tree_set_motion": (_i, [_i, _vp, _vp]),
+    "gplum_b200_tree_set_motion_sparse": (_i, [_i, _vp, _vp, _vp]),
+    "gplum_b200_tree_download_compact": (_i, [_vp, _vp, _vp, _i, C.POINTER(_i)]),
+    "gplum_b200_tree_build_gpu_vel": (_i, [_i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _vp]),
     "gplum_b200_tree_build_gpu_epj": (_i, [_i, _vp, _i, C.c_double, _i, _i, _vp]),
     "gplum_b200_tree_copy_gpu": (_i, [_vp] * 12),
     "gplum_b200_tree_gpu_times": (_i, [C.POINTER(_f)]),

@@ -144,13 +144,19 @@ __device__ __forceinline__ uint64_t key_lo(const uint64_t c[3])
 }
 
 // ---- root cube: bbox of the POSITIONS (FDPS/src/tree_for_force_impl.hpp:770-868; GetMyRSearch yields 0 for EPJGrav) ----
-__global__ void __launch_bounds__(TPB) bbox_kernel(const EpjAos *__restrict__ p, int n, double *__restrict__ part)
+// positions of the unsorted particles: EPJGrav records (stride 14 doubles, pos at +1) or a packed [n][3] column
+struct PosView {
+    const double *base; int stride;
+    __device__ __forceinline__ const double *at(int i) const { return base + (size_t)i * stride; }
+};
+__global__ void __launch_bounds__(TPB) bbox_kernel(PosView p, int n, double *__restrict__ part)
 {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+        const double *x = p.at(i);
         for (int k = 0; k < 3; k++) {
-            lo[k] = fmin(lo[k], p[i].pos[k]);
-            hi[k] = fmax(hi[k], p[i].pos[k]);
+            lo[k] = fmin(lo[k], x[k]);
+            hi[k] = fmax(hi[k], x[k]);
         }
     }
     __shared__ double sm[TPB / 32][6];
@@ -210,13 +216,13 @@ __global__ void bbox_final_kernel(const double *__restrict__ part, int n_part, K
     }
 }
 
-__global__ void __launch_bounds__(TPB) key_kernel(const EpjAos *__restrict__ p, int n, const Meta *__restrict__ m,
+__global__ void __launch_bounds__(TPB) key_kernel(PosView p, int n, const Meta *__restrict__ m,
                                                   uint64_t *__restrict__ key, int *__restrict__ idx)
 {
     const int i = blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     uint64_t c[3];
-    grid_coords(p[i].pos, m, c);
+    grid_coords(p.at(i), m, c);
     key[i] = spread3(c[0] >> LEVEL_HI) << 2 | spread3(c[1] >> LEVEL_HI) << 1 | spread3(c[2] >> LEVEL_HI);   // KeyT::hi_
     idx[i] = i;
 }
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(TPB) key_kernel(const EpjAos *__restrict__ p, 
 // FDPS sorts by (hi, lo); the radix sort above orders by hi only (stable: ties in particle order).  Particles that
 // share all 21 upper levels are closer than 2^-21 of the root edge -- rare --, so the runs of equal hi are put
 // into (lo, particle index) order here, one thread per run.
-__global__ void __launch_bounds__(TPB) tie_fix_kernel(const EpjAos *__restrict__ raw, int n, const Meta *__restrict__ m,
+__global__ void __launch_bounds__(TPB) tie_fix_kernel(PosView raw, int n, const Meta *__restrict__ m,
                                                       const uint64_t *__restrict__ key, int *__restrict__ idx)
 {
     const int i = blockIdx.x * TPB + threadIdx.x;
@@ -236,12 +242,12 @@ __global__ void __launch_bounds__(TPB) tie_fix_kernel(const EpjAos *__restrict__
     for (int a = i + 1; a < e; a++) {                                // insertion sort of idx[i..e) by (lo, index)
         const int va = idx[a];
         uint64_t c[3];
-        grid_coords(raw[va].pos, m, c);
+        grid_coords(raw.at(va), m, c);
         const uint64_t la = key_lo(c);
         int b = a - 1;
         while (b >= i) {
             const int vb = idx[b];
-            grid_coords(raw[vb].pos, m, c);
+            grid_coords(raw.at(vb), m, c);
             const uint64_t lb = key_lo(c);
             if (lb < la || (lb == la && vb < va)) break;
             idx[b + 1] = vb;
@@ -268,17 +274,31 @@ __global__ void __launch_bounds__(TPB) gather_kernel(const uint4 *__restrict__ i
     if (q < 3) reinterpret_cast<uint4 *>(epi)[(size_t)i * 3 + q] = v;
 }
 
-__global__ void __launch_bounds__(TPB) soa_to_epj_kernel(int n, const double *__restrict__ pos, const double *__restrict__ mass,
+// sorted EPJ / EPI from columns: 8 lanes per particle, lane q < 7 writes bytes [16 q, 16 q + 16) of the EPJGrav record
+// (src/particle.h:149-156: id_local, myrank | pos | r_out, r_search | id, mass | vel | acc_d)
+__global__ void __launch_bounds__(TPB) gather_soa_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
                                                          const double *__restrict__ r_out, const double *__restrict__ r_search,
-                                                         int rank, EpjAos *__restrict__ out)
+                                                         const double *__restrict__ vel, int rank, const int *__restrict__ idx, int n,
+                                                         uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
 {
-    const int i = blockIdx.x * TPB + threadIdx.x;
-    if (i >= n) return;
-    EpjAos j;
-    j.id_local = i; j.myrank = rank; j.id = i;
-    for (int k = 0; k < 3; k++) { j.pos[k] = pos[3 * (size_t)i + k]; j.vel[k] = 0.0; j.acc_d[k] = 0.0; }
-    j.r_out = r_out[i]; j.r_search = r_search[i]; j.mass = mass[i];
-    out[i] = j;
+    const int t = blockIdx.x * TPB + threadIdx.x;
+    const int i = t >> 3, q = t & 7;
+    if (i >= n || q == 7) return;
+    const int src = idx[i];
+    const size_t s3 = 3 * (size_t)src;
+    union { uint4 v; double d[2]; int w[4]; long long l[2]; } u;
+    u.v = make_uint4(0, 0, 0, 0);
+    switch (q) {
+        case 0: u.w[0] = src; u.w[1] = rank; u.d[1] = pos[s3]; break;
+        case 1: u.d[0] = pos[s3 + 1]; u.d[1] = pos[s3 + 2]; break;
+        case 2: u.d[0] = r_out[src]; u.d[1] = r_search[src]; break;
+        case 3: u.l[0] = src; u.d[1] = mass[src]; break;
+        case 4: if (vel) { u.d[0] = vel[s3]; u.d[1] = vel[s3 + 1]; } break;
+        case 5: if (vel) u.d[0] = vel[s3 + 2]; break;
+        default: break;
+    }
+    epj[(size_t)i * 7 + q] = u.v;
+    if (q < 3) reinterpret_cast<uint4 *>(epi)[(size_t)i * 3 + q] = u.v;
 }
 
 // ---- cells, one level per launch triple ----
@@ -531,6 +551,7 @@ __global__ void walk_range_kernel(KP P, const int *__restrict__ walk_cell, int n
 {
     if (threadIdx.x != 0) return;
     Meta *m = P.meta;
+    if (part_world <= 1) { m->w0 = 0; m->w1 = n_walk; m->e0 = n_walk > 0 ? 0 : P.n; m->e1 = P.n; return; }   // no searches (20 us of dependent loads)
     const long long p0 = (long long)P.n * part_rank / part_world, p1 = (long long)P.n * (part_rank + 1) / part_world;
     int b[2];
     for (int q = 0; q < 2; q++) {                   // number of walks whose first particle is below the bound
@@ -844,16 +865,6 @@ void tree_release()
     S.timed = false; S.cell_cap = 0; S.n = 0; S.coop_blocks = 0;
 }
 
-int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *r_out, const double *r_search,
-                    int rank, void *epj_out, cudaStream_t st, int *launches)
-{
-    if (n <= 0) return 0;
-    soa_to_epj_kernel<<<nblk(n, TPB), TPB, 0, st>>>(n, pos, mass, r_out, r_search, rank, (EpjAos *)epj_out);
-    CK(cudaGetLastError());
-    ++*launches;
-    return 0;
-}
-
 static KP make_kp(const TreeCfg &cfg, const void *epj_sorted)
 {
     KP P;
@@ -864,7 +875,7 @@ static KP make_kp(const TreeCfg &cfg, const void *epj_sorted)
     return P;
 }
 
-int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, void *epi, TreeCounts *counts,
+int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi, TreeCounts *counts,
                 cudaStream_t st, int *launches)
 {
     const int n = cfg.n;
@@ -893,7 +904,7 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         CK(S.fr_a.reserve(C * 4 + 64)); CK(S.fr_b.reserve(C * 4 + 64));     // a frontier <= the cells of its level
         CK(S.grp_at.reserve((size_t)n * 4)); CK(S.walk_cell.reserve((size_t)n * 4 + 16));
         KP P = make_kp(cfg, epj_sorted);
-        const EpjAos *raw = (const EpjAos *)epj_unsorted;
+        const PosView raw = src.pos ? PosView{src.pos, 3} : PosView{reinterpret_cast<const double *>(src.epj) + 1, (int)(sizeof(EpjAos) / 8)};
 
         CK(cudaEventRecord(S.ev[0], st));
         CK(cudaMemsetAsync(S.grp_at.p, 0xff, (size_t)n * 4, st));
@@ -910,8 +921,15 @@ int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, 
         CK(cub::DeviceRadixSort::SortPairs(S.cub_temp.p, tb, (const uint64_t *)S.keys_a.p, (uint64_t *)S.keys_b.p,
                                            (const int *)S.idx_a.p, (int *)S.idx_b.p, n, 0, 3 * LEVEL_HI, st));
         tie_fix_kernel<<<nblk(n, TPB), TPB, 0, st>>>(raw, n, P.meta, (const uint64_t *)S.keys_b.p, (int *)S.idx_b.p);
-        gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)raw, (const int *)S.idx_b.p, n,
-                                                                   (uint4 *)epj_sorted, (EpiAos *)epi);
+        if (attempt == 0 && src.before_gather) {
+            if (int e = src.before_gather(src.before_gather_arg)) return e;
+        }
+        if (src.pos)
+            gather_soa_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>(src.pos, src.mass, src.r_out, src.r_search, src.vel, src.rank,
+                                                                           (const int *)S.idx_b.p, n, (uint4 *)epj_sorted, (EpiAos *)epi);
+        else
+            gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)src.epj, (const int *)S.idx_b.p, n,
+                                                                       (uint4 *)epj_sorted, (EpiAos *)epi);
         CK(cudaGetLastError());
         *launches += 2;
         CK(cudaEventRecord(S.ev[1], st));

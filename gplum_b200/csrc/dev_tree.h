@@ -36,17 +36,26 @@ struct TreeOut {                 // destination buffers of phase 2 (sizes from T
     void *spj_aos;                               // n_cells x (80 | 32) B
 };
 
+// Where phase 1 finds the particles.  Records: epj = EPJGrav[n] on the device, any order.  Columns (pos != NULL): the
+// caller's SoA arrays on the device, pos is [n][3]; id_local = id = index, myrank = rank, vel = vel[i] or 0, acc_d = 0.
+// Keys and sort need the positions only: `before_gather` (optional) is called once after they are enqueued -- the
+// caller uploads the remaining columns there and makes the stream wait for them, so that the copy of 24 of the 48
+// bytes per particle overlaps the sort.
+struct TreeSrc {
+    const void *epj = nullptr;
+    const double *pos = nullptr, *mass = nullptr, *r_out = nullptr, *r_search = nullptr, *vel = nullptr;
+    int rank = 0;
+    int (*before_gather)(void *) = nullptr; void *before_gather_arg = nullptr;
+};
+
 // Phase 1: Morton keys, radix sort, gather (writes epj_sorted = EPJGrav[n] and epi = EPIGrav[n] in tree
 // order), cells, moments, i-groups, counting walk, scans.  Synchronises the stream twice (cell / group
 // counts, list totals).  epj_unsorted: EPJGrav[n] on the device, any order.  Returns cudaError_t (0 = ok)
 // or -1 with counts->overflow set.
-int tree_phase1(const TreeCfg &cfg, const void *epj_unsorted, void *epj_sorted, void *epi,
+int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi,
                 TreeCounts *counts, cudaStream_t st, int *launches);
 // Phase 2: filling walk, work items (sorted longest first), SPJ records.
 int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *launches);
-// EPJGrav[n] from SoA inputs (device pointers; pos is [n][3]): id_local = id = index, vel = acc_d = 0
-int tree_soa_to_epj(int n, const double *pos, const double *mass, const double *r_out, const double *r_search,
-                    int rank, void *epj_out, cudaStream_t st, int *launches);
 const int *tree_sorted_to_original();            // device pointer, n entries, valid after phase 1
 const int *tree_walk_ni();                       // device pointer, n_walk entries: i-particles per walk
 // milliseconds between the phase marks of the last build: [0] keys+sort+gather, [1] cells+moments (one

@@ -83,6 +83,8 @@ struct PinBuf {
 struct WalkSet {
     DevBuf epi, epi_off, adr_epj, epj_disp, n_epj, adr_spj, spj_disp, n_spj, items, force;
     DevBuf scratch, arrive;      // partial sums and arrival counters of j-split tiles (items.h)
+    DevBuf need;                 // tree_download_compact: particles that occur in captured candidate pairs
+    DevBuf org_index;            // tree_download_compact: particle indices of the compact neighbour records
     DevBuf place;                // claim counters of placed passes (kernels.cuh: PassParams::place), zero between launches
     DevBuf force_org;            // forces in the caller's particle order (tree_download_original)
     DevBuf seg_off;              // segments of a one-wave pass: warp s runs items [seg_off[s], seg_off[s+1]) (items.h)
@@ -109,7 +111,7 @@ struct WalkSet {
     {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (auto *v : {&ev_in, &ev_k, &ev_out}) { for (cudaEvent_t e : *v) cudaEventDestroy(e); v->clear(); }
-        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &place, &seg_off, &force_org,
+        for (DevBuf *b : {&epi, &epi_off, &adr_epj, &epj_disp, &n_epj, &adr_spj, &spj_disp, &n_spj, &items, &force, &scratch, &arrive, &place, &org_index, &need, &seg_off, &force_org,
                           &self_adr, &pairs, &corr_meta, &cnt, &off, &cursor, &csr, &corr_out, &corr_init, &ngb, &scan_temp, &corr_compact})
             b->release();
         h_force.release(); h_stage.release();
@@ -169,8 +171,12 @@ struct Ctx {
     bool corr_on = false;       // the force pass records candidate pairs for the changeover correction
     long long corr_cap = 0;     // pair-buffer capacity (0 = 4 x n_epi + 2^20)
     DevBuf tree_in, tree_raw;   // GPU list builder: SoA inputs, unsorted EPJGrav
+    DevBuf tree_motion;         // tree_set_motion: vel / acc_d columns
+    DevBuf tree_inv; bool tree_inv_valid = false;   // particle -> tree-order index of the last GPU build (built on demand)
     PinBuf tree_pin;            // pinned staging of pageable host inputs (upload_host)
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    PinBuf h_small; cudaEvent_t ev_small = nullptr;        // a few pinned words for counts that come back mid-call
+    cudaEvent_t ev_cols = nullptr, ev_cols0 = nullptr;     // tree_build_columns: columns on the device / columns free to overwrite
     bool stage_used[2] = {false, false};
     bool tree_built = false;    // the selected slot + j-set hold a GPU-built tree
     bool trace_on = false;      // gplum_b200_debug_trace: the force kernel records where and when every item ran
@@ -539,6 +545,74 @@ __global__ void unsort_force_kernel(int n, const uint4 *__restrict__ in, const i
     out[2 * (size_t)idx[t >> 1] + (t & 1)] = in[t];
 }
 
+// Particle order, compact: accphi[i] for every particle; the neighbour words only of particles with candidates
+// (all others hold ForceGrav::clear()'s values, src/particle.h:81-85).  Warp-aggregated append.
+// need[k] = 1 for every particle (tree order) that occurs in a captured candidate pair, as i or as j
+__global__ void mark_pairs_kernel(const int2 *__restrict__ pairs, const unsigned int *__restrict__ pair_count, unsigned int cap,
+                                  unsigned char *__restrict__ need)
+{
+    const unsigned int np = min(*pair_count, cap);
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < np; t += gridDim.x * blockDim.x) {
+        const int2 p = pairs[t];
+        need[p.x] = 1; need[p.y] = 1;
+    }
+}
+__global__ void unsort_compact_kernel(int n, const uint4 *__restrict__ in, const int *__restrict__ idx, uint4 *__restrict__ accphi,
+                                      int *__restrict__ count, int *__restrict__ nb_index, uint4 *__restrict__ nb, int cap,
+                                      const unsigned char *__restrict__ need)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool has = false;
+    int i = 0;
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (k < n) {
+        i = idx[k];
+        accphi[i] = in[2 * (size_t)k];
+        b = in[2 * (size_t)k + 1];
+        has = (int)b.x > 0 || (need && need[k]);
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, has);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (has) {
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        if (slot < cap) { nb_index[slot] = i; nb[slot] = b; }
+    }
+}
+
+// velocities / direct accelerations (columns in particle order) into the tree-order EPJGrav records
+__global__ void invert_order_kernel(int n, const int *__restrict__ idx, int *__restrict__ inv)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) inv[idx[k]] = k;
+}
+// the same for m listed particles: index[t] = particle, columns [m][3]
+__global__ void set_motion_sparse_kernel(int m, const int *__restrict__ index, const int *__restrict__ inv, const double *__restrict__ vel,
+                                         const double *__restrict__ acc_d, EpjAos *__restrict__ epj)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    const int k = inv[index[t]];
+    for (int d = 0; d < 3; d++) {
+        epj[k].vel[d] = vel ? vel[3 * (size_t)t + d] : 0.0;
+        epj[k].acc_d[d] = acc_d ? acc_d[3 * (size_t)t + d] : 0.0;
+    }
+}
+__global__ void set_motion_kernel(int n, const int *__restrict__ idx, const double *__restrict__ vel, const double *__restrict__ acc_d,
+                                  EpjAos *__restrict__ epj)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t s = 3 * (size_t)idx[k];
+    for (int d = 0; d < 3; d++) {
+        epj[k].vel[d] = vel ? vel[s + d] : 0.0;
+        epj[k].acc_d[d] = acc_d ? acc_d[s + d] : 0.0;
+    }
+}
+
 __global__ void iota_kernel(int *p, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -680,7 +754,7 @@ int gplum_b200_finalize(void)
     gplum_b200_peer_close();
     gplum_b200_peer_free();
     g.jset.release();
-    g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release();
+    g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release(); g.h_small.release(); g.tree_motion.release(); g.tree_inv.release(); g.tree_inv_valid = false;
     for (DevBuf *b : {&g.st_epj, &g.st_time, &g.st_dt, &g.st_acc0, &g.st_iso, &g.st_star, &g.st_handled, &g.st_rec, &g.st_idx, &g.st_cnt}) b->release();
     g.st_pin.release(); g.st_n = 0;
     gbt::tree_release();
@@ -1511,14 +1585,14 @@ int download_host(void *dst, const void *src, size_t bytes, cudaStream_t st)
     return 0;
 }
 
-int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_leaf_limit, int n_group_limit, long long *sizes,
+int tree_build_common(int n, const gbt::TreeSrc &src, double theta, int n_leaf_limit, int n_group_limit, long long *sizes,
                       int part_rank = 0, int part_world = 1)
 {
     if (g.rmax > 2) return fail(GPLUM_B200_ERR_STATE, "the GPU list builder needs the RMAX <= 2 kernel");
     cudaStream_t st = g.stream;
     WalkSet &ws = g.slots[g.cur];
     JSet &j = g.jset;
-    g.tree_built = false;
+    g.tree_built = false; g.tree_inv_valid = false;
     if (int r = ws.epi.reserve((size_t)n * sizeof(EpiAos))) return r;
     if (int r = ws.force.reserve((size_t)n * sizeof(ForceAos))) return r;
     if (int r = j.epj_aos.reserve((size_t)n * sizeof(EpjAos))) return r;
@@ -1530,7 +1604,7 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     gbt::TreeCounts c;
     memset(&c, 0, sizeof(c));
     int launches = 0;
-    int e = gbt::tree_phase1(cfg, epj_unsorted_dev, j.epj_aos.p, ws.epi.p, &c, st, &launches);
+    int e = gbt::tree_phase1(cfg, src, j.epj_aos.p, ws.epi.p, &c, st, &launches);
     g.launches += launches;
     if (e > 0) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 1: %s", cudaGetErrorString((cudaError_t)e));
     if (e < 0) return fail(GPLUM_B200_ERR_OVERFLOW, "GPU list builder: %s overflow", c.overflow == 1 ? "cell capacity" : "walk stack");
@@ -1579,6 +1653,50 @@ int tree_build_common(int n, const void *epj_unsorted_dev, double theta, int n_l
     }
     return 0;
 }
+// Particles as host columns (pos [n][3], mass, r_out, r_search, optional vel [n][3]).  Keys and sort need the positions
+// only, so those go up first and the other columns follow on the copy engine while the GPU sorts (dev_tree.h:
+// TreeSrc::before_gather); pageable columns are staged in that same window.
+struct ColumnUpload {
+    const double *cols[4]; size_t bytes[4]; double *dst[4]; int n_cols;
+};
+int upload_rest_columns(void *arg)
+{
+    ColumnUpload &u = *static_cast<ColumnUpload *>(arg);
+    for (int k = 0; k < u.n_cols; k++)
+        if (upload_host(u.dst[k], u.cols[k], u.bytes[k], g.copy_in)) return (int)cudaErrorUnknown;     // last_error holds the text
+    if (cudaEventRecord(g.ev_cols, g.copy_in) != cudaSuccess) return (int)cudaGetLastError();
+    if (cudaStreamWaitEvent(g.stream, g.ev_cols, 0) != cudaSuccess) return (int)cudaGetLastError();
+    return 0;
+}
+int tree_build_columns(int n, const double *pos, const double *mass, const double *r_out, const double *r_search, const double *vel,
+                       double theta, int n_leaf_limit, int n_group_limit, int rank, long long *sizes)
+{
+    cudaStream_t st = g.stream;
+    const size_t N = (size_t)n;
+    if (!g.copy_in) CU(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
+    if (!g.ev_cols) { CU(cudaEventCreateWithFlags(&g.ev_cols, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&g.ev_cols0, cudaEventDisableTiming)); }
+    if (g.tree_in.cap < N * 72) {
+        CU(cudaStreamSynchronize(st));                      // a build in flight may still read the old columns
+        if (int r = g.tree_in.reserve(N * 72)) return r;
+    }
+    double *d = (double *)g.tree_in.p;
+    // the copy engine starts once everything enqueued so far (the previous build's gather) is done with the columns
+    CU(cudaEventRecord(g.ev_cols0, st));
+    CU(cudaStreamWaitEvent(g.copy_in, g.ev_cols0, 0));
+    if (int r = upload_host(d, pos, N * 24, g.copy_in)) return r;
+    CU(cudaEventRecord(g.ev_cols, g.copy_in));
+    CU(cudaStreamWaitEvent(st, g.ev_cols, 0));
+    ColumnUpload u;
+    u.n_cols = 0;
+    auto add = [&](const double *c, size_t bytes, double *dst) { u.cols[u.n_cols] = c; u.bytes[u.n_cols] = bytes; u.dst[u.n_cols] = dst; u.n_cols++; };
+    add(mass, N * 8, d + 3 * N); add(r_out, N * 8, d + 4 * N); add(r_search, N * 8, d + 5 * N);
+    if (vel) add(vel, N * 24, d + 6 * N);
+    gbt::TreeSrc ts;
+    ts.pos = d; ts.mass = d + 3 * N; ts.r_out = d + 4 * N; ts.r_search = d + 5 * N; ts.vel = vel ? d + 6 * N : nullptr;
+    ts.rank = rank;
+    ts.before_gather = upload_rest_columns; ts.before_gather_arg = &u;
+    return tree_build_common(n, ts, theta, n_leaf_limit, n_group_limit, sizes);
+}
 }  // namespace
 
 extern "C" {
@@ -1590,20 +1708,19 @@ int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, cons
     if (n <= 0 || !pos || !mass || !r_out || !r_search || theta <= 0.0) return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu: bad argument");
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
-    cudaStream_t st = g.stream;
-    const size_t N = (size_t)n;
-    if (int r = g.tree_in.reserve(N * 48)) return r;
-    if (int r = g.tree_raw.reserve(N * sizeof(EpjAos))) return r;
-    double *d = (double *)g.tree_in.p;
-    if (int r = upload_host(d, pos, N * 24, st)) return r;
-    if (int r = upload_host(d + 3 * N, mass, N * 8, st)) return r;
-    if (int r = upload_host(d + 4 * N, r_out, N * 8, st)) return r;
-    if (int r = upload_host(d + 5 * N, r_search, N * 8, st)) return r;
-    int launches = 0;
-    if (int e = gbt::tree_soa_to_epj(n, d, d + 3 * N, d + 4 * N, d + 5 * N, rank, g.tree_raw.p, st, &launches))
-        return fail(GPLUM_B200_ERR_CUDA, "soa_to_epj: %s", cudaGetErrorString((cudaError_t)e));
-    g.launches += launches;
-    return tree_build_common(n, g.tree_raw.p, theta, n_leaf_limit, n_group_limit, sizes);
+    return tree_build_columns(n, pos, mass, r_out, r_search, nullptr, theta, n_leaf_limit, n_group_limit, rank, sizes);
+}
+
+/* The same with the velocities (the changeover correction's neighbour re-search and its `initial` form read them,
+ * src/gravity_soft.h:300-346): vel is [n][3] or NULL. */
+int gplum_b200_tree_build_gpu_vel(int n, const double *pos, const double *vel, const double *mass, const double *r_out,
+                                  const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
+                                  int rank, long long *sizes)
+{
+    if (n <= 0 || !pos || !mass || !r_out || !r_search || theta <= 0.0) return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu_vel: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    return tree_build_columns(n, pos, mass, r_out, r_search, vel, theta, n_leaf_limit, n_group_limit, rank, sizes);
 }
 
 int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double theta, int n_leaf_limit,
@@ -1618,7 +1735,9 @@ int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double 
         if (int r = upload_host(g.tree_raw.p, epj, (size_t)n * sizeof(EpjAos), g.stream)) return r;
         src = g.tree_raw.p;
     }
-    return tree_build_common(n, src, theta, n_leaf_limit, n_group_limit, sizes);
+    gbt::TreeSrc ts;
+    ts.epj = src;
+    return tree_build_common(n, ts, theta, n_leaf_limit, n_group_limit, sizes);
 }
 
 // Multi-GPU form: every rank hands over the SAME n particles (device pointer: the all-gathered EPJGrav
@@ -1633,7 +1752,9 @@ int gplum_b200_tree_build_gpu_part(int n, const void *epj_dev, double theta, int
         return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu_part: bad argument");
     if (int r = ensure_init()) return r;
     CU(cudaSetDevice(g.device));
-    return tree_build_common(n, epj_dev, theta, n_leaf_limit, n_group_limit, sizes, part_rank, part_world);
+    gbt::TreeSrc ts;
+    ts.epj = epj_dev;
+    return tree_build_common(n, ts, theta, n_leaf_limit, n_group_limit, sizes, part_rank, part_world);
 }
 
 // ForceGrav[count] of i-particles [first, first + count) of the selected walk set (tree order), host pointer
@@ -1689,6 +1810,118 @@ int gplum_b200_tree_download_original(void *force_out)
     CU(cudaGetLastError());
     g.launches++;
     return download_host(force_out, ws.force_org.p, (size_t)n * sizeof(ForceAos), g.stream);
+}
+
+// What the changeover correction reads besides the positions (src/gravity_soft.h:76-242: relative velocity, and the
+// difference of the direct accelerations in the neighbour re-search): columns in particle order, written into the
+// resident tree-order records of the last GPU build.  Either may be NULL (zeros).
+int gplum_b200_tree_set_motion(int n, const double *vel, const double *acc_d)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_set_motion: no GPU-built tree in the selected slot");
+    WalkSet &ws = g.slots[g.cur];
+    if (n != (int)ws.n_epi || n != g.jset.n_epj) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion: n = %d, the tree holds %lld particles", n, (long long)ws.n_epi);
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    const size_t N = (size_t)n;
+    if (g.tree_motion.cap < N * 48) {
+        CU(cudaStreamSynchronize(st));
+        if (int r = g.tree_motion.reserve(N * 48)) return r;
+    }
+    double *d = (double *)g.tree_motion.p;
+    if (vel) if (int r = upload_host(d, vel, N * 24, st)) return r;
+    if (acc_d) if (int r = upload_host(d + 3 * N, acc_d, N * 24, st)) return r;
+    set_motion_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, gbt::tree_sorted_to_original(), vel ? d : nullptr, acc_d ? d + 3 * N : nullptr,
+                                                       (EpjAos *)g.jset.epj_aos.p);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+// The same for m listed particles (index[t] = particle, columns [m][3]): the post-pass reads the motion only of
+// particles that occur in candidate pairs -- the ones tree_download_compact lists while the capture is on.
+int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_set_motion_sparse: no GPU-built tree in the selected slot");
+    if (m < 0 || (m > 0 && !index)) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_sparse: bad argument");
+    if (m == 0) return 0;
+    WalkSet &ws = g.slots[g.cur];
+    const int n = (int)ws.n_epi;
+    if (m > n) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_sparse: m = %d, the tree holds %d particles", m, n);
+    CU(cudaSetDevice(g.device));
+    cudaStream_t st = g.stream;
+    const size_t M = (size_t)m;
+    if (g.tree_motion.cap < M * 52 + 16) {
+        CU(cudaStreamSynchronize(st));
+        if (int r = g.tree_motion.reserve(M * 52 + 16)) return r;
+    }
+    if (!g.tree_inv_valid) {
+        if (int r = g.tree_inv.reserve((size_t)n * 4)) return r;
+        invert_order_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, gbt::tree_sorted_to_original(), (int *)g.tree_inv.p);
+        CU(cudaGetLastError());
+        g.launches++;
+        g.tree_inv_valid = true;
+    }
+    double *d = (double *)g.tree_motion.p;
+    int *d_index = (int *)(d + 6 * M);
+    if (int r = upload_host(d_index, index, M * 4, st)) return r;
+    if (vel) if (int r = upload_host(d, vel, M * 24, st)) return r;
+    if (acc_d) if (int r = upload_host(d + 3 * M, acc_d, M * 24, st)) return r;
+    set_motion_sparse_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, d_index, (const int *)g.tree_inv.p, vel ? d : nullptr, acc_d ? d + 3 * M : nullptr,
+                                                              (EpjAos *)g.jset.epj_aos.p);
+    CU(cudaGetLastError());
+    g.launches++;
+    return 0;
+}
+
+// The same results with half the bytes on the wire: {acc, phi} of every particle (16 B) and the neighbour words
+// {number, rank, id_max, id_min} only of the particles that have candidates (9 % of the N = 1e6 disk); the caller
+// fills in ForceGrav::clear()'s values (what gplum_b200_force_clear writes) for the rest.
+int gplum_b200_tree_download_compact(float *accphi_out, int *nb_index_out, int *nb_out, int cap, int *n_nb_out)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_download_compact: no GPU-built tree in the selected slot");
+    if (!accphi_out || !nb_index_out || !nb_out || !n_nb_out || cap < 0) return fail(GPLUM_B200_ERR_ARG, "tree_download_compact: bad argument");
+    CU(cudaSetDevice(g.device));
+    WalkSet &ws = g.slots[g.cur];
+    cudaStream_t st = g.stream;
+    const int n = (int)ws.n_epi;
+    if (int r = ws.force_org.reserve((size_t)n * sizeof(ForceAos))) return r;          // [0, 16 n): accphi; [16 n, 32 n): neighbour words
+    if (int r = ws.org_index.reserve((size_t)n * 4 + 16)) return r;                    // particle indices, then the counter
+    if (int r = g.h_small.reserve(64)) return r;
+    uint4 *d_acc = (uint4 *)ws.force_org.p, *d_nb = d_acc + n;
+    int *d_idx = (int *)ws.org_index.p, *d_cnt = d_idx + n;
+    CU(cudaMemsetAsync(d_cnt, 0, 4, st));
+    // with the candidate capture on, the list also names every particle that occurs in a captured pair (a pair that
+    // passes the FP32 test from one side only leaves its other end at number = 0): these are the particles whose
+    // velocities the post-pass needs (tree_set_motion_sparse)
+    unsigned char *need = nullptr;
+    if (g.corr_on && ws.captured) {
+        if (int r = ws.need.reserve((size_t)n)) return r;
+        need = (unsigned char *)ws.need.p;
+        CU(cudaMemsetAsync(need, 0, (size_t)n, st));
+        mark_pairs_kernel<<<148, 256, 0, st>>>((const int2 *)ws.pairs.p, (const unsigned int *)ws.corr_meta.p, ws.pair_cap, need);
+        g.launches++;
+    }
+    unsort_compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, (const uint4 *)ws.force.p, gbt::tree_sorted_to_original(), d_acc, d_cnt, d_idx, d_nb, n, need);
+    CU(cudaGetLastError());
+    g.launches++;
+    if (!g.ev_small) CU(cudaEventCreateWithFlags(&g.ev_small, cudaEventDisableTiming));
+    int *h_cnt = (int *)g.h_small.p;
+    CU(cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(g.ev_small, st));
+    cudaPointerAttributes at;
+    const cudaError_t pe = cudaPointerGetAttributes(&at, accphi_out);
+    if (pe != cudaSuccess) cudaGetLastError();
+    const bool pinned = pe == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+    if (pinned) CU(cudaMemcpyAsync(accphi_out, d_acc, (size_t)n * 16, cudaMemcpyDeviceToHost, st));     // the count arrives while this is on the wire
+    else if (int r = download_host(accphi_out, d_acc, (size_t)n * 16, st)) return r;
+    CU(cudaEventSynchronize(g.ev_small));
+    const int cnt = *h_cnt;
+    *n_nb_out = cnt;
+    if (cnt > cap) return fail(GPLUM_B200_ERR_OVERFLOW, "tree_download_compact: %d particles have neighbour candidates, room for %d", cnt, cap);
+    if (int r = download_host(nb_index_out, d_idx, (size_t)cnt * 4, st)) return r;
+    if (int r = download_host(nb_out, d_nb, (size_t)cnt * 16, st)) return r;
+    CU(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap)

@@ -69,7 +69,7 @@ def build_walks(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_l
 
 
 # ------------------------------------------------------------------ on the GPU (csrc/dev_tree.cu)
-def build_walks_gpu(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=64, rank=0):
+def build_walks_gpu(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_group_limit=64, rank=0, vel=None):
     """Builds tree, i-groups and lists on the device from SoA host arrays; the result becomes the
     selected resident walk set + j-set (nothing is copied back).  Returns sizes[8] like the host
     builder: n_walk, n_epi, n_adr_epj, n_adr_spj, n_epj_all, n_spj_all, n_int_epep, n_int_epsp."""
@@ -79,9 +79,37 @@ def build_walks_gpu(pos, mass, r_out, r_search, theta=0.5, n_leaf_limit=8, n_gro
     r_out = np.ascontiguousarray(np.broadcast_to(r_out, (n,)), dtype=np.float64)
     r_search = np.ascontiguousarray(np.broadcast_to(r_search, (n,)), dtype=np.float64)
     sz = np.zeros(8, dtype=np.int64)
+    if vel is not None:                 # the records the changeover correction reads (gplum_b200_tree_build_gpu_vel)
+        vel = np.ascontiguousarray(vel, dtype=np.float64)
+        assert vel.shape == (n, 3)
+        check(lib().gplum_b200_tree_build_gpu_vel(n, _p(pos), _p(vel), _p(mass), _p(r_out), _p(r_search), float(theta),
+                                                  int(n_leaf_limit), int(n_group_limit), int(rank), _p(sz)))
+        return sz
     check(lib().gplum_b200_tree_build_gpu(n, _p(pos), _p(mass), _p(r_out), _p(r_search), float(theta),
                                           int(n_leaf_limit), int(n_group_limit), int(rank), _p(sz)))
     return sz
+
+
+def download_original(n):
+    """ForceGrav[n] of the last GPU-built pass in the order the particles were handed in."""
+    f = np.zeros(n, dtype=S.FORCE)
+    check(lib().gplum_b200_tree_download_original(_p(f)))
+    return f
+
+
+def download_compact(n):
+    """The same through gplum_b200_tree_download_compact, expanded on the host: {acc, phi} of every particle, the
+    neighbour words of those that have candidates, ForceGrav::clear()'s values for the rest."""
+    accphi = np.zeros((n, 4), dtype=np.float32)
+    idx = np.zeros(n, dtype=np.int32); nb = np.zeros((n, 4), dtype=np.int32)
+    cnt = C.c_int(0)
+    check(lib().gplum_b200_tree_download_compact(_p(accphi), _p(idx), _p(nb), n, C.byref(cnt)))
+    f = S.cleared_force(n)
+    f["acc"] = accphi[:, :3]; f["phi"] = accphi[:, 3]
+    k = idx[:cnt.value]
+    f["number"][k] = nb[:cnt.value, 0]; f["rank"][k] = nb[:cnt.value, 1]
+    f["id_max"][k] = nb[:cnt.value, 2]; f["id_min"][k] = nb[:cnt.value, 3]
+    return f, cnt.value
 
 
 def build_walks_gpu_epj(epj, theta=0.5, n_leaf_limit=8, n_group_limit=64):

@@ -205,8 +205,12 @@ void gplum_b200_counters(long long *kernel_launches, long long *n_epep, long lon
  * result is not copied anywhere: it becomes the selected resident walk set and the current j-set (EPJ in
  * tree order, SPJ = cell moments, both packed), ready for gplum_b200_walks_run / _download and the
  * changeover correction.  Lists equal the host builder's as sets; within a list the order differs.
- *   tree_build_gpu      SoA host inputs (pos is [n][3]), 48 B per particle over PCIe; EPJ records get
- *                       id_local = id = input index, myrank = rank, vel = acc_d = 0.
+ *   tree_build_gpu      host columns (pos is [n][3]), 48 B per particle over PCIe; EPJ records get
+ *                       id_local = id = input index, myrank = rank, vel = acc_d = 0.  The positions go up first;
+ *                       the other columns follow on the copy engine while the GPU computes keys and sorts.
+ *   tree_build_gpu_vel  the same plus the velocities ([n][3], 72 B per particle): what the changeover correction's
+ *                       neighbour re-search reads (src/gravity_soft.h:300-346).  This is the form
+ *                       include/gravity_tree_b200.hpp binds behind calcForceAllAndWriteBack.
  *   tree_build_gpu_epj  EPJGrav[n] in any order (FDPS's epj_org_), host or device memory (16 B aligned);
  *                       records are carried whole, so the correction sees vel / acc_d / id.
  *   tree_copy_gpu       copies lists / particles back to host arrays (tests; any pointer may be NULL).
@@ -215,6 +219,9 @@ void gplum_b200_counters(long long *kernel_launches, long long *n_epep, long lon
 int gplum_b200_tree_build_gpu(int n, const double *pos, const double *mass, const double *r_out,
                               const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
                               int rank, long long *sizes);
+int gplum_b200_tree_build_gpu_vel(int n, const double *pos, const double *vel, const double *mass, const double *r_out,
+                                  const double *r_search, double theta, int n_leaf_limit, int n_group_limit,
+                                  int rank, long long *sizes);
 int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double theta, int n_leaf_limit,
                                   int n_group_limit, long long *sizes);
 /* Multi-GPU form: every rank passes the SAME n EPJGrav records (device pointer -- the all-gather of all
@@ -235,6 +242,25 @@ int gplum_b200_tree_gpu_times(float *ms6);
  * tree_build_gpu / tree_build_gpu_epj (FDPS's copyForceOriginalOrder + writeBack,
  * FDPS/src/tree_for_force_impl.hpp:873-883, tree_for_force.hpp:148-153); host pointer, synchronises. */
 int gplum_b200_tree_download_original(void *force_out);
+/* Velocities and direct accelerations of the particles of the last GPU build -- columns [n][3] in the order the
+ * particles were handed in, either may be NULL (zeros) -- written into the resident tree-order EPJGrav records: what
+ * gplum_b200_correct_long_run reads besides the positions (relative velocity and acc_d difference of the neighbour
+ * re-search, jerk of the `initial` form; src/gravity_soft.h:76-242).  tree_build_gpu + tree_set_motion carry the same
+ * fields as tree_build_gpu_epj, split the way the reference splits calcForceAllAndWriteBack and correctForceLong. */
+int gplum_b200_tree_set_motion(int n, const double *vel, const double *acc_d);
+/* The same for m listed particles: index[t] = particle (as handed in), vel / acc_d are [m][3].  The post-pass reads
+ * the motion only of particles that occur in candidate pairs; gplum_b200_tree_download_compact lists exactly those
+ * while the candidate capture (gplum_b200_soft_corr_enable) is on. */
+int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d);
+
+/* The same results with about half the bytes over PCIe.  accphi_out[4 i .. 4 i + 3] = {acc, phi} of particle i (in
+ * the order the particles were handed in); the neighbour words of ForceGrav come back only for the *n_nb_out
+ * particles that have candidates (number > 0): nb_index_out[k] = particle, nb_out[4 k ..] = {number, rank, id_max,
+ * id_min}.  Every other particle has exactly what gplum_b200_force_clear / ForceGrav::clear() writes
+ * (src/particle.h:81-85).  While the candidate capture is on, the list also names every particle that occurs in a
+ * captured pair from one side only (FP32 borderline; its words are the cleared ones): the set whose motion the
+ * post-pass needs.  cap = room in nb_index_out / nb_out (entries); n is always enough. */
+int gplum_b200_tree_download_compact(float *accphi_out, int *nb_index_out, int *nb_out, int cap, int *n_nb_out);
 /* diagnostics: %globaltimer (ns) at the level boundaries inside the cells+moments kernel of the last build;
  * returns the number of stamps written (<= cap) */
 int gplum_b200_tree_gpu_stamps(unsigned long long *ns_out, int cap);

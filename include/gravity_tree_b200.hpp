@@ -11,13 +11,16 @@
 // sites themselves stay as they are: TreeB200 has the members they use, and the overloads of correctForceLong{,Initial}
 // below are more specialised than the reference's templates (src/gravity_soft.h:245,375), so they are the ones chosen.
 //
-// Per evaluation, 112 B per particle go up (EPJGrav, what FDPS's setParticleLocalTree copies out of FPGrav anyway)
-// and 32 B per particle come back (ForceGrav, in particle order); Morton sort, tree, moments, i-groups, interaction
-// lists, both interaction kernels and the neighbour candidates stay on the device (gplum_b200/csrc/dev_tree.cu,
-// kernels.cuh).  The post-pass downloads what soft_corr.cu computed from the pass's candidate pairs -- the FP64
-// changeover correction and the final neighbour lists -- and enters it into FPGrav / NeighborList exactly where the
-// reference does (src/gravity_soft.h:349-368,506-521, src/neighbor.h:636-668); star gravity and the first time step
-// of the Initial form stay the reference's own host functions.  Single rank (open boundary), default macro set.
+// calcForceAllAndWriteBack: 48 B per particle go up (position, mass, r_out, r_search -- what the interaction kernels
+// read of EPJGrav) and 16 B per particle come back ({acc, phi}, in particle order) plus the four neighbour words of
+// the particles that have candidates; Morton sort, tree, moments, i-groups, interaction lists, both interaction
+// kernels and the neighbour candidates stay on the device (gplum_b200/csrc/dev_tree.cu, kernels.cuh).  The post-pass
+// sends the fields only IT reads (velocity and direct acceleration, 48 B) of the particles that occur in candidate
+// pairs (9 % of an N = 1e6 disk), and downloads what soft_corr.cu
+// computed from the pass's candidate pairs -- the FP64 changeover correction and the final neighbour lists -- and
+// enters it into FPGrav / NeighborList exactly where the reference does (src/gravity_soft.h:349-368,506-521,
+// src/neighbor.h:636-668); star gravity and the first time step of the Initial form stay the reference's own host
+// functions.  Single rank (open boundary), default macro set.
 #pragma once
 #include <cstdio>
 #include <vector>
@@ -38,13 +41,15 @@ class TreeB200 {
 public:
     PS::F64 theta_ = 0.5;
     PS::S32 n_leaf_limit_ = 8, n_group_limit_ = 64;
-    std::vector<EPJ_t> epj_;                     // epj_org_: particle k at slot k (FDPS/src/tree_for_force_impl.hpp:185-246)
-    std::vector<Force_t> force_;
+    std::vector<double> pos_, mass_, r_out_, r_search_, vel_, acc_d_;   // columns, particle k at slot k (FDPS's epj_org_ order)
+    std::vector<float> accphi_;
+    std::vector<int> nb_index_, nb_;
     std::vector<gplum_b200_corr> corr_;
     std::vector<gplum_b200_corr_init> init_;
     std::vector<gplum_b200_ngb> ngb_;
     long long sizes_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     PS::S64 n_walk_ = 0, n_int_epep_ = 0, n_int_epsp_ = 0;
+    PS::S32 n_listed_ = 0;                       // particles the last pass's download listed (candidate pairs)
 
     void initialize(const PS::U64 n_glb_tot, const PS::F64 theta = 0.7, const PS::U32 n_leaf_limit = 8, const PS::U32 n_group_limit = 64)
     {
@@ -69,9 +74,16 @@ public:
     {
         const PS::F64 t0 = PS::GetWtime();
         const PS::S32 n = psys.getNumberOfParticleLocal();
-        epj_.resize(n); force_.resize(n);
+        const size_t N = (size_t)n;
+        pos_.resize(3 * N); mass_.resize(N); r_out_.resize(N); r_search_.resize(N);
+        accphi_.resize(4 * N); nb_index_.resize(N); nb_.resize(4 * N);
 #pragma omp parallel for
-        for (PS::S32 i = 0; i < n; i++) epj_[i].copyFromFP(psys[i]);
+        for (PS::S32 i = 0; i < n; i++) {            // EPJGrav::copyFromFP (src/particle.h:131-169), the fields the kernels read
+            EPJ_t e;
+            e.copyFromFP(psys[i]);
+            pos_[3 * (size_t)i] = e.pos.x; pos_[3 * (size_t)i + 1] = e.pos.y; pos_[3 * (size_t)i + 2] = e.pos.z;
+            mass_[i] = e.mass; r_out_[i] = e.r_out; r_search_[i] = e.r_search;
+        }
 #ifdef USE_QUAD
         const int quad = 1;
 #else
@@ -80,13 +92,27 @@ public:
         tree_check(gplum_b200_set_params((float)FP_t::eps2, quad, -1), "gplum_b200_set_params");
         tree_check(gplum_b200_soft_corr_enable(1, 0), "gplum_b200_soft_corr_enable");       // the post-pass needs the pairs
         tree_check(gplum_b200_walks_select(0), "gplum_b200_walks_select");
-        tree_check(gplum_b200_tree_build_gpu_epj(n, epj_.data(), 0, theta_, n_leaf_limit_, n_group_limit_, sizes_), "gplum_b200_tree_build_gpu_epj");
+        tree_check(gplum_b200_tree_build_gpu(n, pos_.data(), mass_.data(), r_out_.data(), r_search_.data(), theta_, n_leaf_limit_,
+                                             n_group_limit_, PS::Comm::getRank(), sizes_), "gplum_b200_tree_build_gpu");
         tree_check(gplum_b200_walks_run(0), "gplum_b200_walks_run");
-        tree_check(gplum_b200_tree_download_original(force_.data()), "gplum_b200_tree_download_original");
+        int n_nb = 0;
+        tree_check(gplum_b200_tree_download_compact(accphi_.data(), nb_index_.data(), nb_.data(), n, &n_nb), "gplum_b200_tree_download_compact");
+        n_listed_ = n_nb;
         n_walk_ += sizes_[0]; n_int_epep_ += sizes_[6]; n_int_epsp_ += sizes_[7];
         (void)clear;                                                     // the pass overwrites: ForceGrav::clear is fused
 #pragma omp parallel for
-        for (PS::S32 i = 0; i < n; i++) psys[i].copyFromForce(force_[i]);
+        for (PS::S32 i = 0; i < n; i++) {
+            Force_t f;
+            f.clear();                                                   // neighbour words of a particle without candidates
+            f.acc.x = accphi_[4 * (size_t)i]; f.acc.y = accphi_[4 * (size_t)i + 1]; f.acc.z = accphi_[4 * (size_t)i + 2];
+            f.phi = accphi_[4 * (size_t)i + 3];
+            psys[i].copyFromForce(f);
+        }
+#pragma omp parallel for
+        for (PS::S32 k = 0; k < n_nb; k++) {
+            NeighborInfo &nb = psys[nb_index_[k]].neighbor;
+            nb.number = nb_[4 * (size_t)k]; nb.rank = nb_[4 * (size_t)k + 1]; nb.id_max = nb_[4 * (size_t)k + 2]; nb.id_min = nb_[4 * (size_t)k + 3];
+        }
         time_profile_.calc_force += PS::GetWtime() - t0;
     }
 
@@ -104,6 +130,18 @@ public:
         prm.re_search = 0;
 #endif
         prm.reserved = 0;
+        // the fields only the post-pass reads (src/gravity_soft.h:76-242: velocity, direct acceleration), of the
+        // particles that occur in candidate pairs -- the ones the pass's download listed
+        const PS::S32 m = n_listed_;
+        vel_.resize(3 * (size_t)m); acc_d_.resize(3 * (size_t)m);
+#pragma omp parallel for
+        for (PS::S32 t = 0; t < m; t++) {
+            EPJ_t e;
+            e.copyFromFP(pp[nb_index_[t]]);
+            vel_[3 * (size_t)t] = e.vel.x; vel_[3 * (size_t)t + 1] = e.vel.y; vel_[3 * (size_t)t + 2] = e.vel.z;
+            acc_d_[3 * (size_t)t] = e.acc_d.x; acc_d_[3 * (size_t)t + 1] = e.acc_d.y; acc_d_[3 * (size_t)t + 2] = e.acc_d.z;
+        }
+        tree_check(gplum_b200_tree_set_motion_sparse(m, nb_index_.data(), vel_.data(), acc_d_.data()), "gplum_b200_tree_set_motion_sparse");
         tree_check(gplum_b200_correct_long_run(0, &prm, initial ? 1 : 0), "gplum_b200_correct_long_run");
         corr_.resize(n);
         if (initial) init_.resize(n);
@@ -114,7 +152,8 @@ public:
                    "gplum_b200_correct_long_download");
         NList.initializeList(pp);
         n_ngb_tot = 0; n_with_ngb = 0;
-        // records come in tree order; corr.id_local is the particle's index (setIDLocalAndMyrank, src/func.h:135-143).
+        // records come in tree order; corr.id_local and ngb.id_local are particle indices (setIDLocalAndMyrank,
+        // src/func.h:135-143; the column form numbers the particles by index), the particles' ids are looked up here.
         // Serial: NeighborList::addNeighbor appends to shared lists (the reference guards them with omp critical).
         for (PS::S32 k = 0; k < n; k++) {
             const gplum_b200_corr &c = corr_[k];
@@ -130,7 +169,7 @@ public:
             pp[i].id_cluster = pp[i].id;
             for (PS::S32 q = 0; q < c.number; q++) {
                 const gplum_b200_ngb &b = ngb_[(size_t)c.ngb_off + q];
-                NList.addNeighbor(pp, i, b.id, b.rank, b.id_local);      // number++, id_cluster = min, pair / exchange lists
+                NList.addNeighbor(pp, i, pp[b.id_local].id, b.rank, b.id_local);      // number++, id_cluster = min, pair / exchange lists
             }
             if (pp[i].neighbor.number) {
                 NList.with_neighbor_list.push_back(i);

@@ -143,6 +143,55 @@ def test_force_from_gpu_lists_matches_oracle(n, group, rs_scale):
     assert np.array_equal(sz, sz2) and np.array_equal(g1.adr_epj, g2.adr_epj) and np.array_equal(g1.adr_spj, g2.adr_spj)
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_column_form_with_velocities_and_compact_download(pinned):
+    """gplum_b200_tree_build_gpu_vel (what include/gravity_tree_b200.hpp calls: positions first, the other columns
+    while the GPU sorts) builds the same tree-order records as the EPJGrav form, from pageable and from pinned
+    columns; gplum_b200_tree_download_compact returns what gplum_b200_tree_download_original returns."""
+    n = 40000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=31)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    rs = rs * 2.0
+    raw = np.zeros(n, dtype=S.EPJ)
+    raw["id_local"] = np.arange(n); raw["myrank"] = 0; raw["pos"] = d["pos"]; raw["r_out"] = ro; raw["r_search"] = rs
+    raw["id"] = np.arange(n); raw["mass"] = d["mass"]; raw["vel"] = d["vel"]
+    acc_d = np.random.default_rng(3).normal(size=(n, 3)) * 1e-3
+    sz0 = tree.build_walks_gpu_epj(raw, n_group_limit=128)
+    g0, o0 = tree.copy_walks_gpu(sz0)
+    cols = {"pos": d["pos"], "vel": d["vel"], "mass": d["mass"], "r_out": ro, "r_search": rs}
+    keep = []
+    if pinned:
+        import torch
+        for k, v in cols.items():
+            t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).pin_memory()
+            keep.append(t); cols[k] = t.numpy()
+    for rep_ in range(2):                                   # the second build overwrites columns a build has just read
+        sz = tree.build_walks_gpu(cols["pos"], cols["mass"], cols["r_out"], cols["r_search"], n_group_limit=128, vel=cols["vel"])
+    g, o = tree.copy_walks_gpu(sz)
+    assert np.array_equal(sz, sz0) and np.array_equal(o, o0)
+    assert g.epj_all.tobytes() == g0.epj_all.tobytes() and g.epi.tobytes() == g0.epi.tobytes()
+    assert np.array_equal(g.adr_epj, g0.adr_epj) and np.array_equal(g.adr_spj, g0.adr_spj)
+    F.walks_run(repack=False)
+    full = tree.download_original(n)
+    comp, n_nb = tree.download_compact(n)
+    assert full.tobytes() == comp.tobytes()
+    assert n_nb == int((full["number"] > 0).sum()) and 0 < n_nb < n
+    # without velocities: the same tree, vel = 0 in the records
+    sz1 = tree.build_walks_gpu(cols["pos"], cols["mass"], cols["r_out"], cols["r_search"], n_group_limit=128)
+    g1, o1 = tree.copy_walks_gpu(sz1)
+    assert np.array_equal(o1, o0) and not g1.epj_all["vel"].any() and np.array_equal(g1.epj_all["pos"], g0.epj_all["pos"])
+    # ... and tree_set_motion completes the records for the correction: the EPJGrav form with vel and acc_d
+    import ctypes as C
+    from gplum_b200._lib import check, lib
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    check(lib().gplum_b200_tree_set_motion(n, vp(np.ascontiguousarray(d["vel"])), vp(acc_d)))
+    g2, _ = tree.copy_walks_gpu(sz1)
+    raw["acc_d"] = acc_d
+    tree.build_walks_gpu_epj(raw, n_group_limit=128)
+    g3, _ = tree.copy_walks_gpu(sz1)
+    assert g2.epj_all.tobytes() == g3.epj_all.tobytes() and g3.epj_all["acc_d"].any()
+
+
 def test_epj_form_and_changeover_correction():
     """EPJGrav records in arbitrary order in, tree force + changeover correction out: the soft-force
     evaluation of one step (calcForceAllAndWriteBack + correctForceLong) without host-side lists."""
@@ -177,6 +226,31 @@ def test_epj_form_and_changeover_correction():
     from test_soft_corr_gpu import assert_corr_equal
     assert_corr_equal(corr, oc, want_f, None, None, ngb, on)
     assert corr["number"].sum() > 0
+    # The same stage the way include/gravity_tree_b200.hpp drives it: columns up (48 B), compact forces down, then
+    # velocity and direct acceleration of the LISTED particles only, then the correction.  Ids are particle indices.
+    import ctypes as C
+    from gplum_b200._lib import check, lib
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    h.epj_all["id"] = order
+    oc2, _, on2 = O.correct_long(h, prm, force=want_f)
+    F.soft_corr_enable(True)
+    try:
+        tree.build_walks_gpu(d["pos"], d["mass"], ro, rs, n_group_limit=64)
+        F.walks_run(repack=False)
+        f_org, n_listed = tree.download_compact(n)
+        idx = np.zeros(n, np.int32); nbw = np.zeros((n, 4), np.int32); acc4 = np.zeros((n, 4), np.float32); cnt = C.c_int(0)
+        check(lib().gplum_b200_tree_download_compact(vp(acc4), vp(idx), vp(nbw), n, C.byref(cnt)))
+        listed = idx[:cnt.value]
+        assert cnt.value == n_listed and set(np.nonzero(f_org["number"] > 0)[0].tolist()) <= set(listed.tolist())
+        assert len(listed) < n // 2                      # a fraction of the disk, not all of it
+        check(lib().gplum_b200_tree_set_motion_sparse(len(listed), vp(listed), vp(np.ascontiguousarray(d["vel"][listed])),
+                                                      vp(np.ascontiguousarray(acc_d[listed]))))
+        F.correct_long_run(prm)
+        corr2, _, ngb2 = F.correct_long_download(n)
+    finally:
+        F.soft_corr_enable(False)
+    assert f_org[order].tobytes() == got_f.tobytes()
+    assert_corr_equal(corr2, oc2, want_f, None, None, ngb2, on2)
 
 
 def test_full_size_properties():
