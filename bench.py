@@ -9,10 +9,13 @@ The lists are FDPS's own, list for list (tests/test_tree.py pins the host builde
 
   value     interactions/s with raw particles + lists resident in HBM (CUDA events, max over ranks)
   e2e       N=1: the whole soft-force evaluation a caller of calcForceAllAndWriteBack sees, through the C ABI with
-            HOST buffers: raw particles (48 B each) up, tree + groups + lists built on the GPU, force pass, forces
-            back in particle order (32 B each) -- gplum_b200_tree_build_gpu + walks_run + tree_download_original.
-            N>1: every rank ships what its rank of an MPI-FDPS run holds through gplum_b200_dispatch/retrieve.
-  e2e_multiwalk (N=1) the FDPS multi-walk-index functors (dispatch/retrieve) with host-built lists shipped every pass
+            HOST buffers: particle columns (48 B each) up, tree + groups + lists built on the GPU, force pass, {acc, phi}
+            back in particle order (16 B each) + the neighbour words of the particles that have candidates --
+            gplum_b200_tree_build_gpu + walks_run + tree_download_compact (what include/gravity_tree_b200.hpp calls).
+            N>1: the same on N GPUs -- every rank ships its n/N particles (48 B records), NCCL all-gather over NVLink, the
+            same tree on every GPU, every rank its share of the walks, ForceGrav of the share back (multi_tree_e2e_leg)
+  e2e_multiwalk  the FDPS multi-walk-index functors (dispatch/retrieve) with host-built lists shipped every pass; at N>1
+            every rank ships what its rank of an MPI-FDPS run holds (own walks, local + LET particles, its superparticles)
   parity_check   after the timed region: this run's forces of every 50th walk against the oracle
             (acc/phi 1e-4 with the conditioning floor of tests/synth.py, neighbour ints exact); non-zero exit on failure
   roofline  dominant kernel (force_pass_kernel): algorithmic flop (30/EP-EP pair, 59/EP-SP pair,
@@ -457,6 +460,59 @@ def multi_soft_step_leg(args, w, F, S, L, check, world, rank, dist, torch):
                    "walks_download_range + correct_long_download_compact"}
 
 
+def multi_tree_e2e_leg(args, w, F, S, L, check, world, rank, dist, torch, reps):
+    """e2e at N > 1: the evaluation a caller of calcForceAllAndWriteBack sees on an N-GPU run, no host-side lists.
+    Every step, inside the timed region: every rank copies ITS n / world particles (pinned host memory, 48 B records
+    {pos, mass, r_out, r_search}) to its GPU, the ranks all-gather the records over NVLink (NCCL), every GPU builds
+    the same tree and evaluates its Morton-contiguous share of the walks, and copies the ForceGrav records of its
+    share back to pinned host memory (32 B each).  Wall clock per step, max over ranks."""
+    from gplum_b200.multigpu import MultiGpuSoftStep
+    n = args.n
+    if n % world:
+        return None
+    m = n // world
+    sl = slice(rank * m, (rank + 1) * m)
+    rec = np.empty((m, 6), dtype=np.float64)
+    rec[:, :3] = w.raw["pos"][sl]; rec[:, 3] = w.raw["mass"][sl]; rec[:, 4] = w.raw["r_out"][sl]; rec[:, 5] = w.raw["r_search"][sl]
+    keep = []
+    def pin(a):
+        b, t = pinned_like(a); keep.append(t); return b
+    p_rec = pin(rec)
+    p_force = pin(np.zeros(n, dtype=S.FORCE))
+    ms = MultiGpuSoftStep(rec, n, world, rank, theta=0.5, n_leaf_limit=8, n_group_limit=args.group)
+
+    def one():
+        ms.upload_local(p_rec)
+        ms.step(None)
+        ms.forces(out=p_force)
+
+    F.walks_select(0)
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one()
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    w0, w1, e0, e1 = ms.share()
+    # this rank's forces against the single-rank resident pass of the same lists (tree order is the same tree's)
+    mine = torch.tensor([float(ms.sizes[6] + ms.sizes[7]), float(e1 - e0)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    # the forces that came back, against the oracle on every 50th walk of this rank's share (the GPU-built tree is the
+    # host builder's tree: same walks, same order)
+    par = parity_check(w, (w0, w1), p_force[:e1 - e0], e0) if w1 > w0 else {"ok": True, "walks": 0}
+    ok = torch.tensor([1.0 if par["ok"] else 0.0, float(par["walks"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.SUM)
+    return {"value": mine[0].item() / dt.item(), "unit": "interactions/s", "h2d_bytes_per_step": int(48 * m),
+            "d2h_bytes_per_step": int(32 * (e1 - e0)), "ms_per_step": dt.item() * 1e3,
+            "allgather_bytes_per_rank": int(48 * n), "interactions": int(mine[0].item()), "particles_covered": int(mine[1].item()),
+            "api": "per rank: 48 B records up + all_gather_into_tensor (NCCL) + gplum_b200_tree_build_gpu_part_rec48 + "
+                   "gplum_b200_walks_run + gplum_b200_walks_download_range, pinned host buffers",
+            "forces_match_oracle": bool(ok[0].item() == world), "walks_checked": int(ok[1].item())}
+
+
 def resident_step_leg(args, w, F, S, L, check):
     """SURVEY 8f-3 on top of f1 + f2: the particles stay in HBM across steps.  One step, all inside the timed
     region: velKick, Kepler drift of the isolated particles, the particles that need the host's hard part
@@ -763,6 +819,13 @@ def main():
            "api": "gplum_b200_dispatch(send_all) + gplum_b200_dispatch(walks) + gplum_b200_retrieve, pinned host buffers"}
     F.set_params(0.0, True, 0)
     e2e_multiwalk = None
+    if world > 1:
+        # the headline e2e at N > 1 is the same evaluation as at N = 1 -- particles in host memory, no host-side lists --
+        # on N GPUs; the multi-walk-index functors above ship host-built lists every pass: reported as e2e_multiwalk
+        res = multi_tree_e2e_leg(args, w, F, S, L, check, world, rank, dist, torch, n_e2e)
+        if res is not None:
+            e2e_multiwalk = e2e
+            e2e = res
     if world == 1:
         # the headline e2e at N = 1 is the whole evaluation a caller of calcForceAllAndWriteBack sees: raw particles in
         # host memory -> tree, groups and lists built on the GPU -> force pass -> forces back in particle order.

@@ -54,6 +54,7 @@ SYMBOLS = {
     "gplum_b200_tree_gpu_times": (_i, [C.POINTER(_f)]),
     "gplum_b200_tree_download_original": (_i, [_vp]),
     "gplum_b200_tree_build_gpu_part": (_i, [_i, _vp, C.c_double, _i, _i, _i, _i, _vp]),
+    "gplum_b200_tree_build_gpu_part_rec48": (_i, [_i, _vp, C.c_double, _i, _i, _i, _i, _vp]),
     "gplum_b200_walks_download_range": (_i, [_vp, _ll, _ll]),
     "gplum_b200_tree_gpu_stamps": (_i, [_vp, _i]),
     "gplum_b200_state_upload": (_i, [_i, _vp, _vp, _vp]),

@@ -278,21 +278,22 @@ __global__ void __launch_bounds__(TPB) gather_kernel(const uint4 *__restrict__ i
 // (src/particle.h:149-156: id_local, myrank | pos | r_out, r_search | id, mass | vel | acc_d)
 __global__ void __launch_bounds__(TPB) gather_soa_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
                                                          const double *__restrict__ r_out, const double *__restrict__ r_search,
-                                                         const double *__restrict__ vel, int rank, const int *__restrict__ idx, int n,
-                                                         uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
+                                                         const double *__restrict__ vel, int pos_stride, int col_stride, int rank,
+                                                         const int *__restrict__ idx, int n, uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
 {
     const int t = blockIdx.x * TPB + threadIdx.x;
     const int i = t >> 3, q = t & 7;
     if (i >= n || q == 7) return;
     const int src = idx[i];
     const size_t s3 = 3 * (size_t)src;
+    const size_t sp = (size_t)pos_stride * src, sc = (size_t)col_stride * src;
     union { uint4 v; double d[2]; int w[4]; long long l[2]; } u;
     u.v = make_uint4(0, 0, 0, 0);
     switch (q) {
-        case 0: u.w[0] = src; u.w[1] = rank; u.d[1] = pos[s3]; break;
-        case 1: u.d[0] = pos[s3 + 1]; u.d[1] = pos[s3 + 2]; break;
-        case 2: u.d[0] = r_out[src]; u.d[1] = r_search[src]; break;
-        case 3: u.l[0] = src; u.d[1] = mass[src]; break;
+        case 0: u.w[0] = src; u.w[1] = rank; u.d[1] = pos[sp]; break;
+        case 1: u.d[0] = pos[sp + 1]; u.d[1] = pos[sp + 2]; break;
+        case 2: u.d[0] = r_out[sc]; u.d[1] = r_search[sc]; break;
+        case 3: u.l[0] = src; u.d[1] = mass[sc]; break;
         case 4: if (vel) { u.d[0] = vel[s3]; u.d[1] = vel[s3 + 1]; } break;
         case 5: if (vel) u.d[0] = vel[s3 + 2]; break;
         default: break;
@@ -904,7 +905,7 @@ int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *
         CK(S.fr_a.reserve(C * 4 + 64)); CK(S.fr_b.reserve(C * 4 + 64));     // a frontier <= the cells of its level
         CK(S.grp_at.reserve((size_t)n * 4)); CK(S.walk_cell.reserve((size_t)n * 4 + 16));
         KP P = make_kp(cfg, epj_sorted);
-        const PosView raw = src.pos ? PosView{src.pos, 3} : PosView{reinterpret_cast<const double *>(src.epj) + 1, (int)(sizeof(EpjAos) / 8)};
+        const PosView raw = src.pos ? PosView{src.pos, src.pos_stride} : PosView{reinterpret_cast<const double *>(src.epj) + 1, (int)(sizeof(EpjAos) / 8)};
 
         CK(cudaEventRecord(S.ev[0], st));
         CK(cudaMemsetAsync(S.grp_at.p, 0xff, (size_t)n * 4, st));
@@ -925,7 +926,7 @@ int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *
             if (int e = src.before_gather(src.before_gather_arg)) return e;
         }
         if (src.pos)
-            gather_soa_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>(src.pos, src.mass, src.r_out, src.r_search, src.vel, src.rank,
+            gather_soa_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>(src.pos, src.mass, src.r_out, src.r_search, src.vel, src.pos_stride, src.col_stride, src.rank,
                                                                            (const int *)S.idx_b.p, n, (uint4 *)epj_sorted, (EpiAos *)epi);
         else
             gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)src.epj, (const int *)S.idx_b.p, n,

@@ -44,6 +44,8 @@ struct TreeOut {                 // destination buffers of phase 2 (sizes from T
 struct TreeSrc {
     const void *epj = nullptr;
     const double *pos = nullptr, *mass = nullptr, *r_out = nullptr, *r_search = nullptr, *vel = nullptr;
+    int pos_stride = 3, col_stride = 1;      // doubles between particles: packed columns, or one interleaved record per
+                                             // particle ({pos[3], mass, r_out, r_search}: strides 6 and 6, columns offset into it)
     int rank = 0;
     int (*before_gather)(void *) = nullptr; void *before_gather_arg = nullptr;
 };

@@ -1757,6 +1757,22 @@ int gplum_b200_tree_build_gpu_part(int n, const void *epj_dev, double theta, int
     return tree_build_common(n, ts, theta, n_leaf_limit, n_group_limit, sizes, part_rank, part_world);
 }
 
+// The same from 48 B records {pos[3], mass, r_out, r_search} (device pointer, the all-gather of every rank's records):
+// what the interaction kernels read of EPJGrav and nothing else -- 48 instead of 112 B per particle on NVLink.
+// id_local = id = index in the gathered array, myrank = 0, vel = acc_d = 0.
+int gplum_b200_tree_build_gpu_part_rec48(int n, const double *rec_dev, double theta, int n_leaf_limit, int n_group_limit,
+                                         int part_rank, int part_world, long long *sizes)
+{
+    if (n <= 0 || !rec_dev || theta <= 0.0 || part_world < 1 || part_rank < 0 || part_rank >= part_world)
+        return fail(GPLUM_B200_ERR_ARG, "tree_build_gpu_part_rec48: bad argument");
+    if (int r = ensure_init()) return r;
+    CU(cudaSetDevice(g.device));
+    gbt::TreeSrc ts;
+    ts.pos = rec_dev; ts.mass = rec_dev + 3; ts.r_out = rec_dev + 4; ts.r_search = rec_dev + 5;
+    ts.pos_stride = 6; ts.col_stride = 6;
+    return tree_build_common(n, ts, theta, n_leaf_limit, n_group_limit, sizes, part_rank, part_world);
+}
+
 // ForceGrav[count] of i-particles [first, first + count) of the selected walk set (tree order), host pointer
 int gplum_b200_walks_download_range(void *force_out, long long first, long long count)
 {

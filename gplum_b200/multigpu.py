@@ -222,19 +222,25 @@ class MultiGpuSoftStep:
         self.L = lib()
         self.world, self.rank, self.n = world, rank, n_total
         self.theta, self.leaf, self.group = theta, n_leaf_limit, n_group_limit
-        self.d_local = torch.from_numpy(np.ascontiguousarray(epj_local).view(np.uint8).copy()).cuda()
-        self.d_all = torch.empty(n_total * S.EPJ.itemsize, dtype=torch.uint8, device="cuda")
+        # EPJGrav records (112 B: the correction reads vel / acc_d / id), or -- for the force pass alone -- 48 B records
+        # {pos[3], mass, r_out, r_search}: an [m, 6] float64 array
+        local = np.ascontiguousarray(epj_local)
+        self.rec48 = local.dtype == np.float64
+        assert self.rec48 and local.shape[1:] == (6,) or local.dtype == S.EPJ
+        self.rec_bytes = 48 if self.rec48 else S.EPJ.itemsize
+        self.d_local = torch.from_numpy(local.view(np.uint8).reshape(-1).copy()).cuda()
+        self.d_all = torch.empty(n_total * self.rec_bytes, dtype=torch.uint8, device="cuda")
         self.sizes = np.zeros(12, dtype=np.int64)
 
     def upload_local(self, epj_local_pinned):
         """host -> device of this rank's records (a step's H2D when the particles live on the host)"""
-        self.d_local.copy_(torch.from_numpy(epj_local_pinned.view(np.uint8)), non_blocking=True)
+        self.d_local.copy_(torch.from_numpy(epj_local_pinned.view(np.uint8).reshape(-1)), non_blocking=True)
 
     def step(self, prm=None):
         dist.all_gather_into_tensor(self.d_all, self.d_local)
-        check(self.L.gplum_b200_tree_build_gpu_part(self.n, C.c_void_p(self.d_all.data_ptr()), float(self.theta), int(self.leaf),
-                                                    int(self.group), self.rank, self.world,
-                                                    self.sizes.ctypes.data_as(C.c_void_p)))
+        build = self.L.gplum_b200_tree_build_gpu_part_rec48 if self.rec48 else self.L.gplum_b200_tree_build_gpu_part
+        check(build(self.n, C.c_void_p(self.d_all.data_ptr()), float(self.theta), int(self.leaf), int(self.group), self.rank, self.world,
+                    self.sizes.ctypes.data_as(C.c_void_p)))
         F.walks_run(repack=False)
         if prm is not None:
             F.correct_long_run(prm)

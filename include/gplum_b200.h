@@ -232,6 +232,11 @@ int gplum_b200_tree_build_gpu_epj(int n, const void *epj, int on_device, double 
  * tree_build_gpu for THIS rank's lists, [8], [9] = its walks [w0, w1), [10], [11] = its i-particles [e0, e1). */
 int gplum_b200_tree_build_gpu_part(int n, const void *epj_dev, double theta, int n_leaf_limit, int n_group_limit,
                                    int part_rank, int part_world, long long *sizes);
+/* The same from 48 B records {pos[3], mass, r_out, r_search} (device pointer: the all-gather of all ranks' records) --
+ * the fields the interaction kernels read, 48 instead of 112 B per particle over NVLink.  id_local = id = index in the
+ * gathered array, myrank = 0, vel = acc_d = 0 (a following correction needs gplum_b200_tree_set_motion*). */
+int gplum_b200_tree_build_gpu_part_rec48(int n, const double *rec_dev, double theta, int n_leaf_limit, int n_group_limit,
+                                         int part_rank, int part_world, long long *sizes);
 /* ForceGrav[count] of i-particles [first, first + count) of the selected walk set (tree order); host pointer. */
 int gplum_b200_walks_download_range(void *force_out, long long first, long long count);
 int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, long long *epj_disp, int *n_epj,

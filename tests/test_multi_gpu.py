@@ -120,6 +120,63 @@ def _soft_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _rec48_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from gplum_b200 import disk, functors as F
+    from gplum_b200._lib import check, lib
+    from gplum_b200.multigpu import MultiGpuSoftStep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n = 24000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=9)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    F.init(rank)
+    F.set_params(0.0, True, 0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    check(lib().gplum_b200_set_stream(C.c_void_p(stream.cuda_stream)))
+    m = n // world
+    sl = slice(rank * m, (rank + 1) * m)
+    rec = np.empty((m, 6))
+    rec[:, :3] = d["pos"][sl]; rec[:, 3] = d["mass"][sl]; rec[:, 4] = ro[sl]; rec[:, 5] = rs[sl] * 2.0
+    ms = MultiGpuSoftStep(rec, n, world, rank, n_group_limit=128)
+    for _ in range(2):
+        ms.step(None)
+    np.save(os.path.join(out_dir, "rf%d.npy" % rank), ms.forces())
+    np.save(os.path.join(out_dir, "rs%d.npy" % rank), np.array(ms.share()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < WORLD, reason="needs >= %d GPUs" % WORLD)
+def test_multi_rank_force_pass_from_48_byte_records(tmp_path):
+    """the e2e form of bench.py at N > 1: all-gather of {pos, mass, r_out, r_search} records, the same tree on every
+    GPU, every rank its share of the walks; the union equals the single-rank oracle, the shares partition the disk."""
+    import torch.multiprocessing as mp
+    import oracle_api as O
+    import synth
+    from gplum_b200 import disk, structs as S, tree
+    world = WORLD
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_rec48_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    n = 24000
+    d = disk.make_disk(n, a_in=0.98, a_out=1.02, seed=9)
+    ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
+    h, _ = tree.build_walks(d["pos"], d["mass"], ro, rs * 2.0, n_group_limit=128)
+    want, _ = O.calc_walks(h, 0.0)
+    got = S.cleared_force(n); prev = 0
+    for r in range(world):
+        f = np.load(tmp_path / ("rf%d.npy" % r)); w0, w1, e0, e1 = np.load(tmp_path / ("rs%d.npy" % r))
+        assert e0 == prev and len(f) == e1 - e0
+        got[e0:e1] = f; prev = e1
+    assert prev == n and want["number"].sum() > 100
+    synth.assert_force_close(got, want, 1e-4, "multi-rank pass from 48 B records")
+
+
 @pytest.mark.skipif(_ngpu() < WORLD, reason="needs >= %d GPUs" % WORLD)
 def test_multi_rank_soft_step_without_host_lists(tmp_path):
     """all-gather of raw particles over NCCL -> the same tree on every GPU -> every rank its share of walks, forces,

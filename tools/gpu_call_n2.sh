@@ -9,7 +9,9 @@ import json
 try:
     j=json.loads([l for l in open("gpurun_out/r2_bench_n2.json") if l.startswith("{")][-1])
     print("value %.4g ms/step %.4f e2e ms %.3f"%(j["value"], j["ms_per_step"], j["e2e"]["ms_per_step"]))
+    print("e2e", j["e2e"]); print("e2e_multiwalk", j.get("e2e_multiwalk"))
     print("parity", j["parity_check"]); print("soft_step", j.get("soft_step")); print(j["config"]["l2"])
+    for p in j.get("phases_all", []): print("   ", p)
 except Exception as e:
     print("FAILED", e); print(open("gpurun_out/r2_bench_n2.err").read()[-2500:])
 PY
