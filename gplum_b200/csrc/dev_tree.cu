@@ -43,6 +43,7 @@ using gb::EpiAos;
 using gb::EpjAos;
 using gb::SpjMonoAos;
 using gb::SpjQuadAos;
+using gb::EpjPacked;
 using gb::BaseItem;
 using gb::WorkItem;
 
@@ -259,12 +260,19 @@ __global__ void __launch_bounds__(TPB) tie_fix_kernel(PosView raw, int n, const 
 
 // sorted EPJ (112 B records moved as 7 x 16 B) and the EPI of the same particle
 __global__ void __launch_bounds__(TPB) gather_kernel(const uint4 *__restrict__ in, const int *__restrict__ idx, int n,
-                                                     uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
+                                                     uint4 *__restrict__ epj, EpiAos *__restrict__ epi, EpjPacked *__restrict__ packed)
 {
     const int t = blockIdx.x * TPB + threadIdx.x;
     const int i = t >> 3, q = t & 7;              // 8 lanes per record, 7 of them move 16 B
     if (i >= n) return;
     const int src = idx[i];
+    if (q == 7) {                                 // the eighth writes the force kernel's packed record (kernels.cuh)
+        if (packed) {
+            const EpjAos *r = reinterpret_cast<const EpjAos *>(in) + src;
+            packed[i] = gb::epj_pack(r->pos, r->mass, r->r_out, r->r_search, r->id_local, r->myrank);
+        }
+        return;
+    }
     uint4 v = make_uint4(0, 0, 0, 0);
     if (q < 7) {
         v = __ldg(in + (size_t)src * 7 + q);
@@ -279,14 +287,22 @@ __global__ void __launch_bounds__(TPB) gather_kernel(const uint4 *__restrict__ i
 __global__ void __launch_bounds__(TPB) gather_soa_kernel(const double *__restrict__ pos, const double *__restrict__ mass,
                                                          const double *__restrict__ r_out, const double *__restrict__ r_search,
                                                          const double *__restrict__ vel, int pos_stride, int col_stride, int rank,
-                                                         const int *__restrict__ idx, int n, uint4 *__restrict__ epj, EpiAos *__restrict__ epi)
+                                                         const int *__restrict__ idx, int n, uint4 *__restrict__ epj, EpiAos *__restrict__ epi,
+                                                         EpjPacked *__restrict__ packed)
 {
     const int t = blockIdx.x * TPB + threadIdx.x;
     const int i = t >> 3, q = t & 7;
-    if (i >= n || q == 7) return;
+    if (i >= n) return;
     const int src = idx[i];
     const size_t s3 = 3 * (size_t)src;
     const size_t sp = (size_t)pos_stride * src, sc = (size_t)col_stride * src;
+    if (q == 7) {                                 // the force kernel's packed record
+        if (packed) {
+            const double x[3] = {pos[sp], pos[sp + 1], pos[sp + 2]};
+            packed[i] = gb::epj_pack(x, mass[sc], r_out[sc], r_search[sc], src, rank);
+        }
+        return;
+    }
     union { uint4 v; double d[2]; int w[4]; long long l[2]; } u;
     u.v = make_uint4(0, 0, 0, 0);
     switch (q) {
@@ -835,6 +851,7 @@ inline int nblk(long long n, int per) { return (int)((n + per - 1) / per); }
 
 }  // namespace
 
+const void *tree_cell_moments() { return S.c_mom.p; }
 const int *tree_sorted_to_original() { return (const int *)S.idx_b.p; }
 const int *tree_walk_ni() { return (const int *)S.w_ni.p; }
 
@@ -876,7 +893,7 @@ static KP make_kp(const TreeCfg &cfg, const void *epj_sorted)
     return P;
 }
 
-int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi, TreeCounts *counts,
+int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi, void *epj_packed, TreeCounts *counts,
                 cudaStream_t st, int *launches)
 {
     const int n = cfg.n;
@@ -927,10 +944,11 @@ int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *
         }
         if (src.pos)
             gather_soa_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>(src.pos, src.mass, src.r_out, src.r_search, src.vel, src.pos_stride, src.col_stride, src.rank,
-                                                                           (const int *)S.idx_b.p, n, (uint4 *)epj_sorted, (EpiAos *)epi);
+                                                                           (const int *)S.idx_b.p, n, (uint4 *)epj_sorted, (EpiAos *)epi,
+                                                                           (EpjPacked *)epj_packed);
         else
             gather_kernel<<<nblk((long long)n * 8, TPB), TPB, 0, st>>>((const uint4 *)src.epj, (const int *)S.idx_b.p, n,
-                                                                       (uint4 *)epj_sorted, (EpiAos *)epi);
+                                                                       (uint4 *)epj_sorted, (EpiAos *)epi, (EpjPacked *)epj_packed);
         CK(cudaGetLastError());
         *launches += 2;
         CK(cudaEventRecord(S.ev[1], st));
@@ -1058,7 +1076,7 @@ int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *la
         }
     }
     if (S.n_cells > 0) {
-        if (cfg.quad) CK(cudaMemcpyAsync(out.spj_aos, S.c_mom.p, (size_t)S.n_cells * 80, D2D, st));
+        if (cfg.quad) { if (out.spj_aos) CK(cudaMemcpyAsync(out.spj_aos, S.c_mom.p, (size_t)S.n_cells * 80, D2D, st)); }
         else {
             spj_mono_kernel<<<nblk(S.n_cells, TPB), TPB, 0, st>>>(S.n_cells, (const double *)S.c_mom.p, (SpjMonoAos *)out.spj_aos);
             CK(cudaGetLastError());

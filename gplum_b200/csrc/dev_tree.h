@@ -33,7 +33,7 @@ struct TreeOut {                 // destination buffers of phase 2 (sizes from T
     int n_items_out;                             // = TreeCounts::n_items (one work item per tile), or tree_items_bound() of a
                                                  //   pass that splits its tiles along j (trailing entries are empty items)
     int *seg_off;                                // warp_slots + 1 entries, written when the pass is laid out in segments
-    void *spj_aos;                               // n_cells x (80 | 32) B
+    void *spj_aos;                               // n_cells x (80 | 32) B; NULL (quadrupole only): read tree_cell_moments() in place
 };
 
 // Where phase 1 finds the particles.  Records: epj = EPJGrav[n] on the device, any order.  Columns (pos != NULL): the
@@ -51,14 +51,15 @@ struct TreeSrc {
 };
 
 // Phase 1: Morton keys, radix sort, gather (writes epj_sorted = EPJGrav[n] and epi = EPIGrav[n] in tree
-// order), cells, moments, i-groups, counting walk, scans.  Synchronises the stream twice (cell / group
+// order and, if epj_packed != NULL, the force kernel's packed 48 B records of the same particles), cells, moments, i-groups, counting walk, scans.  Synchronises the stream twice (cell / group
 // counts, list totals).  epj_unsorted: EPJGrav[n] on the device, any order.  Returns cudaError_t (0 = ok)
 // or -1 with counts->overflow set.
-int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi,
+int tree_phase1(const TreeCfg &cfg, const TreeSrc &src, void *epj_sorted, void *epi, void *epj_packed,
                 TreeCounts *counts, cudaStream_t st, int *launches);
 // Phase 2: filling walk, work items (sorted longest first), SPJ records.
 int tree_phase2(const TreeCfg &cfg, const TreeOut &out, cudaStream_t st, int *launches);
 const int *tree_sorted_to_original();            // device pointer, n entries, valid after phase 1
+const void *tree_cell_moments();                 // device pointer, n_cells x 80 B {mass, pos, quad}: MySPJQuadrupole records
 const int *tree_walk_ni();                       // device pointer, n_walk entries: i-particles per walk
 // milliseconds between the phase marks of the last build: [0] keys+sort+gather, [1] cells+moments (one
 // cooperative kernel), [2] i-group compaction + first host sync, [3] counting walk + scans + second sync,

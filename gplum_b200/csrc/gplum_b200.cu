@@ -122,7 +122,11 @@ struct WalkSet {
 struct JSet {
     DevBuf epj_aos, spj_aos, epj_packed, spj_packed;
     const void *ext_epj = nullptr, *ext_spj = nullptr;   // caller-owned packed arrays (all-gather output)
+    const void *spj_src = nullptr;                        // the SPJ records live elsewhere on the device (a GPU-built tree's cell
+                                                          // moments, dev_tree.cu) instead of in spj_aos
+    bool epj_packed_fresh = false;                        // the list builder's gather wrote epj_packed itself
     int n_epj = 0, n_spj = 0;
+    const void *spj_records() const { return spj_src ? spj_src : spj_aos.p; }
     const EpjPacked *epj() const { return ext_epj ? (const EpjPacked *)ext_epj : (const EpjPacked *)epj_packed.p; }
     const SpjPacked *spj() const { return ext_spj ? (const SpjPacked *)ext_spj : (const SpjPacked *)spj_packed.p; }
     void release() { epj_aos.release(); spj_aos.release(); epj_packed.release(); spj_packed.release(); }
@@ -386,13 +390,14 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
 int pack_j(cudaStream_t st, float eps2)
 {
     JSet &j = g.jset;
-    if (j.n_epj > 0 && !j.ext_epj) {
+    if (j.n_epj > 0 && !j.ext_epj && !j.epj_packed_fresh) {
         pack_epj_kernel<<<(j.n_epj + 255) / 256, 256, 0, st>>>((const EpjAos *)j.epj_aos.p, j.n_epj, (EpjPacked *)j.epj_packed.p);
         CU(cudaGetLastError());
         g.launches++;
     }
+    j.epj_packed_fresh = false;
     if (j.n_spj > 0 && !j.ext_spj) {
-        pack_spj_kernel<<<(j.n_spj + 255) / 256, 256, 0, st>>>(j.spj_aos.p, j.n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
+        pack_spj_kernel<<<(j.n_spj + 255) / 256, 256, 0, st>>>(j.spj_records(), j.n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
                                                                (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, eps2);
         CU(cudaGetLastError());
         g.launches++;
@@ -404,7 +409,7 @@ int upload_j(const void *epj_all, int n_epj_all, const void *spj_all, int n_spj_
 {
     JSet &j = g.jset;
     const size_t ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
-    j.ext_epj = j.ext_spj = nullptr;
+    j.ext_epj = j.ext_spj = nullptr; j.spj_src = nullptr; j.epj_packed_fresh = false;
     j.n_epj = n_epj_all; j.n_spj = n_spj_all;
     if (int r = j.epj_aos.reserve((size_t)n_epj_all * sizeof(EpjAos))) return r;
     if (int r = j.epj_packed.reserve((size_t)n_epj_all * sizeof(EpjPacked))) return r;
@@ -885,7 +890,7 @@ int send_all_pipelined(const void *epj_all, int n_epj_all, const void *spj_all, 
     JSet &j = g.jset;
     cudaStream_t st = g.stream, ci = g.copy_in;
     const size_t ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
-    j.ext_epj = j.ext_spj = nullptr;
+    j.ext_epj = j.ext_spj = nullptr; j.spj_src = nullptr; j.epj_packed_fresh = false;
     j.n_epj = n_epj_all; j.n_spj = n_spj_all;
     if (int r = j.epj_aos.reserve((size_t)n_epj_all * sizeof(EpjAos))) return r;
     if (int r = j.epj_packed.reserve((size_t)n_epj_all * sizeof(EpjPacked))) return r;
@@ -1253,7 +1258,7 @@ int gplum_b200_peer_pack(const void *epj_aos_dev, int n)
     const int n_spj = (j.n_spj > 0 && !j.ext_spj) ? j.n_spj : 0;
     const int nb_e = std::max(1, (n + PACK_BLOCK - 1) / PACK_BLOCK), nb_s = (n_spj + PACK_BLOCK - 1) / PACK_BLOCK;
     peer_pack_kernel<<<nb_e + nb_s, PACK_BLOCK, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)pe.slab[pe.parity],
-                                                                j.spj_aos.p, n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
+                                                                j.spj_records(), n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
                                                                 (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2, nb_e,
                                                                 (unsigned int *)pe.done.p, (void *const *)pe.table[0].p,
                                                                 ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
@@ -1604,7 +1609,7 @@ int tree_build_common(int n, const gbt::TreeSrc &src, double theta, int n_leaf_l
     gbt::TreeCounts c;
     memset(&c, 0, sizeof(c));
     int launches = 0;
-    int e = gbt::tree_phase1(cfg, src, j.epj_aos.p, ws.epi.p, &c, st, &launches);
+    int e = gbt::tree_phase1(cfg, src, j.epj_aos.p, ws.epi.p, j.epj_packed.p, &c, st, &launches);
     g.launches += launches;
     if (e > 0) return fail(GPLUM_B200_ERR_CUDA, "GPU list builder, phase 1: %s", cudaGetErrorString((cudaError_t)e));
     if (e < 0) return fail(GPLUM_B200_ERR_OVERFLOW, "GPU list builder: %s overflow", c.overflow == 1 ? "cell capacity" : "walk stack");
@@ -1625,13 +1630,14 @@ int tree_build_common(int n, const gbt::TreeSrc &src, double theta, int n_leaf_l
     if (int r = reserve_split(ws, dev_split ? n_items_out : 1, dev_split ? c.n_items : 1, st)) return r;
     if (int r = ws.seg_off.reserve((size_t)(g.warp_slots + 1) * 4)) return r;
     ws.n_seg = dev_split ? (int)g.warp_slots : 0;
-    if (int r = j.spj_aos.reserve((size_t)c.n_cells * ssz)) return r;
+    if (!g.quad) if (int r = j.spj_aos.reserve((size_t)c.n_cells * ssz)) return r;
     if (int r = j.spj_packed.reserve((size_t)c.n_cells * sizeof(SpjPacked))) return r;
     gbt::TreeOut o;
     o.epi_off = (int *)ws.epi_off.p; o.ni = nullptr; o.n_epj = (int *)ws.n_epj.p; o.n_spj = (int *)ws.n_spj.p;
     o.epj_disp = (long long *)ws.epj_disp.p; o.spj_disp = (long long *)ws.spj_disp.p;
     o.adr_epj = (int *)ws.adr_epj.p; o.adr_spj = (int *)ws.adr_spj.p;
-    o.items = ws.items.p; o.n_items_out = n_items_out; o.seg_off = (int *)ws.seg_off.p; o.spj_aos = j.spj_aos.p;
+    o.items = ws.items.p; o.n_items_out = n_items_out; o.seg_off = (int *)ws.seg_off.p;
+    o.spj_aos = g.quad ? nullptr : j.spj_aos.p;           // quadrupole records ARE the cells' moment records: read in place
     launches = 0;
     e = gbt::tree_phase2(cfg, o, st, &launches);
     g.launches += launches;
@@ -1644,6 +1650,8 @@ int tree_build_common(int n, const gbt::TreeSrc &src, double theta, int n_leaf_l
     ws.pending = false; ws.captured = false; ws.corrected = false;
     j.ext_epj = j.ext_spj = nullptr;
     j.n_epj = n; j.n_spj = c.n_cells;
+    j.spj_src = g.quad ? gbt::tree_cell_moments() : nullptr;
+    j.epj_packed_fresh = true;                           // written by the gather (dev_tree.cu)
     if (int r = pack_j(st, g.eps2)) return r;
     g.tree_built = true;
     if (sizes) {
@@ -1797,7 +1805,7 @@ int gplum_b200_tree_copy_gpu(void *epi, int *epi_off, int *ni, int *adr_epj, lon
     const size_t nw = (size_t)ws.n_walk, ssz = g.quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
     if (epi) CU(cudaMemcpy(epi, ws.epi.p, (size_t)ws.n_epi * sizeof(EpiAos), D2H));
     if (epj_all) CU(cudaMemcpy(epj_all, j.epj_aos.p, (size_t)j.n_epj * sizeof(EpjAos), D2H));
-    if (spj_all && j.n_spj) CU(cudaMemcpy(spj_all, j.spj_aos.p, (size_t)j.n_spj * ssz, D2H));
+    if (spj_all && j.n_spj) CU(cudaMemcpy(spj_all, j.spj_records(), (size_t)j.n_spj * ssz, D2H));
     if (sorted_to_original) CU(cudaMemcpy(sorted_to_original, gbt::tree_sorted_to_original(), (size_t)ws.n_epi * 4, D2H));
     if (nw) {
         if (epi_off) CU(cudaMemcpy(epi_off, ws.epi_off.p, nw * 4, D2H));

@@ -45,21 +45,6 @@ constexpr int UNROLL = GB_UNROLL;
 constexpr float RS = GB_NEWTON ? 2.0f : 1.0f;
 constexpr float RS2_INV = 1.0f / (RS * RS), RS_INV = 1.0f / RS, RS3_INV = 1.0f / (RS * RS * RS);
 
-// ---- packed j-records in HBM (written by the pack kernels, read by vectorised 16 B loads) ----
-struct __align__(16) EpjPacked {   // 48 B
-    double x, y;
-    double z; float m, rout2;
-    float rs2; int id; int rank; int pad;
-};
-struct __align__(16) SpjPacked {   // 64 B; Q = (3q - tr*I)/RS^2, mtr = -(eps2*tr)/RS^2 hoisted (j-only terms;
-                                   // the exact power-of-two scale pairs with a = RS*y in the pair loop)
-    double x, y;
-    double z; float m, qxx;
-    float qyy, qzz, qxy, qyz;
-    float qzx, mtr, pad0, pad1;
-};
-static_assert(sizeof(EpjPacked) == 48 && sizeof(SpjPacked) == 64, "packed layout");
-
 struct PassParams {
     const EpiAos *epi;            // concatenated i-particles
     const int *epi_off;           // per walk
@@ -182,14 +167,7 @@ __device__ __forceinline__ void pack_epj_block(const EpjAos *__restrict__ in, in
     const int i = blk * PACK_BLOCK + threadIdx.x;
     if (i >= n) return;
     const EpjAos &a = reinterpret_cast<const EpjAos *>(sm)[threadIdx.x];
-    EpjPacked o;
-    o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2];
-    o.m = (float)a.mass;
-    const float ro = (float)a.r_out, rs = (float)a.r_search;
-    o.rout2 = __fmul_rn(ro, ro);
-    o.rs2 = __fmul_rn(__fmul_rn(rs, rs), 1.0201f);
-    o.id = a.id_local; o.rank = a.myrank; o.pad = 0;
-    out[i] = o;
+    out[i] = epj_pack(a.pos, a.mass, a.r_out, a.r_search, a.id_local, a.myrank);
 }
 
 __global__ void __launch_bounds__(PACK_BLOCK) pack_epj_kernel(const EpjAos *__restrict__ in, int n, EpjPacked *__restrict__ out)
