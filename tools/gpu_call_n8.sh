@@ -1,10 +1,9 @@
 #!/bin/bash
-# 8-GPU box: the NCCL parity tests at 8 ranks (and 2), then the bench at N = 8, 4, 2, configs[4] strong + weak
+# 8-GPU box: the NCCL parity tests at 8 ranks, then the bench at N = 8, 4, 2 and configs[4] (N = 1e7) on 8 GPUs
+# (its 1-GPU points run in tools/gpu_call_final.sh)
 mkdir -p gpurun_out
 ( GPLUM_TEST_WORLD=8 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/r2_pytest_multi_w8.log 2>&1
 tail -3 gpurun_out/r2_pytest_multi_w8.log
-( timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q ) > gpurun_out/r2_pytest_multi_w2.log 2>&1
-tail -3 gpurun_out/r2_pytest_multi_w2.log
 show() { python - "$1" <<'PY'
 import json,sys
 f=sys.argv[1]
@@ -23,5 +22,3 @@ done
 # configs[4]: wide disk N = 1e7, 0.5-10 AU: strong scaling point at 8 GPUs, weak scaling points 1.25e6 per GPU at 1 and 8
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 10 --warmup 3 --particles 10000000 --a-in 0.5 --a-out 10 > gpurun_out/r2_bench_cfg4_n8.json 2> gpurun_out/r2_bench_cfg4_n8.err
 show gpurun_out/r2_bench_cfg4_n8.json
-timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --n 1250000 --a-in 0.5 --a-out 10 --no-cpu-baseline > gpurun_out/r2_bench_cfg4_weak_n1.json 2> gpurun_out/r2_bench_cfg4_weak_n1.err
-show gpurun_out/r2_bench_cfg4_weak_n1.json

@@ -10,7 +10,8 @@ tot = 0.0
 for name, unit, val in zip(h, u, v):
     if name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(val) * scale[unit]
-head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+import os
+head = os.environ.get("GPLUM_HEAD") or subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 out = {"dram_bytes": int(tot), "n": n, "group": group, "a_in": a_in, "a_out": a_out, "kernel": "force_pass_kernel<2, false>",
        "source": "ncu --set full --clock-control none, one launch inside bench.py (cold L2: ncu flushes caches between replays)",
        "commit": head}
