@@ -505,12 +505,15 @@ def multi_tree_e2e_leg(args, w, F, S, L, check, world, rank, dist, torch, reps):
     par = parity_check(w, (w0, w1), p_force[:e1 - e0], e0) if w1 > w0 else {"ok": True, "walks": 0}
     ok = torch.tensor([1.0 if par["ok"] else 0.0, float(par["walks"])], dtype=torch.float64, device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.SUM)
+    errs = [None] * world
+    dist.all_gather_object(errs, par.get("error"))
     return {"value": mine[0].item() / dt.item(), "unit": "interactions/s", "h2d_bytes_per_step": int(48 * m),
             "d2h_bytes_per_step": int(32 * (e1 - e0)), "ms_per_step": dt.item() * 1e3,
             "allgather_bytes_per_rank": int(48 * n), "interactions": int(mine[0].item()), "particles_covered": int(mine[1].item()),
             "api": "per rank: 48 B records up + all_gather_into_tensor (NCCL) + gplum_b200_tree_build_gpu_part_rec48 + "
                    "gplum_b200_walks_run + gplum_b200_walks_download_range, pinned host buffers",
-            "forces_match_oracle": bool(ok[0].item() == world), "walks_checked": int(ok[1].item())}
+            "forces_match_oracle": bool(ok[0].item() == world), "walks_checked": int(ok[1].item()),
+            **({"parity_errors": [e for e in errs if e]} if any(errs) else {})}
 
 
 def resident_step_leg(args, w, F, S, L, check):
