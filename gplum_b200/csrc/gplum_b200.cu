@@ -145,6 +145,11 @@ struct Peer {
     void *mapped[2][MAX_PEERS] = {};                    // every rank's slabs in this process' address space
     DevBuf table[2];                                    // device copies of mapped[b][0..world)
     DevBuf done;                                        // block counter of peer_pack_kernel
+    // a pack requested by gplum_b200_peer_pack and not launched yet: the next force launch does it in its prologue if
+    // it is a placed pass (kernels.cuh: fp_*), else it launches peer_pack_kernel first
+    bool pending = false; const void *pending_epj = nullptr; int pending_n = 0;
+    int fuse = 0;                                       // GPLUM_B200_FUSE_PACK=1: pack in the prologue of placed passes; measured 4 % slower
+                                                        // than the separate launch at 8 GPUs (profiles/r2_fused_pack.txt), so off by default
 };
 
 struct Ctx {
@@ -304,6 +309,25 @@ int reserve_split(WalkSet &ws, int n_slots, int n_groups, cudaStream_t st)
     return 0;
 }
 
+// The pack of a multi-GPU peer step as a launch of its own (kernels.cuh: peer_pack_kernel)
+int launch_peer_pack(cudaStream_t st)
+{
+    Peer &pe = g.peer;
+    JSet &j = g.jset;
+    const int n = pe.pending_n;
+    const int n_spj = (j.n_spj > 0 && !j.ext_spj) ? j.n_spj : 0;
+    const int nb_e = std::max(1, (n + PACK_BLOCK - 1) / PACK_BLOCK), nb_s = (n_spj + PACK_BLOCK - 1) / PACK_BLOCK;
+    peer_pack_kernel<<<nb_e + nb_s, PACK_BLOCK, 0, st>>>((const EpjAos *)pe.pending_epj, n, (EpjPacked *)pe.slab[pe.parity],
+                                                         j.spj_records(), n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
+                                                         (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2, nb_e,
+                                                         (unsigned int *)pe.done.p, (void *const *)pe.table[0].p,
+                                                         ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
+    CU(cudaGetLastError());
+    g.launches++;
+    pe.pending = false;
+    return 0;
+}
+
 // Launches the force kernel on items [item0, item0 + n_items) of the set (default: all).  `first` resets the
 // candidate capture and counts the pass's interactions; sub-batch launches of one pass pass first = false.
 int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_items = -1, bool first = true,
@@ -371,7 +395,7 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
     p.place = nullptr; p.place_bins = 0; p.place_rounds = 0;
     if (g.place && g.rmax <= 2 && n_seg == 0 && item0 == 0 && n_items == ws.n_items && n_items > n_bins && n_items <= g.warp_slots * g.place) {
         const size_t cap0 = ws.place.cap;
-        if (int r = ws.place.reserve((size_t)(n_bins + 2) * 4)) return r;
+        if (int r = ws.place.reserve((size_t)(n_bins + 3) * 4)) return r;
         if (ws.place.cap != cap0) CU(cudaMemsetAsync(ws.place.p, 0, ws.place.cap, st));
         p.place = (int *)ws.place.p; p.place_bins = n_bins; p.place_rounds = place_rounds(n_items, n_bins);
         n_warps = n_bins * std::min(p.place_rounds, (int)(g.warp_slots / n_bins));      // more rounds than fit: the resident warps loop
@@ -379,6 +403,33 @@ int launch_pass(WalkSet &ws, cudaStream_t st, float eps2, int item0 = 0, int n_i
     // bulk-copy staging of the EP tiles (kernels.cuh) or per-record cp.async; peer slabs are always gathered by cp.async
     const bool bulk = g.bulk && !g.peer.on;
     const dim3 grid((n_warps + WPB - 1) / WPB), block(WPB * 32);
+    // multi-GPU peer mode: the step's pack, fused into a placed pass (cooperative launch: the prologue ends in a grid
+    // barrier) or as a launch of its own
+    p.fp_slab = nullptr;
+    if (g.peer.on && g.peer.pending) {
+        Peer &pe = g.peer;
+        bool fused = false;
+        if (pe.fuse && p.place && g.rmax <= 2 && !bulk) {
+            JSet &j = g.jset;
+            p.fp_epj_in = (const EpjAos *)pe.pending_epj; p.fp_n_epj = pe.pending_n; p.fp_slab = (EpjPacked *)pe.slab[pe.parity];
+            p.fp_n_spj = (j.n_spj > 0 && !j.ext_spj) ? j.n_spj : 0;
+            p.fp_spj_in = j.spj_records(); p.fp_spj_out = (SpjPacked *)j.spj_packed.p;
+            p.fp_quad = g.quad; p.fp_trace = (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0;
+            p.fp_slab0_of = (void *const *)pe.table[0].p; p.fp_flag_off = ((size_t)1 << pe.shift) * sizeof(EpjPacked); p.fp_rank = pe.rank;
+            int n_it = n_items;
+            void *args[] = {(void *)&p, (void *)&n_it};
+            const cudaError_t ce = cudaLaunchCooperativeKernel((const void *)force_pass_kernel<2, false>, grid, block, args, (size_t)g.smem_bytes, st);
+            if (ce == cudaSuccess) {
+                fused = true;
+            } else {                                    // not co-resident here (another context on the GPU): separate launches
+                cudaGetLastError();
+                p.fp_slab = nullptr;
+            }
+        }
+        pe.pending = false;
+        if (fused) { g.launches++; return 0; }
+        if (int r = launch_peer_pack(st)) return r;
+    }
     if (g.rmax > 2) force_pass_kernel<4, false><<<grid, block, g.smem_bytes, st>>>(p, n_items);
     else if (bulk) force_pass_kernel<2, true><<<grid, block, g.smem_bytes, st>>>(p, n_items);
     else force_pass_kernel<2, false><<<grid, block, g.smem_bytes, st>>>(p, n_items);
@@ -688,7 +739,7 @@ int single_call(int which, const void *epi, int ni, const void *jp, int nj, void
     p.rank_squared = (g.flags & GPLUM_B200_RANK_SQUARED) ? 1 : 0;
     p.self_adr = nullptr; p.pairs = nullptr; p.pair_count = nullptr; p.pair_cap = 0;
     p.scratch = nullptr; p.arrive = nullptr; p.peer_flags = nullptr; p.peer_world = 0; p.peer_epoch = 0;
-    p.seg_off = nullptr; p.n_seg = 0; p.trace = nullptr; p.place = nullptr; p.place_bins = 0; p.place_rounds = 0;
+    p.seg_off = nullptr; p.n_seg = 0; p.trace = nullptr; p.place = nullptr; p.place_bins = 0; p.place_rounds = 0; p.fp_slab = nullptr;
     if (g.rmax > 2) force_pass_kernel<4, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else if (g.bulk) force_pass_kernel<2, true><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
     else force_pass_kernel<2, false><<<((int)items.size() + WPB - 1) / WPB, WPB * 32, g.smem_bytes, s.st>>>(p, (int)items.size());
@@ -732,6 +783,7 @@ int gplum_b200_init(int device, size_t max_i, size_t max_j)
     if (const char *e = getenv("GPLUM_B200_JSPLIT")) g.jsplit = atoi(e);
     if (const char *e = getenv("GPLUM_B200_SPLIT_M")) g.split_m = std::max(0, atoi(e));
     if (const char *e = getenv("GPLUM_B200_PLACE")) g.place = atoi(e);
+    if (const char *e = getenv("GPLUM_B200_FUSE_PACK")) g.peer.fuse = atoi(e);
     if (const char *e = getenv("GPLUM_B200_BULK")) g.bulk = atoi(e) ? 1 : 0;
     g.smem_bytes = (int)(g.rmax <= 2 ? sizeof(WarpSmem<64>) : sizeof(WarpSmem<128>)) * WPB;
     CU(cudaFuncSetAttribute(force_pass_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem<64>) * WPB));
@@ -1250,20 +1302,13 @@ int gplum_b200_peer_pack(const void *epj_aos_dev, int n)
     if (!pe.on) return fail(GPLUM_B200_ERR_STATE, "peer_pack without peer_open");
     if (n < 0 || n > (1 << pe.shift)) return fail(GPLUM_B200_ERR_ARG, "peer_pack n=%d exceeds the slab (%d)", n, 1 << pe.shift);
     CU(cudaSetDevice(g.device));
+    if (pe.pending) if (int r = launch_peer_pack(g.stream)) return r;       // two packs in a row: the first one goes out now
     pe.parity ^= 1;                  // peers may still be reading the slab of the previous step
     pe.epoch++;
-    // one launch: this rank's EPJ into its slab, its superparticles (the current j-set's, unless they are external),
-    // and the flag stores that tell every rank "packed" (kernels.cuh: peer_pack_kernel)
-    JSet &j = g.jset;
-    const int n_spj = (j.n_spj > 0 && !j.ext_spj) ? j.n_spj : 0;
-    const int nb_e = std::max(1, (n + PACK_BLOCK - 1) / PACK_BLOCK), nb_s = (n_spj + PACK_BLOCK - 1) / PACK_BLOCK;
-    peer_pack_kernel<<<nb_e + nb_s, PACK_BLOCK, 0, g.stream>>>((const EpjAos *)epj_aos_dev, n, (EpjPacked *)pe.slab[pe.parity],
-                                                                j.spj_records(), n_spj, (SpjPacked *)j.spj_packed.p, g.quad,
-                                                                (g.flags & GPLUM_B200_TRACE_AS_SHIPPED) ? 1 : 0, g.eps2, nb_e,
-                                                                (unsigned int *)pe.done.p, (void *const *)pe.table[0].p,
-                                                                ((size_t)1 << pe.shift) * sizeof(EpjPacked), pe.rank, pe.world, pe.epoch);
-    CU(cudaGetLastError());
-    g.launches++;
+    // the pack itself -- this rank's EPJ into its slab, its superparticles (the current j-set's, unless they are
+    // external) and the flag stores that tell every rank "packed" -- goes out with the next force launch
+    // (launch_pass): in that kernel's prologue when the pass is placed, else as peer_pack_kernel right before it
+    pe.pending = true; pe.pending_epj = epj_aos_dev; pe.pending_n = n;
     return 0;
 }
 
@@ -1273,6 +1318,7 @@ int gplum_b200_peer_wait(void)
     Peer &pe = g.peer;
     if (!pe.on) return fail(GPLUM_B200_ERR_STATE, "peer_wait without peer_open");
     CU(cudaSetDevice(g.device));
+    if (pe.pending) if (int r = launch_peer_pack(g.stream)) return r;
     const int *flags = reinterpret_cast<const int *>(static_cast<const char *>(pe.slab[0]) + ((size_t)1 << pe.shift) * sizeof(EpjPacked));
     peer_wait_kernel<<<1, 32, 0, g.stream>>>(flags, pe.world, pe.epoch);
     CU(cudaGetLastError());
@@ -1286,6 +1332,7 @@ int gplum_b200_peer_close(void)
     if (!pe.slab[0]) return 0;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
+    pe.pending = false;
     for (int b = 0; b < 2; b++) {
         for (int q = 0; q < pe.world; q++)
             if (pe.on && q != pe.rank && pe.mapped[b][q]) cudaIpcCloseMemHandle(pe.mapped[b][q]);

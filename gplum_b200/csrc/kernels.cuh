@@ -75,8 +75,15 @@ struct PassParams {
     // Placed passes (items.h: place_item): a pass whose warps are all resident at once has no dynamic balancing; its
     // warps claim their item by WHERE they run -- bin = SM x scheduler, k = how many warps of that bin came before.
     // place[0 .. place_bins) = the bins' claim counters, [place_bins] = items claimed so far, [place_bins + 1] = warps
-    // that have exited; all zero before and after a launch.  nullptr: warp s runs item s (or segment s).
+    // that have exited, [place_bins + 2] = CTAs at the fused pack's barrier; all zero before and after a launch.  nullptr: warp s runs item s (or segment s).
     int *place; int place_bins, place_rounds;
+    // Multi-GPU peer mode, fused pack (placed passes only: every CTA is resident, the launch is cooperative): before
+    // their first item the CTAs pack this rank's EPJ into its slab and its SPJ, meet at a grid barrier
+    // (place[place_bins + 2]), and the last one to arrive stores the epoch into every rank's flag array -- what
+    // peer_pack_kernel does as a launch of its own.  fp_slab == nullptr: off.
+    const EpjAos *fp_epj_in; int fp_n_epj; EpjPacked *fp_slab;
+    const void *fp_spj_in; int fp_n_spj; SpjPacked *fp_spj_out; int fp_quad, fp_trace;
+    void *const *fp_slab0_of; size_t fp_flag_off; int fp_rank;
     // placement trace (gplum_b200_debug_trace): per item {start, end (globaltimer ns), %smid | %warpid << 32, times run};
     // nullptr = off
     unsigned long long *trace;
@@ -186,18 +193,12 @@ __global__ void gather_epj_packed_kernel(const uint4 *__restrict__ src, const in
     dst[3 * (size_t)k + c] = src[3 * (size_t)idx[k] + c];
 }
 
-// quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
-// src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).  sm: PACK_BLOCK * 80 B.
-__device__ __forceinline__ void pack_spj_block(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
-                                               int quad, int trace_as_shipped, float eps2, int blk, unsigned char *sm)
+// one packed superparticle from its AoS record (quad: MySPJQuadrupole, else MySPJMonopole)
+__device__ __forceinline__ SpjPacked spj_pack(const void *rec, int quad, int trace_as_shipped, float eps2)
 {
-    if (quad) stage_records<sizeof(SpjQuadAos)>(in, n, sm, blk);
-    else stage_records<sizeof(SpjMonoAos)>(in, n, sm, blk);
-    const int i = blk * PACK_BLOCK + threadIdx.x;
-    if (i >= n) return;
     SpjPacked o;
     if (quad) {
-        const SpjQuadAos &a = reinterpret_cast<const SpjQuadAos *>(sm)[threadIdx.x];
+        const SpjQuadAos &a = *reinterpret_cast<const SpjQuadAos *>(rec);
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
         const float qxx = (float)a.quad[0], qyy = (float)a.quad[1], qzz = (float)a.quad[2];
         const float qxy = (float)a.quad[3], qzx = (float)a.quad[4], qyz = (float)a.quad[5];
@@ -209,12 +210,24 @@ __device__ __forceinline__ void pack_spj_block(const void *__restrict__ in, int 
         o.qxy = RS2_INV * __fmul_rn(3.0f, qxy); o.qyz = RS2_INV * __fmul_rn(3.0f, qyz); o.qzx = RS2_INV * __fmul_rn(3.0f, qzx);
         o.mtr = -RS2_INV * __fmul_rn(eps2, tr);
     } else {
-        const SpjMonoAos &a = reinterpret_cast<const SpjMonoAos *>(sm)[threadIdx.x];
+        const SpjMonoAos &a = *reinterpret_cast<const SpjMonoAos *>(rec);
         o.x = a.pos[0]; o.y = a.pos[1]; o.z = a.pos[2]; o.m = (float)a.mass;
         o.qxx = o.qyy = o.qzz = o.qxy = o.qyz = o.qzx = 0.0f; o.mtr = 0.0f;
     }
     o.pad0 = o.pad1 = 0.0f;
-    out[i] = o;
+    return o;
+}
+
+// quad: 1 = MySPJQuadrupole (80 B), 0 = MySPJMonopole (32 B).  trace_as_shipped reproduces
+// src/gravity_kernel.hpp:177 (F32 <- qxx+qyy+qxx summed in F64).  sm: PACK_BLOCK * 80 B.
+__device__ __forceinline__ void pack_spj_block(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
+                                               int quad, int trace_as_shipped, float eps2, int blk, unsigned char *sm)
+{
+    if (quad) stage_records<sizeof(SpjQuadAos)>(in, n, sm, blk);
+    else stage_records<sizeof(SpjMonoAos)>(in, n, sm, blk);
+    const int i = blk * PACK_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    out[i] = spj_pack(sm + (size_t)threadIdx.x * (quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos)), quad, trace_as_shipped, eps2);
 }
 
 __global__ void __launch_bounds__(PACK_BLOCK) pack_spj_kernel(const void *__restrict__ in, int n, SpjPacked *__restrict__ out,
@@ -707,6 +720,32 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
         if (slot >= p.n_seg) return;
         item = p.seg_off[slot]; item_end = p.seg_off[slot + 1];
     }
+    if (p.fp_slab) {
+        const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+        for (int i = tid; i < p.fp_n_epj; i += nthreads) {
+            const EpjAos &a = p.fp_epj_in[i];
+            p.fp_slab[i] = epj_pack(a.pos, a.mass, a.r_out, a.r_search, a.id_local, a.myrank);
+        }
+        const size_t ssz = p.fp_quad ? sizeof(SpjQuadAos) : sizeof(SpjMonoAos);
+        for (int i = tid; i < p.fp_n_spj; i += nthreads)
+            p.fp_spj_out[i] = spj_pack(static_cast<const char *>(p.fp_spj_in) + (size_t)i * ssz, p.fp_quad, p.fp_trace, p.eps2);
+        __threadfence();                                   // records visible in this GPU's L2, where the peers' loads arrive
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int *bar = p.place + p.place_bins + 2;
+            const int old = atomicAdd(bar, 1);
+            if (old == (int)gridDim.x - 1) {               // the slab is complete: tell every rank
+                __threadfence_system();
+                for (int q = 0; q < p.peer_world; q++) {
+                    int *f = reinterpret_cast<int *>(static_cast<char *>(p.fp_slab0_of[q]) + p.fp_flag_off) + p.fp_rank;
+                    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(p.peer_epoch) : "memory");
+                }
+            }
+            int seen;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory"); } while (seen < (int)gridDim.x);
+        }
+        __syncthreads();
+    }
     // placed pass: this warp's bin, and where its search for unclaimed entries stands (-1: own bin not yet tried)
     int my_bin = 0, scan = -1;
     bool first_claim = true;
@@ -808,7 +847,7 @@ __global__ void __launch_bounds__(WPB * 32, RMAX <= 2 ? GB_MINB2 : 4) force_pass
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old == (int)(gridDim.x * WPB) - 1) {
             __threadfence();
-            for (int k = lane; k < p.place_bins + 2; k += 32) p.place[k] = 0;
+            for (int k = lane; k < p.place_bins + 3; k += 32) p.place[k] = 0;
         }
     }
 }

@@ -22,15 +22,15 @@ def _ngpu():
         return 0
 
 
-def _workload():
+def _workload(n=20000, group=128):
     from gplum_b200 import disk, tree
-    d = disk.make_disk(20000, a_in=0.97, a_out=1.03, seed=5)
+    d = disk.make_disk(n, a_in=0.97, a_out=1.03, seed=5)
     ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
-    w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=128)
+    w, _ = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=group)
     return w
 
 
-def _worker(rank, world, port, out_dir, exchange):
+def _worker(rank, world, port, out_dir, exchange, n=20000, group=128):
     import torch
     import torch.distributed as dist
     from gplum_b200 import functors as F
@@ -39,7 +39,9 @@ def _worker(rank, world, port, out_dir, exchange):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    w = _workload()
+    w = _workload(n, group)
+    if exchange == "peer" and n > 20000:
+        os.environ["GPLUM_B200_FUSE_PACK"] = "1"       # read at init: the step's pack runs in the force launch's prologue
     F.init(rank)
     F.set_params(0.0, True, 0)
     stream = torch.cuda.Stream()
@@ -49,7 +51,10 @@ def _worker(rank, world, port, out_dir, exchange):
     check(lib().gplum_b200_set_stream(C.c_void_p(stream.cuda_stream)))
     mg = MultiGpuPass(w, world, rank, stream, exchange=exchange)
     for _ in range(3):                      # repeated steps reuse the buffers: results must not drift
+        F.counters(reset=True)
         mg.step()
+        launches = F.counters()[0]
+    np.save(os.path.join(out_dir, "l%d.npy" % rank), np.array([launches, mg.sh.walks_interior.n_walk + mg.sh.walks_boundary.n_walk]))
     f = mg.forces()
     np.save(os.path.join(out_dir, "f%d.npy" % rank), f)
     np.save(os.path.join(out_dir, "r%d.npy" % rank), np.array(list(mg.sh.epi_range) + [mg.n_boundary]))
@@ -76,6 +81,33 @@ def test_two_ranks_match_single_rank_oracle(exchange, tmp_path):
         got[e0:e1] = f; covered += e1 - e0; n_bnd += nb
     assert covered == len(w.epi) and n_bnd > 0
     synth.assert_force_close(got, want, 1e-4, "%d ranks, " % world + exchange)
+
+
+@pytest.mark.skipif(_ngpu() < WORLD, reason="needs >= %d GPUs" % WORLD)
+def test_peer_step_of_a_placed_pass_is_one_launch(tmp_path):
+    """A rank's share with at most one wave of work items (what 8 GPUs hold of the N = 1e6 disk) is a placed pass, and
+    with GPLUM_B200_FUSE_PACK=1 the step's pack in peer mode -- EPJ slab, superparticles, flags to the peers -- runs in
+    the prologue of that one cooperative launch (kernels.cuh: fp_*; off by default, it measured slower than the
+    separate pack launch).  Forces against the single-rank oracle; one kernel launch per step."""
+    import torch.multiprocessing as mp
+    import oracle_api as O
+    import synth
+    from gplum_b200 import structs as S
+    world = WORLD
+    n, group = 80000 * world, 512               # ~1900 items per rank
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(world, port, str(tmp_path), "peer", n, group), nprocs=world, join=True)
+    w = _workload(n, group)
+    want, _ = O.calc_walks(w, 0.0)
+    cond = O.calc_walks_abs(w, 0.0)
+    got = S.cleared_force(len(w.epi)); covered = 0
+    for r in range(world):
+        f = np.load(tmp_path / ("f%d.npy" % r)); e0, e1, nb = np.load(tmp_path / ("r%d.npy" % r))
+        got[e0:e1] = f; covered += e1 - e0
+        launches, n_walks = np.load(tmp_path / ("l%d.npy" % r))
+        assert launches == 1, (r, launches, n_walks)
+    assert covered == len(w.epi)
+    synth.assert_force_close(got, want, 1e-4, "%d ranks, peer, placed + fused pack" % world, cond=cond)
 
 
 def _soft_worker(rank, world, port, out_dir):
