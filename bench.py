@@ -272,7 +272,6 @@ def soft_step_leg(args, w, F, S, L, check):
         b, t = pinned_like(a); keep.append(t); return b
     raw = {k: pin(np.ascontiguousarray(v, dtype=np.float64)) for k, v in w.raw.items()}
     p_acc = pin(np.zeros((n, 4), dtype=np.float32)); p_idx = pin(np.zeros(n, dtype=np.int32)); p_nb = pin(np.zeros((n, 4), dtype=np.int32))
-    p_vel = pin(np.zeros((n, 3), dtype=np.float64))
     vel_all = np.ascontiguousarray(w.raw_vel, dtype=np.float64)
     n_listed = C.c_int(0)
     p_corr = pin(np.zeros(n, dtype=S.CORR))
@@ -288,9 +287,7 @@ def soft_step_leg(args, w, F, S, L, check):
                                         n_leaf_limit=8, n_group_limit=args.group)
         F.walks_run(repack=False)
         check(L.gplum_b200_tree_download_compact(vp(p_acc), vp(p_idx), vp(p_nb), n, C.byref(n_listed)))
-        m = n_listed.value
-        np.take(vel_all, p_idx[:m], axis=0, out=p_vel[:m])           # the caller's gather of the listed particles
-        check(L.gplum_b200_tree_set_motion_sparse(m, vp(p_idx), vp(p_vel), None))
+        check(L.gplum_b200_tree_set_motion_gather(n_listed.value, vp(p_idx), vp(vel_all), None))   # velocities of the listed particles
         F.correct_long_run(prm)
         check(L.gplum_b200_correct_long_download_compact(0, vp(p_corr), n, C.byref(n_corr), vp(p_ngb), ngb_cap,
                                                          C.byref(n_slots), C.byref(n_pairs)))
@@ -328,7 +325,7 @@ def soft_step_leg(args, w, F, S, L, check):
             "list_build_ms_host_builder": w.t_host_lists * 1e3,
             "force_pass_ms_on_gpu_lists": k_ms, "n_walks": int(sz[0]), "n_cells": int(sz[5]),
             "neighbour_pairs": int(n_pairs.value),
-            "api": "gplum_b200_tree_build_gpu + walks_run + tree_download_compact + tree_set_motion_sparse + correct_long_run + "
+            "api": "gplum_b200_tree_build_gpu + walks_run + tree_download_compact + tree_set_motion_gather + correct_long_run + "
                    "correct_long_download_compact, pinned host buffers (include/gravity_tree_b200.hpp: "
                    "calcForceAllAndWriteBack + correctForceLong)"}
 

@@ -184,6 +184,7 @@ struct Ctx {
     DevBuf tree_inv; bool tree_inv_valid = false;   // particle -> tree-order index of the last GPU build (built on demand)
     PinBuf tree_pin;            // pinned staging of pageable host inputs (upload_host)
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    PinBuf motion_pin;                                     // tree_set_motion_gather: staging of the listed particles' columns
     PinBuf h_small; cudaEvent_t ev_small = nullptr;        // a few pinned words for counts that come back mid-call
     cudaEvent_t ev_cols = nullptr, ev_cols0 = nullptr;     // tree_build_columns: columns on the device / columns free to overwrite
     bool stage_used[2] = {false, false};
@@ -646,11 +647,12 @@ __global__ void invert_order_kernel(int n, const int *__restrict__ idx, int *__r
     if (k < n) inv[idx[k]] = k;
 }
 // the same for m listed particles: index[t] = particle, columns [m][3]
-__global__ void set_motion_sparse_kernel(int m, const int *__restrict__ index, const int *__restrict__ inv, const double *__restrict__ vel,
+__global__ void set_motion_sparse_kernel(int m, int n, const int *__restrict__ index, const int *__restrict__ inv, const double *__restrict__ vel,
                                          const double *__restrict__ acc_d, EpjAos *__restrict__ epj)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
+    if ((unsigned int)index[t] >= (unsigned int)n) return;          // not a particle of this tree: ignored
     const int k = inv[index[t]];
     for (int d = 0; d < 3; d++) {
         epj[k].vel[d] = vel ? vel[3 * (size_t)t + d] : 0.0;
@@ -811,7 +813,7 @@ int gplum_b200_finalize(void)
     gplum_b200_peer_close();
     gplum_b200_peer_free();
     g.jset.release();
-    g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release(); g.h_small.release(); g.tree_motion.release(); g.tree_inv.release(); g.tree_inv_valid = false;
+    g.tree_in.release(); g.tree_raw.release(); g.tree_pin.release(); g.h_small.release(); g.motion_pin.release(); g.tree_motion.release(); g.tree_inv.release(); g.tree_inv_valid = false;
     for (DevBuf *b : {&g.st_epj, &g.st_time, &g.st_dt, &g.st_acc0, &g.st_iso, &g.st_star, &g.st_handled, &g.st_rec, &g.st_idx, &g.st_cnt}) b->release();
     g.st_pin.release(); g.st_n = 0;
     gbt::tree_release();
@@ -1937,11 +1939,39 @@ int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel
     if (int r = upload_host(d_index, index, M * 4, st)) return r;
     if (vel) if (int r = upload_host(d, vel, M * 24, st)) return r;
     if (acc_d) if (int r = upload_host(d + 3 * M, acc_d, M * 24, st)) return r;
-    set_motion_sparse_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, d_index, (const int *)g.tree_inv.p, vel ? d : nullptr, acc_d ? d + 3 * M : nullptr,
+    set_motion_sparse_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, n, d_index, (const int *)g.tree_inv.p, vel ? d : nullptr, acc_d ? d + 3 * M : nullptr,
                                                               (EpjAos *)g.jset.epj_aos.p);
     CU(cudaGetLastError());
     g.launches++;
     return 0;
+}
+
+// The same for a caller that holds whole columns: vel_all / acc_d_all are [n][3] in particle order; the library
+// gathers the m listed particles (OpenMP) into pinned staging and sends only those.
+int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all)
+{
+    if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_set_motion_gather: no GPU-built tree in the selected slot");
+    if (m < 0 || (m > 0 && !index)) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_gather: bad argument");
+    if (m == 0) return 0;
+    const int n = (int)g.slots[g.cur].n_epi;
+    if (m > n) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_gather: m = %d, the tree holds %d particles", m, n);
+    const size_t M = (size_t)m;
+    CU(cudaSetDevice(g.device));
+    CU(cudaStreamSynchronize(g.stream));                      // the staging buffer of the previous call is free
+    if (int r = g.motion_pin.reserve(M * 48)) return r;
+    double *hv = (double *)g.motion_pin.p, *ha = hv + 3 * M;
+    bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (long long t = 0; t < (long long)M; t++) {
+        const int i = index[t];
+        if (i < 0 || i >= n) { bad = true; continue; }
+        for (int d = 0; d < 3; d++) {
+            if (vel_all) hv[3 * t + d] = vel_all[3 * (size_t)i + d];
+            if (acc_d_all) ha[3 * t + d] = acc_d_all[3 * (size_t)i + d];
+        }
+    }
+    if (bad) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_gather: an index is outside [0, %d)", n);
+    return gplum_b200_tree_set_motion_sparse(m, index, vel_all ? hv : nullptr, acc_d_all ? ha : nullptr);
 }
 
 // The same results with half the bytes on the wire: {acc, phi} of every particle (16 B) and the neighbour words

@@ -257,6 +257,9 @@ int gplum_b200_tree_set_motion(int n, const double *vel, const double *acc_d);
  * the motion only of particles that occur in candidate pairs; gplum_b200_tree_download_compact lists exactly those
  * while the candidate capture (gplum_b200_soft_corr_enable) is on. */
 int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d);
+/* The same for a caller that holds whole columns (vel_all / acc_d_all are [n][3] in particle order): the library
+ * gathers the m listed particles with OpenMP into pinned staging and sends only those. */
+int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all);
 
 /* The same results with about half the bytes over PCIe.  accphi_out[4 i .. 4 i + 3] = {acc, phi} of particle i (in
  * the order the particles were handed in); the neighbour words of ForceGrav come back only for the *n_nb_out

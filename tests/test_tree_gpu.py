@@ -247,10 +247,16 @@ def test_epj_form_and_changeover_correction():
                                                       vp(np.ascontiguousarray(acc_d[listed]))))
         F.correct_long_run(prm)
         corr2, _, ngb2 = F.correct_long_download(n)
+        # the same from whole columns, gathered by the library
+        check(lib().gplum_b200_tree_set_motion(n, None, None))
+        check(lib().gplum_b200_tree_set_motion_gather(len(listed), vp(listed), vp(np.ascontiguousarray(d["vel"])), vp(acc_d)))
+        F.correct_long_run(prm)
+        corr3, _, ngb3 = F.correct_long_download(n)
     finally:
         F.soft_corr_enable(False)
     assert f_org[order].tobytes() == got_f.tobytes()
     assert_corr_equal(corr2, oc2, want_f, None, None, ngb2, on2)
+    assert corr3.tobytes() == corr2.tobytes() and ngb3.tobytes() == ngb2.tobytes()
 
 
 def test_full_size_properties():
