@@ -45,6 +45,8 @@ SYMBOLS = {
     "gplum_b200_synchronize": (_i, []),
     "gplum_b200_counters": (None, [C.POINTER(_ll), C.POINTER(_ll), C.POINTER(_ll), _i]),
     "gplum_b200_tree_build_gpu": (_i, [_i, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _vp]),
+    "gplum_b200_pinned_alloc": (_vp, [C.c_size_t]),
+    "gplum_b200_pinned_free": (None, [_vp]),
     "gplum_b200_tree_set_motion": (_i, [_i, _vp, _vp]),
     "gplum_b200_tree_set_motion_sparse": (_i, [_i, _vp, _vp, _vp]),
     "gplum_b200_tree_set_motion_gather": (_i, [_i, _vp, _vp, _vp]),

@@ -1974,6 +1974,24 @@ int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel
     return gplum_b200_tree_set_motion_sparse(m, index, vel_all ? hv : nullptr, acc_d_all ? ha : nullptr);
 }
 
+// Page-locked host memory for a caller's staging columns (include/gravity_tree_b200.hpp keeps its columns in it, so
+// that uploads and downloads go straight over PCIe instead of through the library's pinned chunks)
+void *gplum_b200_pinned_alloc(size_t bytes)
+{
+    if (ensure_init()) return nullptr;
+    void *p = nullptr;
+    if (cudaSetDevice(g.device) != cudaSuccess || cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        fail(GPLUM_B200_ERR_CUDA, "pinned_alloc of %zu bytes failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void gplum_b200_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 // The same results with half the bytes on the wire: {acc, phi} of every particle (16 B) and the neighbour words
 // {number, rank, id_max, id_min} only of the particles that have candidates (9 % of the N = 1e6 disk); the caller
 // fills in ForceGrav::clear()'s values (what gplum_b200_force_clear writes) for the rest.

@@ -261,6 +261,12 @@ int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel
  * gathers the m listed particles with OpenMP into pinned staging and sends only those. */
 int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all);
 
+/* Page-locked host memory for a caller's staging arrays (NULL on failure, gplum_b200_last_error has the reason):
+ * arrays handed to the tree_build_gpu / tree_download / tree_set_motion calls from such memory cross PCIe directly;
+ * pageable ones are staged through the library's own pinned chunks (correct, 1.4x slower end to end at N = 1e6). */
+void *gplum_b200_pinned_alloc(size_t bytes);
+void gplum_b200_pinned_free(void *p);
+
 /* The same results with about half the bytes over PCIe.  accphi_out[4 i .. 4 i + 3] = {acc, phi} of particle i (in
  * the order the particles were handed in); the neighbour words of ForceGrav come back only for the *n_nb_out
  * particles that have candidates (number > 0): nb_index_out[k] = particle, nb_out[4 k ..] = {number, rank, id_max,

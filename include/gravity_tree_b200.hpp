@@ -37,16 +37,38 @@ inline void tree_check(int rc, const char *what)
     }
 }
 
+// a growable array in page-locked host memory (gplum_b200_pinned_alloc): what crosses PCIe directly
+template <class T>
+class PinnedArray {
+    T *p_ = nullptr;
+    size_t cap_ = 0;
+public:
+    PinnedArray() = default;
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    ~PinnedArray() { gplum_b200_pinned_free(p_); }
+    void resize(size_t n)
+    {
+        if (n <= cap_) return;
+        gplum_b200_pinned_free(p_);
+        cap_ = n + n / 4 + 64;
+        p_ = static_cast<T *>(gplum_b200_pinned_alloc(cap_ * sizeof(T)));
+        if (!p_) tree_check(-1, "gplum_b200_pinned_alloc");
+    }
+    T *data() { return p_; }
+    T &operator[](size_t i) { return p_[i]; }
+};
+
 class TreeB200 {
 public:
     PS::F64 theta_ = 0.5;
     PS::S32 n_leaf_limit_ = 8, n_group_limit_ = 64;
-    std::vector<double> pos_, mass_, r_out_, r_search_, vel_, acc_d_;   // columns, particle k at slot k (FDPS's epj_org_ order)
-    std::vector<float> accphi_;
-    std::vector<int> nb_index_, nb_;
-    std::vector<gplum_b200_corr> corr_;
-    std::vector<gplum_b200_corr_init> init_;
-    std::vector<gplum_b200_ngb> ngb_;
+    PinnedArray<double> pos_, mass_, r_out_, r_search_, vel_, acc_d_;   // columns, particle k at slot k (FDPS's epj_org_ order)
+    PinnedArray<float> accphi_;
+    PinnedArray<int> nb_index_, nb_;
+    PinnedArray<gplum_b200_corr> corr_;
+    PinnedArray<gplum_b200_corr_init> init_;
+    PinnedArray<gplum_b200_ngb> ngb_;
     long long sizes_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     PS::S64 n_walk_ = 0, n_int_epep_ = 0, n_int_epsp_ = 0;
     PS::S32 n_listed_ = 0;                       // particles the last pass's download listed (candidate pairs)
@@ -146,7 +168,7 @@ public:
         corr_.resize(n);
         if (initial) init_.resize(n);
         const long long ngb_cap = 4LL * n + (1 << 20);
-        if ((long long)ngb_.size() < ngb_cap) ngb_.resize((size_t)ngb_cap);
+        ngb_.resize((size_t)ngb_cap);
         long long n_slots = 0, n_pairs = 0;
         tree_check(gplum_b200_correct_long_download(0, corr_.data(), initial ? init_.data() : nullptr, ngb_.data(), ngb_cap, &n_slots, &n_pairs),
                    "gplum_b200_correct_long_download");
