@@ -287,7 +287,7 @@ def soft_step_leg(args, w, F, S, L, check):
                                         n_leaf_limit=8, n_group_limit=args.group)
         F.walks_run(repack=False)
         check(L.gplum_b200_tree_download_compact(vp(p_acc), vp(p_idx), vp(p_nb), n, C.byref(n_listed)))
-        check(L.gplum_b200_tree_set_motion_gather(n_listed.value, vp(p_idx), vp(vel_all), None))   # velocities of the listed particles
+        check(L.gplum_b200_tree_set_motion_gather(n_listed.value, vp(p_idx), vp(vel_all), None, None))   # velocities of the listed particles
         F.correct_long_run(prm)
         check(L.gplum_b200_correct_long_download_compact(0, vp(p_corr), n, C.byref(n_corr), vp(p_ngb), ngb_cap,
                                                          C.byref(n_slots), C.byref(n_pairs)))

@@ -48,8 +48,8 @@ SYMBOLS = {
     "gplum_b200_pinned_alloc": (_vp, [C.c_size_t]),
     "gplum_b200_pinned_free": (None, [_vp]),
     "gplum_b200_tree_set_motion": (_i, [_i, _vp, _vp]),
-    "gplum_b200_tree_set_motion_sparse": (_i, [_i, _vp, _vp, _vp]),
-    "gplum_b200_tree_set_motion_gather": (_i, [_i, _vp, _vp, _vp]),
+    "gplum_b200_tree_set_motion_sparse": (_i, [_i, _vp, _vp, _vp, _vp]),
+    "gplum_b200_tree_set_motion_gather": (_i, [_i, _vp, _vp, _vp, _vp]),
     "gplum_b200_tree_download_compact": (_i, [_vp, _vp, _vp, _i, C.POINTER(_i)]),
     "gplum_b200_tree_build_gpu_vel": (_i, [_i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _i, _i, _vp]),
     "gplum_b200_tree_build_gpu_epj": (_i, [_i, _vp, _i, C.c_double, _i, _i, _vp]),

@@ -648,7 +648,7 @@ __global__ void invert_order_kernel(int n, const int *__restrict__ idx, int *__r
 }
 // the same for m listed particles: index[t] = particle, columns [m][3]
 __global__ void set_motion_sparse_kernel(int m, int n, const int *__restrict__ index, const int *__restrict__ inv, const double *__restrict__ vel,
-                                         const double *__restrict__ acc_d, EpjAos *__restrict__ epj)
+                                         const double *__restrict__ acc_d, const long long *__restrict__ id, EpjAos *__restrict__ epj)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
@@ -658,6 +658,7 @@ __global__ void set_motion_sparse_kernel(int m, int n, const int *__restrict__ i
         epj[k].vel[d] = vel ? vel[3 * (size_t)t + d] : 0.0;
         epj[k].acc_d[d] = acc_d ? acc_d[3 * (size_t)t + d] : 0.0;
     }
+    if (id) epj[k].id = id[t];
 }
 __global__ void set_motion_kernel(int n, const int *__restrict__ idx, const double *__restrict__ vel, const double *__restrict__ acc_d,
                                   EpjAos *__restrict__ epj)
@@ -1912,7 +1913,7 @@ int gplum_b200_tree_set_motion(int n, const double *vel, const double *acc_d)
 
 // The same for m listed particles (index[t] = particle, columns [m][3]): the post-pass reads the motion only of
 // particles that occur in candidate pairs -- the ones tree_download_compact lists while the capture is on.
-int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d)
+int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d, const long long *id)
 {
     if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_set_motion_sparse: no GPU-built tree in the selected slot");
     if (m < 0 || (m > 0 && !index)) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_sparse: bad argument");
@@ -1923,9 +1924,9 @@ int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel
     CU(cudaSetDevice(g.device));
     cudaStream_t st = g.stream;
     const size_t M = (size_t)m;
-    if (g.tree_motion.cap < M * 52 + 16) {
+    if (g.tree_motion.cap < M * 60 + 16) {
         CU(cudaStreamSynchronize(st));
-        if (int r = g.tree_motion.reserve(M * 52 + 16)) return r;
+        if (int r = g.tree_motion.reserve(M * 60 + 16)) return r;
     }
     if (!g.tree_inv_valid) {
         if (int r = g.tree_inv.reserve((size_t)n * 4)) return r;
@@ -1935,12 +1936,14 @@ int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel
         g.tree_inv_valid = true;
     }
     double *d = (double *)g.tree_motion.p;
-    int *d_index = (int *)(d + 6 * M);
+    long long *d_id = (long long *)(d + 6 * M);
+    int *d_index = (int *)(d + 7 * M);
     if (int r = upload_host(d_index, index, M * 4, st)) return r;
     if (vel) if (int r = upload_host(d, vel, M * 24, st)) return r;
     if (acc_d) if (int r = upload_host(d + 3 * M, acc_d, M * 24, st)) return r;
+    if (id) if (int r = upload_host(d_id, id, M * 8, st)) return r;
     set_motion_sparse_kernel<<<(m + 255) / 256, 256, 0, st>>>(m, n, d_index, (const int *)g.tree_inv.p, vel ? d : nullptr, acc_d ? d + 3 * M : nullptr,
-                                                              (EpjAos *)g.jset.epj_aos.p);
+                                                              id ? d_id : nullptr, (EpjAos *)g.jset.epj_aos.p);
     CU(cudaGetLastError());
     g.launches++;
     return 0;
@@ -1948,7 +1951,7 @@ int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel
 
 // The same for a caller that holds whole columns: vel_all / acc_d_all are [n][3] in particle order; the library
 // gathers the m listed particles (OpenMP) into pinned staging and sends only those.
-int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all)
+int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all, const long long *id_all)
 {
     if (!g.ready || !g.tree_built) return fail(GPLUM_B200_ERR_STATE, "tree_set_motion_gather: no GPU-built tree in the selected slot");
     if (m < 0 || (m > 0 && !index)) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_gather: bad argument");
@@ -1958,8 +1961,9 @@ int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel
     const size_t M = (size_t)m;
     CU(cudaSetDevice(g.device));
     CU(cudaStreamSynchronize(g.stream));                      // the staging buffer of the previous call is free
-    if (int r = g.motion_pin.reserve(M * 48)) return r;
+    if (int r = g.motion_pin.reserve(M * 56)) return r;
     double *hv = (double *)g.motion_pin.p, *ha = hv + 3 * M;
+    long long *hi = (long long *)(hv + 6 * M);
     bool bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : bad)
     for (long long t = 0; t < (long long)M; t++) {
@@ -1969,9 +1973,10 @@ int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel
             if (vel_all) hv[3 * t + d] = vel_all[3 * (size_t)i + d];
             if (acc_d_all) ha[3 * t + d] = acc_d_all[3 * (size_t)i + d];
         }
+        if (id_all) hi[t] = id_all[i];
     }
     if (bad) return fail(GPLUM_B200_ERR_ARG, "tree_set_motion_gather: an index is outside [0, %d)", n);
-    return gplum_b200_tree_set_motion_sparse(m, index, vel_all ? hv : nullptr, acc_d_all ? ha : nullptr);
+    return gplum_b200_tree_set_motion_sparse(m, index, vel_all ? hv : nullptr, acc_d_all ? ha : nullptr, id_all ? hi : nullptr);
 }
 
 // Page-locked host memory for a caller's staging columns (include/gravity_tree_b200.hpp keeps its columns in it, so

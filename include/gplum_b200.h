@@ -255,11 +255,15 @@ int gplum_b200_tree_download_original(void *force_out);
 int gplum_b200_tree_set_motion(int n, const double *vel, const double *acc_d);
 /* The same for m listed particles: index[t] = particle (as handed in), vel / acc_d are [m][3].  The post-pass reads
  * the motion only of particles that occur in candidate pairs; gplum_b200_tree_download_compact lists exactly those
- * while the candidate capture (gplum_b200_soft_corr_enable) is on. */
-int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d);
+ * while the candidate capture (gplum_b200_soft_corr_enable) is on.  id (optional, [m]): the particles' ids.  The tree
+ * built from columns numbers particles by index; the post-pass treats a candidate with the particle's own id as the
+ * particle itself (src/gravity_soft.h:105-108) -- after a merging collision the absorbed particle carries the id and the
+ * position of its target until MergeParticle removes it (src/collisionA.h:267-277), so a caller whose ids can repeat
+ * must pass them. */
+int gplum_b200_tree_set_motion_sparse(int m, const int *index, const double *vel, const double *acc_d, const long long *id);
 /* The same for a caller that holds whole columns (vel_all / acc_d_all are [n][3] in particle order): the library
  * gathers the m listed particles with OpenMP into pinned staging and sends only those. */
-int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all);
+int gplum_b200_tree_set_motion_gather(int m, const int *index, const double *vel_all, const double *acc_d_all, const long long *id_all);
 
 /* Page-locked host memory for a caller's staging arrays (NULL on failure, gplum_b200_last_error has the reason):
  * arrays handed to the tree_build_gpu / tree_download / tree_set_motion calls from such memory cross PCIe directly;

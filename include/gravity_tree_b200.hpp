@@ -64,6 +64,7 @@ public:
     PS::F64 theta_ = 0.5;
     PS::S32 n_leaf_limit_ = 8, n_group_limit_ = 64;
     PinnedArray<double> pos_, mass_, r_out_, r_search_, vel_, acc_d_;   // columns, particle k at slot k (FDPS's epj_org_ order)
+    PinnedArray<long long> id_;
     PinnedArray<float> accphi_;
     PinnedArray<int> nb_index_, nb_;
     PinnedArray<gplum_b200_corr> corr_;
@@ -155,15 +156,16 @@ public:
         // the fields only the post-pass reads (src/gravity_soft.h:76-242: velocity, direct acceleration), of the
         // particles that occur in candidate pairs -- the ones the pass's download listed
         const PS::S32 m = n_listed_;
-        vel_.resize(3 * (size_t)m); acc_d_.resize(3 * (size_t)m);
+        vel_.resize(3 * (size_t)m); acc_d_.resize(3 * (size_t)m); id_.resize((size_t)m);
 #pragma omp parallel for
         for (PS::S32 t = 0; t < m; t++) {
             EPJ_t e;
             e.copyFromFP(pp[nb_index_[t]]);
             vel_[3 * (size_t)t] = e.vel.x; vel_[3 * (size_t)t + 1] = e.vel.y; vel_[3 * (size_t)t + 2] = e.vel.z;
             acc_d_[3 * (size_t)t] = e.acc_d.x; acc_d_[3 * (size_t)t + 1] = e.acc_d.y; acc_d_[3 * (size_t)t + 2] = e.acc_d.z;
+            id_[t] = e.id;       // the absorbed particle of a merger carries its target's id and position (src/collisionA.h:267-277)
         }
-        tree_check(gplum_b200_tree_set_motion_sparse(m, nb_index_.data(), vel_.data(), acc_d_.data()), "gplum_b200_tree_set_motion_sparse");
+        tree_check(gplum_b200_tree_set_motion_sparse(m, nb_index_.data(), vel_.data(), acc_d_.data(), id_.data()), "gplum_b200_tree_set_motion_sparse");
         tree_check(gplum_b200_correct_long_run(0, &prm, initial ? 1 : 0), "gplum_b200_correct_long_run");
         corr_.resize(n);
         if (initial) init_.resize(n);
@@ -175,7 +177,7 @@ public:
         NList.initializeList(pp);
         n_ngb_tot = 0; n_with_ngb = 0;
         // records come in tree order; corr.id_local and ngb.id_local are particle indices (setIDLocalAndMyrank,
-        // src/func.h:135-143; the column form numbers the particles by index), the particles' ids are looked up here.
+        // src/func.h:135-143), ngb.id the ids sent above.
         // Serial: NeighborList::addNeighbor appends to shared lists (the reference guards them with omp critical).
         for (PS::S32 k = 0; k < n; k++) {
             const gplum_b200_corr &c = corr_[k];
@@ -191,7 +193,7 @@ public:
             pp[i].id_cluster = pp[i].id;
             for (PS::S32 q = 0; q < c.number; q++) {
                 const gplum_b200_ngb &b = ngb_[(size_t)c.ngb_off + q];
-                NList.addNeighbor(pp, i, pp[b.id_local].id, b.rank, b.id_local);      // number++, id_cluster = min, pair / exchange lists
+                NList.addNeighbor(pp, i, b.id, b.rank, b.id_local);      // number++, id_cluster = min, pair / exchange lists
             }
             if (pp[i].neighbor.number) {
                 NList.with_neighbor_list.push_back(i);

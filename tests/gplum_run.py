@@ -52,3 +52,26 @@ def run(binary, workdir, t_end="2^-2", dt_snap="2^-6", threads=4, env_extra=None
         raise RuntimeError("%s failed (%d):\n%s\n%s" % (binary, r.returncode, r.stdout[-2000:], r.stderr[-2000:]))
     e = np.loadtxt(os.path.join(workdir, "TEST", "energy.dat"), ndmin=2)
     return e, r.stdout
+
+
+def _big_stack():
+    # FDPS keeps per-thread work arrays on the stack; at N >= 1e5 the default 8 MB overflows (the reference itself)
+    import resource
+    resource.setrlimit(resource.RLIMIT_STACK, (resource.RLIM_INFINITY, resource.RLIM_INFINITY))
+
+
+def run_generated(binary, workdir, n, t_end="2^-2", dt_snap="2^-4", threads=8, env_extra=None, timeout=900, n_group_limit=64):
+    """The same program on a disk it generates itself (makeInit = 1, n particles, seed 0): energy.dat rows and stdout."""
+    os.makedirs(workdir, exist_ok=True)
+    p = dict(PARAMS, makeInit="1", n_init=str(n), n_group_limit=str(n_group_limit), t_end=t_end, dt_snap=dt_snap, dt_snap_tmp=dt_snap)
+    with open(os.path.join(workdir, "param.dat"), "w") as f:
+        for k, v in p.items():
+            f.write("%-16s= %s\n" % (k, v))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_STACKSIZE="1G")
+    env.update(env_extra or {})
+    r = subprocess.run([os.path.join(REF_DIR, binary), "-p", "param.dat"], cwd=workdir, env=env,
+                       capture_output=True, text=True, timeout=timeout, preexec_fn=_big_stack)
+    if r.returncode != 0:
+        raise RuntimeError("%s failed (%d):\n%s\n%s" % (binary, r.returncode, r.stdout[-2000:], r.stderr[-2000:]))
+    e = np.loadtxt(os.path.join(workdir, "TEST", "energy.dat"), ndmin=2)
+    return e, r.stdout

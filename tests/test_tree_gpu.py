@@ -199,10 +199,17 @@ def test_epj_form_and_changeover_correction():
     d = disk.make_disk(n, a_in=0.99, a_out=1.01, seed=5)
     ro, rs = disk.cutoff_radii(d["pos"], d["vel"], d["mass"])
     ro, rs = ro * 2.0, rs * 3.0
-    h, order = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=64)
     rng = np.random.default_rng(5)
     acc_d = rng.normal(size=(n, 3)) * 1e-3
     ids = rng.permutation(n).astype(np.int64) * 5 + 3
+    # three absorbed particles of mergers: same position and same id as their targets until MergeParticle removes
+    # them (src/collisionA.h:267-277, src/func.h:160-205); the post-pass must take them for the particle itself
+    for k in range(3):
+        a, b = 10 + k, n - 1 - k
+        for key in ("pos", "vel"):
+            d[key][b] = d[key][a]
+        ro[b], rs[b], acc_d[b], ids[b] = ro[a], rs[a], acc_d[a], ids[a]
+    h, order = tree.build_walks(d["pos"], d["mass"], ro, rs, n_group_limit=64)
     h.epj_all["vel"] = d["vel"][order]; h.epj_all["acc_d"] = acc_d[order]; h.epj_all["id"] = ids[order]
     # the unsorted records FDPS would hand over (epj_org_): particle k at slot k
     raw = np.zeros(n, dtype=S.EPJ)
@@ -227,12 +234,11 @@ def test_epj_form_and_changeover_correction():
     assert_corr_equal(corr, oc, want_f, None, None, ngb, on)
     assert corr["number"].sum() > 0
     # The same stage the way include/gravity_tree_b200.hpp drives it: columns up (48 B), compact forces down, then
-    # velocity and direct acceleration of the LISTED particles only, then the correction.  Ids are particle indices.
+    # velocity, direct acceleration and id of the LISTED particles only, then the correction.
     import ctypes as C
     from gplum_b200._lib import check, lib
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    h.epj_all["id"] = order
-    oc2, _, on2 = O.correct_long(h, prm, force=want_f)
+    oc2, on2 = oc, on
     F.soft_corr_enable(True)
     try:
         tree.build_walks_gpu(d["pos"], d["mass"], ro, rs, n_group_limit=64)
@@ -244,17 +250,23 @@ def test_epj_form_and_changeover_correction():
         assert cnt.value == n_listed and set(np.nonzero(f_org["number"] > 0)[0].tolist()) <= set(listed.tolist())
         assert len(listed) < n // 2                      # a fraction of the disk, not all of it
         check(lib().gplum_b200_tree_set_motion_sparse(len(listed), vp(listed), vp(np.ascontiguousarray(d["vel"][listed])),
-                                                      vp(np.ascontiguousarray(acc_d[listed]))))
+                                                      vp(np.ascontiguousarray(acc_d[listed])), vp(np.ascontiguousarray(ids[listed]))))
         F.correct_long_run(prm)
         corr2, _, ngb2 = F.correct_long_download(n)
         # the same from whole columns, gathered by the library
         check(lib().gplum_b200_tree_set_motion(n, None, None))
-        check(lib().gplum_b200_tree_set_motion_gather(len(listed), vp(listed), vp(np.ascontiguousarray(d["vel"])), vp(acc_d)))
+        check(lib().gplum_b200_tree_set_motion_gather(len(listed), vp(listed), vp(np.ascontiguousarray(d["vel"])), vp(acc_d), vp(ids)))
         F.correct_long_run(prm)
         corr3, _, ngb3 = F.correct_long_download(n)
     finally:
         F.soft_corr_enable(False)
     assert f_org[order].tobytes() == got_f.tobytes()
+    # particles that are not listed keep the tree's numbering (id = index): their id_cluster, which no pair touches,
+    # is their index; everything else -- and every field of the listed ones -- equals the oracle's with the real ids
+    unlisted = ~np.isin(order, listed)
+    assert (corr2["id_cluster"][unlisted] == order[unlisted]).all() and (corr2["number"][unlisted] == 0).all()
+    for c in (corr2, corr3):
+        c["id_cluster"][unlisted] = oc2["id_cluster"][unlisted]
     assert_corr_equal(corr2, oc2, want_f, None, None, ngb2, on2)
     assert corr3.tobytes() == corr2.tobytes() and ngb3.tobytes() == ngb2.tobytes()
 
