@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(128) corr_apply_kernel(SoftCorrArgs a)
         while (m >= 0 && seg[m] > v) { seg[m + 1] = seg[m]; m--; }
         seg[m + 1] = v;
     }
+    // An entry with the particle's own id is the absorbed twin of a merger (src/collisionA.h:267-277).  The reference
+    // adds massj * r_out_inv to phi for it only on its branch for at most two candidates, all on this rank
+    // (src/gravity_soft.h:295-317, 105-108); its tree-search branch skips such entries.
+    const bool twin_phi = n_cand <= 2 && ((const ForceAos *)a.force)[i].rank == 0;
     for (int k = 0; k < n_cand; k++) {
         const EpjAos q = epj[seg[k]];
         // ---- correctForceBetween2Particles{,Initial} (src/gravity_soft.h:76-153,155-242) ----
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(128) corr_apply_kernel(SoftCorrArgs a)
         const double r_out = std_max(self.r_out, q.r_out);
         const double r_out_inv = std_min(r_out_inv_i, 1. / q.r_out);
         const double r_search = std_max(self.r_search, q.r_search);
-        if (q.id == self.id) { phii += massj * r_out_inv; continue; }
+        if (q.id == self.id) { if (twin_phi) phii += massj * r_out_inv; continue; }
         const double dr[3] = {q.pos[0] - self.pos[0], q.pos[1] - self.pos[1], q.pos[2] - self.pos[2]};
         double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
         dr2 += eps2;

@@ -157,6 +157,19 @@ long long oracle_correct_long(int n_walk, const epi_t *epi_all, const int *epi_o
             const double r_out_inv_i = 1. / self->r_out;          /* particle.h:728 */
             phii += self->mass * r_out_inv_i;                     /* gravity_soft.h:281,293 */
             const long long off0 = n_ngb;
+            /* The reference has two branches (gravity_soft.h:295-317): with more than two candidates, or a candidate
+             * on another rank, it searches the tree and SKIPS every entry that carries the particle's own id -- the
+             * particle itself and, after a merger, the absorbed twin (collisionA.h:267-277); otherwise it walks
+             * neighbor.getId() and a twin reaches correctForceBetween2Particles, which adds massj * r_out_inv to phi
+             * for an entry with the particle's own id (gravity_soft.h:105-108). */
+            int n_all = 0, other_rank = 0;
+            for (int j = 0; j < n_epj[w]; j++) {
+                const epj_t *q = epj_all + ae[j];
+                if (q == self || !is_candidate(&e[i], q, o, (float)eps2)) continue;
+                n_all++;
+                if (q->myrank != self->myrank) other_rank = 1;
+            }
+            const int twin_phi = n_all <= 2 && !other_rank;
             for (int j = 0; j < n_epj[w]; j++) {
                 const epj_t *q = epj_all + ae[j];
                 if (q == self) continue;
@@ -167,7 +180,7 @@ long long oracle_correct_long(int n_walk, const epi_t *epi_all, const int *epi_o
                 const double r_out = STDMAX(self->r_out, q->r_out);
                 const double r_out_inv = STDMIN(r_out_inv_i, 1. / q->r_out);
                 const double r_search = STDMAX(self->r_search, q->r_search);
-                if (q->id == self->id) { phii += massj * r_out_inv; continue; }
+                if (q->id == self->id) { if (twin_phi) phii += massj * r_out_inv; continue; }
                 const double dr[3] = {q->pos[0] - self->pos[0], q->pos[1] - self->pos[1], q->pos[2] - self->pos[2]};
                 double dr2 = dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2];
                 dr2 += eps2;
